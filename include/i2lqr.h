@@ -1,0 +1,146 @@
+/*
+ * i2lqr.h -- C ABI of the B200-native i2LQR per-timestep control solve.
+ *
+ * The reference (HybridRobotics/ilqr-iterative-tasks) has no FFI: its boundary for this path is two plain
+ * Python call levels.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  Signatures carry plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; i2lqr_last_error() gives the message of
+ *     the last failure on the calling thread.  The Python shim turns a failure into RuntimeError, the one
+ *     exception the reference's caller handles (iterative_ilqr/utils/base.py:146-155).
+ *   - all floating point is IEEE double; matrices are row-major; arrays use the reference's shapes:
+ *     xvar (4, N+1), uvar (2, N) per candidate, laps (T, 4) as passed to add_trajectory.
+ *   - "host" pointers are ordinary host memory (pinned or not); "_device" entry points take device
+ *     pointers resident on the handle's GPU and a cudaStream_t passed as void*.
+ *   - there is no CPU fallback: every compute entry point fails if no sm_100-class GPU is usable.
+ */
+#ifndef I2LQR_H_
+#define I2LQR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2LQR_ABI_VERSION 1
+#define I2LQR_X_DIM 4 /* iterative_ilqr/utils/constants_kinetic_bicycle.py:2 */
+#define I2LQR_U_DIM 2
+#define I2LQR_OUTER_ITERS 3 /* calc_input breaks at iter == 2: iterative_ilqr/utils/base.py:472-478 */
+
+/* iLqrParam (iterative_ilqr/utils/base.py:242-302) + KineticBicycleParam (:15-20) + the constants the
+ * simulator hard-codes (Simulator.sim :708-726), flattened into one POD. */
+typedef struct i2lqr_params {
+  int32_t num_horizon;    /* N, iLqrParam.num_horizon (6) */
+  int32_t num_ss_points;  /* K, iLqrParam.num_ss_points (8) */
+  int32_t num_ss_iter;    /* L, iLqrParam.num_ss_iter (1) */
+  int32_t max_ilqr_iter;  /* 150 */
+  int32_t max_relax_iter; /* 55 */
+  int32_t max_sim_steps;  /* 121, Simulator.sim :709-710 */
+  int32_t reserved0;
+  int32_t reserved1;
+  double matrix_Q[16];         /* default 0 */
+  double matrix_R[4];          /* default 0 */
+  double matrix_Qterminal[16]; /* default 2*diag(1,1,20,0.02) */
+  double tuning_ctrl_q1, tuning_ctrl_q2; /* input barriers, 1, 1 */
+  double tuning_obs_q1, tuning_obs_q2;   /* obstacle barrier, 2.74, 2.74 */
+  double safety_margin;                  /* 0 */
+  double eps;                            /* 1e-2 */
+  double lamb, lamb_factor, max_lamb;    /* 1, 10, 1000 */
+  double a_max;     /* KineticBicycleParam.a_max (2.0) */
+  double delta_lim; /* round(KineticBicycleParam.delta_max, 2) = 1.57, iterative_ilqr/control/iterative_ilqr.py:37-39 */
+  double timestep;  /* dt */
+  double xtarget[4]; /* always zero in the reference: iterative_ilqr/utils/base.py:374 */
+  double goal_tol;   /* 0.8, Simulator.sim :715 */
+} i2lqr_params;
+
+/* Obstacle (iterative_ilqr/utils/base.py:23-35).  present == 0 stands for `obstacle is None`.
+ * moving_option: 0 = static (None in the reference), 1 = moving up, 2 = moving left. */
+typedef struct i2lqr_obstacle {
+  double x, y, width, height, spd;
+  int32_t moving_option;
+  int32_t present;
+} i2lqr_obstacle;
+
+typedef struct i2lqr_handle i2lqr_handle;
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+int i2lqr_abi_version(void);
+const char* i2lqr_last_error(void);
+/* Fills p with the reference's defaults (iLqrParam(), KineticBicycleParam()). */
+void i2lqr_default_params(i2lqr_params* p);
+
+/* One handle = one GPU, one stream, `n_episodes` independent controllers (safe sets), each keeping its
+ * most recent `num_ss_iter` laps of at most `lap_capacity` points.  Replaces iLqr.__init__
+ * (iterative_ilqr/utils/base.py:305-330). */
+int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capacity, i2lqr_handle** out);
+int i2lqr_destroy(i2lqr_handle* h);
+/* Re-reads the parameter block (scripts mutate iLqrParam between laps). */
+int i2lqr_set_params(i2lqr_handle* h, const i2lqr_params* p);
+
+/* ---- flat batch of independent candidate solves ----------------------------------------------------- */
+/* Replaces B calls of control.iterative_ilqr.ilqr (iterative_ilqr/control/iterative_ilqr.py:7-85), each
+ * set up as calc_input does (zero uvar, xvar[:,0] = x0: iterative_ilqr/utils/base.py:405-410).
+ *   x0, x_term : (B,4)   lamb_in : (B)   obs : n_obs entries, n_obs in {0 (no obstacle), 1 (shared), B}
+ *   uvar : (B,2,N)  xvar : (B,4,N+1)  lamb_out : (B)  iters : (B) executed iLQR iterations
+ * Any output pointer may be NULL.  Host-pointer form: H2D, solve, D2H inside the call. */
+int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
+                      const i2lqr_obstacle* obs, int64_t n_obs, double* uvar, double* xvar, double* lamb_out,
+                      int32_t* iters);
+/* Same, all pointers resident on the handle's device; runs on `cuda_stream` (NULL = the handle's stream)
+ * and does not synchronise. */
+int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term,
+                             const double* lamb_in, const i2lqr_obstacle* obs, int64_t n_obs, double* uvar,
+                             double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream);
+
+/* ---- safe set --------------------------------------------------------------------------------------- */
+/* Replaces iLqr.add_trajectory (iterative_ilqr/utils/base.py:343-369): x is (T,4); Qfun[j] = T-1-j is
+ * implied.  Requires T > num_horizon (as :348 does) and T <= lap_capacity. */
+int i2lqr_add_lap(i2lqr_handle* h, int episode, const double* x, int T);
+int i2lqr_num_laps(i2lqr_handle* h, int episode, int* n_laps);
+/* `ilqr.obstacle = ...` (iterative_ilqr/result/ilqr_test_add_moving_obstacle.py:73-75); NULL = None. */
+int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs);
+/* Replaces iLqr.select_close_ss (iterative_ilqr/utils/base.py:332-341): 1-norm K-nearest points of stored
+ * lap `lap` (absolute lap number, as the reference's `iter` argument) in ascending (distance, index) order.
+ * Writes min(K, T) indices and that count. */
+int i2lqr_select_knn(i2lqr_handle* h, int episode, int lap, const double* x0, int K, int64_t* idx_out,
+                     int32_t* n_out);
+
+/* ---- controller step -------------------------------------------------------------------------------- */
+/* Replaces the solve branch of iLqr.calc_input (iterative_ilqr/utils/base.py:384-478) for episodes
+ * 0..n_episodes-1: 3 outer iterations x active laps x K candidates (lambda carried along each lap's
+ * candidates), relax-cost ladder, lexicographic winner.
+ *   x : (E,4) current states          u : (E,2)   x_pred : (E,4,N+1)   u_pred : (E,2,N)
+ *   winner_lap : absolute lap number   winner_rank : position in the K-nearest order
+ *   winner_idx : index of the winning point in its lap   winner_cost : its relaxed cost
+ *   shrink : 1 when the winner is its lap's last point (horizon shrink / playback trigger, :472-478)
+ * Any output pointer may be NULL. */
+int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u, double* x_pred, double* u_pred,
+                     int32_t* winner_lap, int32_t* winner_rank, int64_t* winner_idx, double* winner_cost,
+                     int32_t* shrink);
+/* Per-candidate record of the last i2lqr_solve_step, shaped (E, 3, L, K): selected indices (-1 = unused
+ * slot), relaxed costs, lambda after each candidate and executed iLQR iterations. */
+int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, double* cand_cost, double* cand_lamb,
+                         int32_t* cand_iters);
+
+/* ---- batched closed-loop episodes (device-resident plant + controller) ------------------------------ */
+/* Replaces Simulator.sim + KineticBicycle.forward_one_step (iterative_ilqr/utils/base.py:157-213,708-726)
+ * and the lap post-processing of iterative_ilqr/tests/ilqr_test.py:56-60 for all episodes of the handle.
+ * x_init : (E,4) state every lap starts from; goal : (4) the initial lap's last row. */
+int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* goal);
+/* Runs one lap for every episode (at most max_sim_steps controller steps each); on return lap_len[e] is the
+ * number of steps taken and the finished lap (last row snapped to the goal) is already appended to the
+ * episode's safe set.  lap_x : optional (E, max_sim_steps+1, 4); lap_u : optional (E, max_sim_steps, 2). */
+int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, double* lap_u);
+
+/* ---- instrumentation -------------------------------------------------------------------------------- */
+/* Device time (CUDA events on the handle's stream) of the kernels of the last compute call, the number
+ * of kernels it launched, and the iLQR iterations it executed (for the roofline). */
+int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int64_t* ilqr_iterations,
+                     int64_t* solves);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2LQR_H_ */

@@ -1,0 +1,111 @@
+"""Pins the CPU oracle (oracle/i2lqr_oracle.c) to outputs of the unmodified Python reference.
+
+tests/golden/*.npz were minted by tests/golden/make_golden.py from /root/reference in the build container.
+Discrete results (selected indices, iteration counts, the lambda chain, winner, horizon-shrink flag) must
+be exact; states and inputs within 1e-9 relative (the oracle uses libm and a Jacobi 2x2 eigen form where
+the reference uses NumPy SIMD transcendentals and LAPACK dgeev).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("grp", H.FLAT_GROUPS)
+def test_ilqr_matches_reference(grp):
+    g = H.load("ilqr_flat.npz")
+    p, inp, obs, exp = H.flat_group(g, grp)
+    u, x, lamb, iters = oracle.ilqr_batch(p, inp["x0"], inp["x_term"], inp["lamb_in"], obs, nthreads=4)
+    assert np.array_equal(iters, exp["iters"])
+    assert np.array_equal(lamb, exp["lamb_out"])  # bit-exact: same /10, *10 sequence on doubles
+    assert H.rel_err(x, exp["xvar"]).max() <= H.RTOL
+    assert H.rel_err(u, exp["uvar"]).max() <= H.RTOL
+
+
+def test_single_call_equals_batch():
+    g = H.load("ilqr_flat.npz")
+    p, inp, obs, exp = H.flat_group(g, "n6")
+    from ilqr_iterative_tasks_b200 import _abi
+
+    for b in (0, 17, 255):
+        o = _abi.Obstacle(*[float(v) for v in g["n6/obs"][b]], int(g["n6/mode"][b]), 1)
+        u, x, lamb, it = oracle.ilqr(p, inp["x0"][b], inp["x_term"][b], float(inp["lamb_in"][b]), o)
+        assert it == exp["iters"][b] and lamb == exp["lamb_out"][b]
+        assert np.abs(x - exp["xvar"][b]).max() <= 1e-9 * max(1, np.abs(exp["xvar"][b]).max())
+
+
+def test_knn_matches_reference():
+    g = H.load("knn.npz")
+    for c in range(int(g["n_cases"])):
+        idx = oracle.select_knn(g["c%d/lap" % c], g["c%d/x0" % c], int(g["c%d/K" % c]))
+        assert np.array_equal(idx, g["c%d/idx" % c]), "case %d" % c
+
+
+def test_knn_edge_cases():
+    lap = np.array([[0.0, 0, 0, 0], [1.0, 0, 0, 0], [1.0, 0, 0, 0], [-1.0, 0, 0, 0]])
+    # K > T returns T indices; exact ties resolve by index
+    assert list(oracle.select_knn(lap, np.zeros(4), 8)) == [0, 1, 2, 3]
+    assert list(oracle.select_knn(lap, np.array([1.0, 0, 0, 0]), 2)) == [1, 2]
+    assert list(oracle.select_knn(lap[:1], np.ones(4), 3)) == [0]
+
+
+@pytest.mark.parametrize("name", H.STEP_SCENARIOS)
+def test_calc_input_matches_reference(name):
+    g = H.load("steps_%s.npz" % name)
+    p = H.step_params(g)
+    N = p.num_horizon
+    laps = [g["lap%d" % i] for i in range(int(g["n_laps"]))]
+    for si, s in enumerate(g["solve_ids"]):
+        out = oracle.calc_input(p, laps[: int(g["step/n_laps"][s])], g["step/x"][s], H.step_obstacle(g, s))
+        assert np.array_equal(out["sel_idx"], g["solve/sel_idx"][si]), "step %d" % s
+        assert np.array_equal(out["cand_iters"], g["solve/c_iters"][si]), "step %d" % s
+        assert np.array_equal(np.nan_to_num(out["cand_lamb"], nan=-1.0), np.nan_to_num(g["solve/c_lamb"][si], nan=-1.0))
+        assert bool(out["shrink"]) == (int(g["step/num_horizon_after"][s]) < N)
+        xr, ur = g["solve/x_pred"][si], g["solve/u_pred"][si]
+        assert np.abs(out["x_pred"] - xr).max() <= H.RTOL * max(1.0, np.abs(xr).max())
+        assert np.abs(out["u_pred"] - ur).max() <= H.RTOL * max(1.0, np.abs(ur).max())
+        assert np.abs(out["u"] - g["step/u"][s]).max() <= H.RTOL * 2
+
+
+def test_calc_input_synthetic_horizons():
+    g = H.load("step_synth.npz")
+    from ilqr_iterative_tasks_b200 import _abi
+
+    for N in g["horizons"]:
+        k = "n%d/" % N
+        p = _abi.default_params(num_horizon=int(N), num_ss_points=8, num_ss_iter=1)
+        o = _abi.Obstacle(*[float(v) for v in g[k + "obs"]], int(g[k + "mode"]), 1)
+        out = oracle.calc_input(p, [g[k + "lap"]], g[k + "x"], o)
+        assert np.array_equal(out["cand_iters"].ravel(), g[k + "c_iters"])
+        assert np.array_equal(out["cand_lamb"].ravel(), g[k + "c_lamb"])
+        assert np.abs(out["x_pred"] - g[k + "x_pred"]).max() <= H.RTOL * max(1.0, np.abs(g[k + "x_pred"]).max())
+        assert np.abs(out["u_pred"] - g[k + "u_pred"]).max() <= H.RTOL * 2
+
+
+def test_plant_step_pinned_by_reference_fixture():
+    """data/closed_loop_feasible.txt (the reference's only known-answer file, 6 decimals): the scripted
+    first lap regenerated through the oracle's kinetic_bicycle must reproduce it (stored as lap0)."""
+    g = H.load("steps_stock.npz")
+    lap0 = g["lap0"]
+    from ilqr_iterative_tasks_b200 import synth
+
+    xcl, ucl = synth.initial_lap()
+    assert xcl.shape == (121, 4) and np.abs(xcl - lap0).max() < 1e-12
+    x = np.zeros(4)
+    for i in range(120):
+        x = oracle.kinetic_bicycle(x, ucl[i], 1.0)
+        assert np.abs(x - lap0[i + 1]).max() < 1e-9
+    # the three duplicated final rows
+    assert np.array_equal(lap0[-1], lap0[-2]) and np.array_equal(lap0[-1], lap0[-3])
+
+
+def test_relax_cost_ladder():
+    from ilqr_iterative_tasks_b200 import _abi
+
+    p = _abi.default_params()
+    xt = np.zeros(4)
+    assert oracle.relax_cost(p, np.array([3.0, 4.0, 0, 0]), xt, 10, 0) == 10 + 6 + 100  # r=5 <= 80
+    assert oracle.relax_cost(p, np.array([3.0, 4.0, 0, 0]), xt, 10, 1) == 10 + 6 + 100  # r=5 <= 8
+    assert oracle.relax_cost(p, np.array([3.0, 4.0, 0, 0]), xt, 10, 2) == 10 + 6 + 700  # 5 <= 0.8*i -> i=7
+    assert oracle.relax_cost(p, np.array([300.0, 400.0, 0, 0]), xt, 10, 1) == np.inf  # 500 > 440

@@ -1,0 +1,392 @@
+"""bench.py -- candidate iLQR solves/s of the i2LQR control solve (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A "step" is one pass of the hot path over one batch of synthetic input: B independent candidate iLQR solves
+per GPU (BASELINE config 5: 2^20 flat candidates, horizon 6, per-candidate obstacle near the path, seed
+20260101 + rank).  Weak scaling: every rank owns its own B candidates, there is no data-path collective.
+
+One JSON line on rank 0:
+  value      whole-job solves/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e        the same metric through the C-ABI host call (pinned host buffers, H2D + D2H inside the timed region)
+  roofline   FP64 FMA-pipe: executed iLQR iterations (device counter) x (927 N + 177) algorithmic flops
+              / kernel time, against the DFMA peak measured on this GPU in the same run
+  cpu_baseline  the C oracle port (kind "port") on all host cores over a bounded sample of the same workload
+  latency    p50 / p90 of one full controller step (BASELINE config 2 shape: K=64, L=8) through the C ABI
+
+--impl reference times the CPU implementation alone (the reference is pure Python and cannot travel to the
+GPU box; the C oracle restates it -- kind "port"), same metric / config, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate iLQR solves/sec"
+UNIT = "solves/s"
+
+
+def flops_per_iteration(N):
+    return 927 * N + 177  # dense algorithmic FP64 flops per iLQR iteration
+
+
+def bytes_per_solve(N):
+    return 48 * N + 132  # algorithmic HBM bytes per candidate solve
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": float(max(power)) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def make_workload(B, N, rank):
+    from ilqr_iterative_tasks_b200 import _abi, synth
+
+    d = synth.flat_candidates(B, N, seed=synth.SEED + rank)
+    return d, _abi.obstacle_array(d["obs"], d["mode"])
+
+
+def cpu_arm(params, B, N, seconds_target=12.0):
+    """The oracle port on all host cores over a bounded sample of the workload."""
+    from oracle import oracle
+
+    cores = os.cpu_count() or 1
+    probe_n = min(B, 4096 * cores)
+    d, obs = make_workload(probe_n, N, 0)
+    t0 = time.perf_counter()
+    oracle.ilqr_batch(params, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=cores)
+    rate = probe_n / (time.perf_counter() - t0)
+    sample = int(min(B, max(probe_n, rate * seconds_target)))
+    d, obs = make_workload(sample, N, 0)
+    t0 = time.perf_counter()
+    _, _, _, iters = oracle.ilqr_batch(params, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return {
+        "value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "first %d of the %d candidates of rank 0's batch, C oracle port (oracle/i2lqr_oracle.c), %d host threads, %.1f s"
+        % (sample, B, cores, dt),
+        "iters_per_solve": float(iters.mean()), "seconds": dt,
+    }  # fmt: skip
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ilqr_iterative_tasks_b200 import _abi
+    from oracle import oracle
+
+    oracle.build()
+    params = _abi.default_params()
+    N, B = params.num_horizon, args.batch
+    cores = os.cpu_count() or 1
+    # each step = a bounded sample of the per-GPU batch so that warmup+steps end within minutes
+    d, obs = make_workload(min(B, 8192 * cores), N, 0)
+    t0 = time.perf_counter()
+    oracle.ilqr_batch(params, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=cores)
+    rate = d["x0"].shape[0] / (time.perf_counter() - t0)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    sample = int(min(B, max(4096, rate * min(budget, 15.0))))
+    d, obs = make_workload(sample, N, 0)
+    for _ in range(args.warmup):
+        oracle.ilqr_batch(params, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.ilqr_batch(params, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = "first %d of the %d candidates per step, C oracle port of the reference's NumPy path, %d host threads" % (sample, B, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(B, N, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python (29.7 solves/s/core measured in the build container, BASELINE.md) and cannot "
+                "travel to the GPU box; this arm times its C restatement (oracle/), which is ~500x faster per core",
+    }  # fmt: skip
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(B, N, gpus):
+    return {
+        "workload": "BASELINE config 5: flat batch of independent candidate iLQR solves, synthetic obstacles near the path",
+        "candidates_per_gpu": B, "global_candidates": B * gpus, "num_horizon": N, "state_dim": 4, "input_dim": 2,
+        "seed": 20260101, "parallelism": "candidates sharded by rank, no data-path collective",
+        "l2": "per-step working set (inputs 120 B + outputs 300 B per candidate) is %.0f MB > 126 MB L2" % (B * 420 / 1e6),
+    }  # fmt: skip
+
+
+def latency_probe(device, max_seconds=60.0):
+    """p50 / p90 latency of one controller step at the BASELINE config 2 shape (K=64, L=8) via the C ABI."""
+    from ilqr_iterative_tasks_b200 import _abi, engine, episodes, synth
+
+    p = _abi.default_params(num_ss_points=64, num_ss_iter=8)
+    lap0, _ = synth.initial_lap()
+    obs = _abi.obstacle_array(np.array([[31.0, -3.0, 8.0, 6.0, 0.0]]), [0])
+    eb = episodes.EpisodeBatch(p, np.zeros((1, 4)), obstacles=obs, initial_lap=lap0, device=device)
+    t0 = time.perf_counter()
+    laps = [lap0]
+    for _ in range(8):  # fill the safe set with 8 learned laps
+        n, lx, _ = eb.run_lap(want_traj=True)
+        laps.append(lx[0, : int(n[0]) + 1].copy())
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    eb.close()
+    eng = engine.Engine(p, device=device, n_episodes=1, lap_capacity=128)
+    for lp in laps[-8:]:
+        eng.add_lap(0, lp)
+    eng.set_obstacle(0, _abi.Obstacle(31.0, -3.0, 8.0, 6.0, 0.0, 0, 1))
+    states = laps[-1][:-6]  # the solve steps of the last lap
+    times, solves = [], []
+    for rep in range(3):
+        for x in states:
+            t1 = time.perf_counter()
+            eng.solve_step(x.reshape(1, 4))
+            times.append((time.perf_counter() - t1) * 1e3)
+            solves.append(eng.last_stats()["solves"])
+    eng.close()
+    times = np.array(times[len(states):])  # first pass = warm-up
+    return {
+        "p50_ms": float(np.percentile(times, 50)), "p90_ms": float(np.percentile(times, 90)), "steps_timed": int(times.size),
+        "solves_per_step": float(np.mean(solves)), "stored_laps": len(laps[-8:]),
+        "workload": "BASELINE config 2: one controller step (state in -> u, x_pred, u_pred on host), K=64, L=8, stock scenario",
+        "reference_cpu_p50_ms": 9100.0, "reference_note": "Python reference, 1 core, build container (BASELINE.md)",
+    }  # fmt: skip
+
+
+def run_ours(args):
+    import torch
+
+    from ilqr_iterative_tasks_b200 import _abi, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    params = _abi.default_params()
+    N, B = params.num_horizon, args.batch
+    d, obs = make_workload(B, N, rank)
+    eng = engine.Engine(params, device=local)
+    dev = torch.device("cuda", local)
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_x0, h_xt, h_lamb = pinned(d["x0"]), pinned(d["x_term"]), pinned(d["lamb_in"])
+    h_obs = torch.from_numpy(obs.view(np.uint8).reshape(B, -1).copy()).pin_memory()
+    h_out = {
+        "uvar": torch.empty((B, 2, N), dtype=torch.float64).pin_memory(),
+        "xvar": torch.empty((B, 4, N + 1), dtype=torch.float64).pin_memory(),
+        "lamb_out": torch.empty(B, dtype=torch.float64).pin_memory(),
+        "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
+    }
+    # ---- HBM-resident arm (value + roofline)
+    g_x0, g_xt, g_lamb, g_obs = h_x0.to(dev), h_xt.to(dev), h_lamb.to(dev), h_obs.to(dev)
+    g_u = torch.empty((B, 2, N), dtype=torch.float64, device=dev)
+    g_x = torch.empty((B, 4, N + 1), dtype=torch.float64, device=dev)
+    g_l = torch.empty(B, dtype=torch.float64, device=dev)
+    g_i = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+
+    def device_step():
+        eng.solve_batch_device(
+            B, g_x0.data_ptr(), g_xt.data_ptr(), g_lamb.data_ptr(), g_obs.data_ptr(), B,
+            g_u.data_ptr(), g_x.data_ptr(), g_l.data_ptr(), g_i.data_ptr(), stream=stream.cuda_stream,
+        )  # fmt: skip
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = engine.measure_fp64_peak(local, reps=5)
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    iters_total = 0
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for k in range(args.steps):
+            device_step()
+            ev[k + 1].record(stream)
+    stream.synchronize()
+    barrier()
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    st = eng.sync_stats(stream.cuda_stream)
+    iters_total = st["ilqr_iterations"]  # per step (identical every step)
+    kernel_ms = st["kernel_ms"]
+    launches_per_step = st["launches"]
+    # ---- end-to-end arm: host buffers through the C-ABI host call
+    out_np = {k: v.numpy() for k, v in h_out.items()}
+    x0_np, xt_np, lamb_np = h_x0.numpy(), h_xt.numpy(), h_lamb.numpy()
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.solve_batch(x0_np, xt_np, lamb_np, obs, out=out_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.solve_batch(x0_np, xt_np, lamb_np, obs, out=out_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    parity_ok = bool(np.array_equal(out_np["iters"], g_i.cpu().numpy()) and np.array_equal(out_np["xvar"], g_x.cpu().numpy()))
+    # ---- max over ranks
+    t = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms, float(iters_total)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        iters_all = float(tsum[3])
+    else:
+        e2e_ms = e2e_s * 1e3
+        iters_all = float(iters_total)
+    if rank == 0:
+        peaks = measured_peaks()
+        hbm_peak = peaks.get("hbm_gbs")
+        value = B * world * args.steps / (total_ms * 1e-3)
+        e2e_value = B * world * args.steps / (e2e_ms * 1e-3)
+        flops = iters_total * flops_per_iteration(N)
+        avg_ms = float(t[0]) / args.steps  # this rank's average launch duration over the timed region
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        h2d = B * (32 + 32 + 8 + 48)
+        d2h = B * (16 * N + 32 * (N + 1) + 8 + 4)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(B, N, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "api": "i2lqr_solve_batch (ctypes), pinned host buffers"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None, "kernel": "solve_kernel<false,true>", "kernel_ms": avg_ms, "last_launch_ms": kernel_ms,
+                "ilqr_iterations_per_step": int(iters_total), "iters_per_solve": iters_total / B,
+                "flops_per_iteration": flops_per_iteration(N),
+                "peak_source": "dependent-free DFMA micro-benchmark (i2lqr_measure_fp64_peak) on this GPU, same run; "
+                               "MEASURED_PEAKS.json has no FP64 figure (nominal B200 FP64 ~37 TFLOP/s)",
+                "hbm": {"achieved_gbs": B * bytes_per_solve(N) / (avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "bytes_per_solve": bytes_per_solve(N), "peak_source": "MEASURED_PEAKS.json"},
+            },
+            "step_ms": step_ms, "e2e_matches_device_arm": parity_ok,
+        }  # fmt: skip
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_arm(params, B, N)
+        if world == 1 and not args.no_latency:
+            try:
+                line["latency"] = latency_probe(local)
+            except Exception as err:  # the probe must never cost the headline number
+                line["latency"] = {"error": str(err)[:200]}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="candidates per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-latency", action="store_true", help="skip the controller-step latency probe")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

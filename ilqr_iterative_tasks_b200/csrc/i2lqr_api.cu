@@ -1,0 +1,815 @@
+// i2lqr_api.cu -- C ABI (include/i2lqr.h) over the sm_100a kernels.  No CPU fallback: every compute entry
+// point needs a CUDA device and fails with an error message otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/i2lqr.h"
+#include "kernels.cuh"
+
+using namespace i2lqr;
+
+static_assert(sizeof(DevObstacle) == sizeof(i2lqr_obstacle), "obstacle layouts must match");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t want) {
+    if (want <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) n = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+bool symmetric(const double* m, int n) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (m[i * n + j] != m[j * n + i]) return false;
+  return true;
+}
+
+void upper4(const double* m, double s, double* out) {
+  int t = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = i; j < 4; ++j) out[t++] = s * m[i * 4 + j];
+}
+
+}  // namespace
+
+struct i2lqr_handle {
+  int device = 0;
+  int n_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  i2lqr_params params;
+  KParams kp;
+  int E = 0, L = 0, K = 0, Tcap = 0;
+  // statistics of the last compute call
+  double last_ms = 0;
+  long long last_launches = 0, last_iters = 0, last_solves = 0;
+  // work-fetch counter + stats (3 x u64)
+  DevBuf<unsigned long long> ctl;
+  DevBuf<double> gscratch;
+  // flat batch staging
+  DevBuf<double> b_x0, b_xt, b_lamb, b_uvar, b_xvar, b_lamb_out, b_uinit;
+  DevBuf<DevObstacle> b_obs;
+  DevBuf<int> b_iters;
+  // safe sets
+  SafeSet set{};
+  std::vector<int> h_lap_len, h_lap_count;
+  std::vector<DevObstacle> h_obs;
+  DevBuf<DevObstacle> d_obs;
+  bool obs_dirty = true;
+  // controller-step workspace
+  DevBuf<double> s_x, s_u, s_xpred, s_upred, s_cand_x, s_cand_u, s_cand_cost, s_cand_lamb, s_wcost;
+  DevBuf<long long> s_sel_idx, s_widx, q_idx;
+  DevBuf<int> s_sel_cnt, s_cand_iters, s_wlap, s_wrank, s_shrink, q_cnt;
+  DevBuf<double> q_x0;
+  // batched episodes (K4)
+  bool ep_ready = false;
+  DevBuf<double> ep_upred, ep_goal, ep_lapx, ep_lapu;
+  DevBuf<int> ep_step, ep_done, ep_horizon, ep_pb, ep_active, ep_status, ep_nrun, ep_laplen;
+  DevBuf<DevObstacle> d_obs0;
+  int* h_nrun = nullptr;  // pinned
+};
+
+namespace {
+
+int make_kparams(const i2lqr_params& p, KParams* k) {
+  if (p.num_horizon < 2) return fail("num_horizon must be >= 2 (the reference's N==1 branch is unreachable, utils/base.py:438-450)");
+  if (p.num_ss_points < 1 || p.num_ss_iter < 1) return fail("num_ss_points and num_ss_iter must be >= 1");
+  if (!symmetric(p.matrix_Q, 4) || !symmetric(p.matrix_R, 2) || !symmetric(p.matrix_Qterminal, 4))
+    return fail("matrix_Q, matrix_R and matrix_Qterminal must be symmetric");
+  memset(k, 0, sizeof(*k));
+  k->N = p.num_horizon;
+  k->N_param = p.obstacle_horizon > 0 ? p.obstacle_horizon : p.num_horizon;
+  k->K = p.num_ss_points;
+  k->L = p.num_ss_iter;
+  k->max_iter = p.max_ilqr_iter;
+  k->max_relax = p.max_relax_iter;
+  k->dt = p.timestep;
+  k->dt2 = p.timestep * p.timestep;
+  k->a_max = p.a_max;
+  k->d_lim = p.delta_lim;
+  k->eps = p.eps;
+  k->lamb0 = p.lamb;
+  k->lamb_factor = p.lamb_factor;
+  k->max_lamb = p.max_lamb;
+  k->cq2 = p.tuning_ctrl_q2;
+  k->cg = p.tuning_ctrl_q1 * p.tuning_ctrl_q2;
+  k->ch = p.tuning_ctrl_q1 * (p.tuning_ctrl_q2 * p.tuning_ctrl_q2);
+  k->oq2 = p.tuning_obs_q2;
+  k->og = p.tuning_obs_q1 * p.tuning_obs_q2;
+  k->oh = p.tuning_obs_q1 * (p.tuning_obs_q2 * p.tuning_obs_q2);
+  k->one_margin = 1 + p.safety_margin;
+  for (int i = 0; i < 4; ++i) k->xtarget[i] = p.xtarget[i];
+  upper4(p.matrix_Qterminal, 1.0, k->Qf);
+  upper4(p.matrix_Qterminal, 2.0, k->Qf2);
+  upper4(p.matrix_Q, 1.0, k->Q);
+  upper4(p.matrix_Q, 2.0, k->Q2);
+  k->R[0] = p.matrix_R[0];
+  k->R[1] = p.matrix_R[1];
+  k->R[2] = p.matrix_R[3];
+  for (int i = 0; i < 3; ++i) k->R2[i] = 2.0 * k->R[i];
+  bool qr = false;
+  for (int i = 0; i < 16; ++i) qr = qr || p.matrix_Q[i] != 0.0;
+  for (int i = 0; i < 4; ++i) qr = qr || p.matrix_R[i] != 0.0;
+  k->has_qr = qr;
+  return 0;
+}
+
+constexpr int kThreads = 128;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+// Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
+int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st) {
+  const KParams& kp = h->kp;
+  const size_t per_block = (size_t)kThreads * scratch_doubles(kp.N) * sizeof(double);
+  const bool use_smem = per_block <= kSmemLimit;
+  CU(h->ctl.ensure(4));
+  CU(cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned long long), st));
+  w.counter = h->ctl.p;
+  w.stats = h->ctl.p + 1;
+  const long long lanes_needed = w.mode == 0 ? w.n_items : w.n_items;  // one lane per item
+  long long blocks_needed = (lanes_needed + kThreads - 1) / kThreads;
+  if (blocks_needed < 1) blocks_needed = 1;
+  auto kern = kp.has_qr ? (use_smem ? solve_kernel<true, true> : solve_kernel<true, false>)
+                        : (use_smem ? solve_kernel<false, true> : solve_kernel<false, false>);
+  int per_sm = 0;
+  size_t smem = use_smem ? per_block : 0;
+  if (use_smem) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
+  long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
+  if (!use_smem) {
+    const size_t need = (size_t)grid * kThreads * scratch_doubles(kp.N);
+    CU(h->gscratch.ensure(need));
+    w.gscratch = h->gscratch.p;
+    w.gstride = grid * kThreads;
+  }
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(kp, w);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  return 0;
+}
+
+int begin_stats(i2lqr_handle* h, cudaStream_t st) {
+  h->last_launches = 0;
+  CU(h->ctl.ensure(4));
+  CU(cudaMemsetAsync(h->ctl.p, 0, 4 * sizeof(unsigned long long), st));
+  CU(cudaEventRecord(h->ev0, st));
+  return 0;
+}
+
+// Waits for `st` and reads back the device-side counters and the ev0..ev1 kernel time.
+int finish_stats(i2lqr_handle* h, cudaStream_t st) {
+  unsigned long long s[2];
+  CU(cudaMemcpyAsync(s, h->ctl.p + 1, sizeof s, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  h->last_iters = (long long)s[0];
+  h->last_solves = (long long)s[1];
+  return 0;
+}
+
+int end_stats(i2lqr_handle* h, cudaStream_t st, bool sync) {
+  CU(cudaEventRecord(h->ev1, st));
+  return sync ? finish_stats(h, st) : 0;
+}
+
+int check_episode(i2lqr_handle* h, int e) {
+  if (!h) return fail("null handle");
+  if (e < 0 || e >= h->E) return fail("episode %d out of range [0,%d)", e, h->E);
+  return 0;
+}
+
+int sync_obstacles(i2lqr_handle* h) {
+  if (!h->obs_dirty) return 0;
+  CU(h->d_obs.ensure(h->E));
+  CU(cudaMemcpyAsync(h->d_obs.p, h->h_obs.data(), sizeof(DevObstacle) * h->E, cudaMemcpyHostToDevice, h->stream));
+  h->obs_dirty = false;
+  return 0;
+}
+
+int knn_smem_config(i2lqr_handle* h, int* warps, size_t* smem) {
+  const size_t per_warp = (size_t)h->Tcap * sizeof(double);
+  int w = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
+  if (w < 1) return fail("lap_capacity %d too large for the K-nearest kernel", h->Tcap);
+  *warps = w;
+  *smem = per_warp * w;
+  if (*smem > 48 * 1024) CU(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int i2lqr_abi_version(void) { return I2LQR_ABI_VERSION; }
+
+const char* i2lqr_last_error(void) { return g_err.c_str(); }
+
+void i2lqr_default_params(i2lqr_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->num_horizon = 6;
+  p->num_ss_points = 8;
+  p->num_ss_iter = 1;
+  p->max_ilqr_iter = 150;
+  p->max_relax_iter = 55;
+  p->max_sim_steps = 121;
+  p->matrix_Qterminal[0] = 2.0;
+  p->matrix_Qterminal[5] = 2.0;
+  p->matrix_Qterminal[10] = 40.0;
+  p->matrix_Qterminal[15] = 0.04;
+  p->tuning_ctrl_q1 = p->tuning_ctrl_q2 = 1.0;
+  p->tuning_obs_q1 = p->tuning_obs_q2 = 2.74;
+  p->eps = 1e-2;
+  p->lamb = 1.0;
+  p->lamb_factor = 10.0;
+  p->max_lamb = 1000.0;
+  p->a_max = 2.0;
+  p->delta_lim = 1.57;
+  p->timestep = 1.0;
+  p->goal_tol = 0.8;
+}
+
+int i2lqr_set_params(i2lqr_handle* h, const i2lqr_params* p) {
+  if (!h || !p) return fail("null argument");
+  if (h->E > 0 && (p->num_ss_iter != h->L)) return fail("num_ss_iter cannot change after create (safe-set ring size)");
+  KParams kp;
+  if (make_kparams(*p, &kp)) return 1;
+  h->params = *p;
+  h->kp = kp;
+  h->K = p->num_ss_points;
+  return 0;
+}
+
+int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capacity, i2lqr_handle** out) {
+  if (!p || !out) return fail("null argument");
+  if (n_episodes < 0 || lap_capacity < 0) return fail("negative size");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail("device %d out of range (have %d)", device, count);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail("device %d is sm_%d%d; this build targets sm_100a (B200)", device, prop.major, prop.minor);
+  i2lqr_handle* h = new i2lqr_handle();
+  h->device = device;
+  h->n_sms = prop.multiProcessorCount;
+  if (make_kparams(*p, &h->kp)) {
+    delete h;
+    return 1;
+  }
+  h->params = *p;
+  h->E = n_episodes;
+  h->L = p->num_ss_iter;
+  h->K = p->num_ss_points;
+  h->Tcap = lap_capacity;
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(h->ctl.ensure(4));
+  if (n_episodes > 0) {
+    if (lap_capacity <= p->num_horizon) return fail("lap_capacity must exceed num_horizon");
+    const size_t ss_n = (size_t)h->E * h->L * 4 * h->Tcap;
+    CU(cudaMalloc(&h->set.ss, ss_n * sizeof(double)));
+    CU(cudaMemset(h->set.ss, 0, ss_n * sizeof(double)));
+    CU(cudaMalloc(&h->set.lap_len, sizeof(int) * h->E * h->L));
+    CU(cudaMalloc(&h->set.lap_count, sizeof(int) * h->E));
+    CU(cudaMemset(h->set.lap_len, 0, sizeof(int) * h->E * h->L));
+    CU(cudaMemset(h->set.lap_count, 0, sizeof(int) * h->E));
+    h->set.L = h->L;
+    h->set.Tcap = h->Tcap;
+    h->h_lap_len.assign((size_t)h->E * h->L, 0);
+    h->h_lap_count.assign(h->E, 0);
+    DevObstacle none{};
+    h->h_obs.assign(h->E, none);
+  }
+  *out = h;
+  return 0;
+}
+
+int i2lqr_destroy(i2lqr_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->gscratch, &h->s_x, &h->s_u,
+                  &h->s_xpred, &h->s_upred, &h->s_cand_x, &h->s_cand_u, &h->s_cand_cost, &h->s_cand_lamb, &h->s_wcost,
+                  &h->q_x0})
+    b->release();
+  for (auto* b : {&h->s_sel_idx, &h->s_widx, &h->q_idx}) b->release();
+  for (auto* b : {&h->b_iters, &h->s_sel_cnt, &h->s_cand_iters, &h->s_wlap, &h->s_wrank, &h->s_shrink, &h->q_cnt}) b->release();
+  for (auto* b : {&h->ep_upred, &h->ep_goal, &h->ep_lapx, &h->ep_lapu}) b->release();
+  for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen}) b->release();
+  h->d_obs0.release();
+  if (h->h_nrun) cudaFreeHost(h->h_nrun);
+  h->ctl.release();
+  h->b_obs.release();
+  h->d_obs.release();
+  if (h->set.ss) cudaFree(h->set.ss);
+  if (h->set.lap_len) cudaFree(h->set.lap_len);
+  if (h->set.lap_count) cudaFree(h->set.lap_count);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ flat batch
+int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
+                             const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar,
+                             double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("negative batch");
+  if (B > 0 && (!x0 || !x_term)) return fail("x0 and x_term are required");
+  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
+  if (n_obs != 0 && !obs) return fail("obs is null but n_obs != 0");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  if (begin_stats(h, st)) return 1;
+  if (B > 0) {
+    Work w{};
+    w.mode = 0;
+    w.n_items = B;
+    w.x0 = x0;
+    w.x_term = x_term;
+    w.lamb_in = lamb_in;
+    w.obs = reinterpret_cast<const DevObstacle*>(obs);
+    w.n_obs = n_obs;
+    w.u_init = uvar_init;
+    w.uvar = uvar;
+    w.xvar = xvar;
+    w.lamb_out = lamb_out;
+    w.iters = iters;
+    if (launch_solve(h, w, st)) return 1;
+  }
+  return end_stats(h, st, false);
+}
+
+int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
+                      const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
+                      double* lamb_out, int32_t* iters) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("negative batch");
+  if (B > 0 && (!x0 || !x_term)) return fail("x0 and x_term are required");
+  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
+  if (n_obs != 0 && !obs) return fail("obs is null but n_obs != 0");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int N = h->kp.N;
+  const size_t nb = (size_t)B;
+  if (B > 0) {
+    CU(h->b_x0.ensure(nb * 4));
+    CU(h->b_xt.ensure(nb * 4));
+    CU(cudaMemcpyAsync(h->b_x0.p, x0, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->b_xt.p, x_term, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (lamb_in) {
+      CU(h->b_lamb.ensure(nb));
+      CU(cudaMemcpyAsync(h->b_lamb.p, lamb_in, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (n_obs) {
+      CU(h->b_obs.ensure((size_t)n_obs));
+      CU(cudaMemcpyAsync(h->b_obs.p, obs, (size_t)n_obs * sizeof(DevObstacle), cudaMemcpyHostToDevice, st));
+    }
+    if (uvar_init) {
+      CU(h->b_uinit.ensure(nb * 2 * N));
+      CU(cudaMemcpyAsync(h->b_uinit.p, uvar_init, nb * 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (uvar) CU(h->b_uvar.ensure(nb * 2 * N));
+    if (xvar) CU(h->b_xvar.ensure(nb * 4 * (N + 1)));
+    if (lamb_out) CU(h->b_lamb_out.ensure(nb));
+    if (iters) CU(h->b_iters.ensure(nb));
+  }
+  if (i2lqr_solve_batch_device(h, B, h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr,
+                               reinterpret_cast<const i2lqr_obstacle*>(h->b_obs.p), n_obs,
+                               uvar_init ? h->b_uinit.p : nullptr, uvar ? h->b_uvar.p : nullptr,
+                               xvar ? h->b_xvar.p : nullptr, lamb_out ? h->b_lamb_out.p : nullptr,
+                               iters ? h->b_iters.p : nullptr, st))
+    return 1;
+  if (B > 0) {
+    if (uvar) CU(cudaMemcpyAsync(uvar, h->b_uvar.p, nb * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (xvar) CU(cudaMemcpyAsync(xvar, h->b_xvar.p, nb * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lamb_out) CU(cudaMemcpyAsync(lamb_out, h->b_lamb_out.p, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (iters) CU(cudaMemcpyAsync(iters, h->b_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  return finish_stats(h, st);
+}
+
+// -------------------------------------------------------------------------------------------- safe set
+int i2lqr_add_lap(i2lqr_handle* h, int episode, const double* x, int T) {
+  if (check_episode(h, episode)) return 1;
+  if (!x) return fail("null lap");
+  if (T <= h->kp.N) return fail("lap of %d points is not longer than the horizon %d (utils/base.py:348)", T, h->kp.N);
+  if (T > h->Tcap) return fail("lap of %d points exceeds lap_capacity %d", T, h->Tcap);
+  CU(cudaSetDevice(h->device));
+  const int count = h->h_lap_count[episode];
+  const int slot = count % h->L;
+  std::vector<double> soa((size_t)4 * h->Tcap, 0.0);
+  for (int j = 0; j < T; ++j)
+    for (int i = 0; i < 4; ++i) soa[(size_t)i * h->Tcap + j] = x[(size_t)j * 4 + i];
+  double* dst = h->set.ss + ((size_t)episode * h->L + slot) * 4 * (size_t)h->Tcap;
+  CU(cudaMemcpyAsync(dst, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->h_lap_len[(size_t)episode * h->L + slot] = T;
+  h->h_lap_count[episode] = count + 1;
+  CU(cudaMemcpyAsync(h->set.lap_len + (size_t)episode * h->L + slot, &h->h_lap_len[(size_t)episode * h->L + slot],
+                     sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->set.lap_count + episode, &h->h_lap_count[episode], sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // soa is a stack-lifetime staging buffer
+  return 0;
+}
+
+int i2lqr_num_laps(i2lqr_handle* h, int episode, int* n_laps) {
+  if (check_episode(h, episode)) return 1;
+  if (n_laps) *n_laps = h->h_lap_count[episode];
+  return 0;
+}
+
+int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs) {
+  if (check_episode(h, episode)) return 1;
+  DevObstacle o{};
+  if (obs) {
+    memcpy(&o, obs, sizeof o);
+    if (o.present && (o.moving_option < 0 || o.moving_option > 2)) return fail("moving_option must be 0, 1 or 2");
+    if (o.present && o.moving_option == 0 && o.spd != 0.0)
+      return fail("obstacle with spd != 0 needs moving_option 1 or 2 (control/ilqr_helper.py:34-43)");
+  }
+  h->h_obs[episode] = o;
+  h->obs_dirty = true;
+  return 0;
+}
+
+int i2lqr_select_knn(i2lqr_handle* h, int episode, int lap, const double* x0, int K, int64_t* idx_out, int32_t* n_out) {
+  if (check_episode(h, episode)) return 1;
+  if (!x0 || !idx_out) return fail("null argument");
+  const int count = h->h_lap_count[episode];
+  if (lap < 0 || lap >= count || lap < count - h->L) return fail("lap %d is not stored (have laps %d..%d)", lap, std::max(0, count - h->L), count - 1);
+  if (K < 1) return fail("K must be >= 1");
+  CU(cudaSetDevice(h->device));
+  CU(h->q_x0.ensure(4));
+  CU(h->q_idx.ensure((size_t)K));
+  CU(h->q_cnt.ensure(1));
+  CU(cudaMemcpyAsync(h->q_x0.p, x0, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  KnnArgs a{};
+  a.set = h->set;
+  a.K = K;
+  a.q_episode = episode;
+  a.q_lap = lap;
+  a.q_x0 = h->q_x0.p;
+  a.q_idx = h->q_idx.p;
+  a.q_cnt = h->q_cnt.p;
+  int warps;
+  size_t smem;
+  if (knn_smem_config(h, &warps, &smem)) return 1;
+  if (begin_stats(h, h->stream)) return 1;
+  knn_kernel<<<1, 32 * warps, smem, h->stream>>>(a);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, h->q_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (end_stats(h, h->stream, true)) return 1;
+  static_assert(sizeof(long long) == sizeof(int64_t), "");
+  CU(cudaMemcpy(idx_out, h->q_idx.p, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+  if (n_out) *n_out = n;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- controller step
+namespace {
+int ensure_step_workspace(i2lqr_handle* h) {
+  const size_t E = h->E, L = h->L, K = h->K, N = h->kp.N;
+  CU(h->s_x.ensure(E * 4));
+  CU(h->s_u.ensure(E * 2));
+  CU(h->s_xpred.ensure(E * 4 * (N + 1)));
+  CU(h->s_upred.ensure(E * 2 * N));
+  CU(h->s_cand_x.ensure(E * L * K * 4 * (N + 1)));
+  CU(h->s_cand_u.ensure(E * L * K * 2 * N));
+  CU(h->s_cand_cost.ensure(E * kOuter * L * K));
+  CU(h->s_cand_lamb.ensure(E * kOuter * L * K));
+  CU(h->s_cand_iters.ensure(E * kOuter * L * K));
+  CU(h->s_sel_idx.ensure(E * kOuter * L * K));
+  CU(h->s_sel_cnt.ensure(E * L));
+  CU(h->s_wlap.ensure(E));
+  CU(h->s_wrank.ensure(E));
+  CU(h->s_widx.ensure(E));
+  CU(h->s_wcost.ensure(E));
+  CU(h->s_shrink.ensure(E));
+  return 0;
+}
+
+// The three outer iterations of calc_input on device-resident state x (E,4); results stay on the device.
+int run_step(i2lqr_handle* h, int n_episodes, const int* d_active, cudaStream_t st) {
+  int warps;
+  size_t smem;
+  if (knn_smem_config(h, &warps, &smem)) return 1;
+  if (sync_obstacles(h)) return 1;
+  const size_t E = h->E, L = h->L, K = h->K;
+  // unused trace slots read as "no candidate"
+  CU(cudaMemsetAsync(h->s_sel_idx.p, 0xff, sizeof(long long) * E * kOuter * L * K, st));
+  CU(cudaMemsetAsync(h->s_cand_cost.p, 0xff, sizeof(double) * E * kOuter * L * K, st));
+  CU(cudaMemsetAsync(h->s_cand_lamb.p, 0xff, sizeof(double) * E * kOuter * L * K, st));
+  CU(cudaMemsetAsync(h->s_cand_iters.p, 0xff, sizeof(int) * E * kOuter * L * K, st));
+  double scale = 1.0;
+  for (int it = 0; it < kOuter; ++it) {
+    KnnArgs ka{};
+    ka.set = h->set;
+    ka.K = h->K;
+    ka.it = it;
+    ka.n_episodes = n_episodes;
+    ka.x = h->s_x.p;
+    ka.x_pred = h->s_xpred.p;
+    ka.N = h->kp.N;
+    ka.active = d_active;
+    ka.sel_idx = h->s_sel_idx.p;
+    ka.sel_cnt = h->s_sel_cnt.p;
+    const long long n_warps = (long long)n_episodes * h->L;
+    knn_kernel<<<(unsigned)((n_warps + warps - 1) / warps), 32 * warps, smem, st>>>(ka);
+    CU(cudaGetLastError());
+    h->last_launches += 1;
+
+    Work w{};
+    w.mode = 1;
+    w.n_items = n_warps;
+    w.it = it;
+    w.scale = scale;
+    w.set = h->set;
+    w.x = h->s_x.p;
+    w.ep_obs = h->d_obs.p;
+    w.active = d_active;
+    w.sel_idx = h->s_sel_idx.p;
+    w.sel_cnt = h->s_sel_cnt.p;
+    w.cand_x = h->s_cand_x.p;
+    w.cand_u = h->s_cand_u.p;
+    w.cand_cost = h->s_cand_cost.p;
+    w.cand_lamb = h->s_cand_lamb.p;
+    w.cand_iters = h->s_cand_iters.p;
+    if (launch_solve(h, w, st)) return 1;
+
+    WinnerArgs wa{};
+    wa.n_episodes = n_episodes;
+    wa.it = it;
+    wa.L = h->L;
+    wa.K = h->K;
+    wa.N = h->kp.N;
+    wa.lap_count = h->set.lap_count;
+    wa.lap_len = h->set.lap_len;
+    wa.active = d_active;
+    wa.sel_cnt = h->s_sel_cnt.p;
+    wa.sel_idx = h->s_sel_idx.p;
+    wa.cand_cost = h->s_cand_cost.p;
+    wa.cand_x = h->s_cand_x.p;
+    wa.cand_u = h->s_cand_u.p;
+    wa.u = h->s_u.p;
+    wa.x_pred = h->s_xpred.p;
+    wa.u_pred = h->s_upred.p;
+    wa.winner_lap = h->s_wlap.p;
+    wa.winner_rank = h->s_wrank.p;
+    wa.winner_idx = h->s_widx.p;
+    wa.winner_cost = h->s_wcost.p;
+    wa.shrink = h->s_shrink.p;
+    const int wthreads = 128;
+    winner_kernel<<<(unsigned)(((long long)n_episodes * 32 + wthreads - 1) / wthreads), wthreads, 0, st>>>(wa);
+    CU(cudaGetLastError());
+    h->last_launches += 1;
+    scale *= 10.0;
+  }
+  return 0;
+}
+}  // namespace
+
+int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u, double* x_pred, double* u_pred,
+                     int32_t* winner_lap, int32_t* winner_rank, int64_t* winner_idx, double* winner_cost,
+                     int32_t* shrink) {
+  if (!h) return fail("null handle");
+  if (n_episodes < 1 || n_episodes > h->E) return fail("n_episodes %d out of range [1,%d]", n_episodes, h->E);
+  if (!x) return fail("null state");
+  for (int e = 0; e < n_episodes; ++e)
+    if (h->h_lap_count[e] == 0) return fail("episode %d has no stored lap (call add_trajectory first)", e);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (ensure_step_workspace(h)) return 1;
+  const size_t E = n_episodes, N = h->kp.N;
+  CU(cudaMemcpyAsync(h->s_x.p, x, E * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (begin_stats(h, st)) return 1;
+  if (run_step(h, n_episodes, nullptr, st)) return 1;
+  CU(cudaEventRecord(h->ev1, st));
+  if (u) CU(cudaMemcpyAsync(u, h->s_u.p, E * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (x_pred) CU(cudaMemcpyAsync(x_pred, h->s_xpred.p, E * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (u_pred) CU(cudaMemcpyAsync(u_pred, h->s_upred.p, E * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (winner_lap) CU(cudaMemcpyAsync(winner_lap, h->s_wlap.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (winner_rank) CU(cudaMemcpyAsync(winner_rank, h->s_wrank.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (winner_idx) CU(cudaMemcpyAsync(winner_idx, h->s_widx.p, E * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (winner_cost) CU(cudaMemcpyAsync(winner_cost, h->s_wcost.p, E * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (shrink) CU(cudaMemcpyAsync(shrink, h->s_shrink.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return finish_stats(h, st);
+}
+
+int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, double* cand_cost, double* cand_lamb,
+                         int32_t* cand_iters) {
+  if (!h) return fail("null handle");
+  if (n_episodes < 1 || n_episodes > h->E) return fail("n_episodes out of range");
+  if (!h->s_sel_idx.p) return fail("no controller step has run yet");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t)n_episodes * kOuter * h->L * h->K;
+  if (sel_idx) CU(cudaMemcpy(sel_idx, h->s_sel_idx.p, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (cand_cost) CU(cudaMemcpy(cand_cost, h->s_cand_cost.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cand_lamb) CU(cudaMemcpy(cand_lamb, h->s_cand_lamb.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cand_iters) CU(cudaMemcpy(cand_iters, h->s_cand_iters.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ batched episodes
+namespace {
+EpisodeState episode_state(i2lqr_handle* h) {
+  EpisodeState s{};
+  s.x = h->s_x.p;
+  s.upred = h->ep_upred.p;
+  s.step = h->ep_step.p;
+  s.done = h->ep_done.p;
+  s.horizon = h->ep_horizon.p;
+  s.pb = h->ep_pb.p;
+  s.active = h->ep_active.p;
+  s.status = h->ep_status.p;
+  s.lap_x = h->ep_lapx.p;
+  s.lap_u = h->ep_lapu.p;
+  s.S = h->params.max_sim_steps;
+  s.obs = h->d_obs.p;
+  s.obs0 = h->d_obs0.p;
+  s.goal = h->ep_goal.p;
+  s.n_running = h->ep_nrun.p;
+  return s;
+}
+}  // namespace
+
+int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* goal) {
+  if (!h) return fail("null handle");
+  if (h->E < 1) return fail("handle was created without episodes");
+  if (!x_init || !goal) return fail("null argument");
+  if (h->params.max_sim_steps < 1) return fail("max_sim_steps must be >= 1");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  if (ensure_step_workspace(h)) return 1;
+  const size_t E = h->E, N = h->kp.N, S = h->params.max_sim_steps;
+  CU(h->ep_upred.ensure(E * 2 * N));
+  CU(h->ep_goal.ensure(4));
+  CU(h->ep_lapx.ensure(E * (S + 1) * 4));
+  CU(h->ep_lapu.ensure(E * S * 2));
+  for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_laplen}) CU(b->ensure(E));
+  CU(h->ep_nrun.ensure(1));
+  if (!h->h_nrun) CU(cudaMallocHost(&h->h_nrun, sizeof(int)));
+  CU(cudaMemcpyAsync(h->s_x.p, x_init, E * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(h->ep_goal.p, goal, 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(h->ep_step.p, 0, E * sizeof(int), st));
+  CU(cudaMemsetAsync(h->ep_done.p, 0, E * sizeof(int), st));
+  CU(cudaMemsetAsync(h->ep_pb.p, 0, E * sizeof(int), st));
+  CU(cudaMemsetAsync(h->ep_status.p, 0, E * sizeof(int), st));
+  std::vector<int> hor(E, (int)N);
+  CU(cudaMemcpyAsync(h->ep_horizon.p, hor.data(), E * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  h->ep_ready = true;
+  return 0;
+}
+
+int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, double* lap_u) {
+  if (!h) return fail("null handle");
+  if (!h->ep_ready) return fail("call i2lqr_episodes_begin first");
+  for (int e = 0; e < h->E; ++e)
+    if (h->h_lap_count[e] == 0) return fail("episode %d has no stored lap", e);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  const int E = h->E, S = h->params.max_sim_steps, N = h->kp.N;
+  if (sync_obstacles(h)) return 1;
+  CU(h->d_obs0.ensure(E));
+  CU(cudaMemcpyAsync(h->d_obs0.p, h->d_obs.p, sizeof(DevObstacle) * E, cudaMemcpyDeviceToDevice, st));
+  EpisodeState es = episode_state(h);
+  // row 0 of every lap log = the state the lap starts from
+  CU(cudaMemcpy2DAsync(h->ep_lapx.p, (size_t)(S + 1) * 4 * sizeof(double), h->s_x.p, 4 * sizeof(double), 4 * sizeof(double), E,
+                       cudaMemcpyDeviceToDevice, st));
+  *h->h_nrun = E;
+  CU(cudaMemcpyAsync(h->ep_nrun.p, h->h_nrun, sizeof(int), cudaMemcpyHostToDevice, st));
+  if (begin_stats(h, st)) return 1;
+  const int tb = 128, gb = (E + tb - 1) / tb;
+  for (int i = 0; i < S; ++i) {
+    episode_pre_kernel<<<gb, tb, 0, st>>>(es, E, N);
+    CU(cudaGetLastError());
+    if (run_step(h, E, h->ep_active.p, st)) return 1;
+    episode_post_kernel<<<gb, tb, 0, st>>>(es, h->kp, h->s_u.p, h->s_upred.p, h->s_shrink.p, E, i, h->params.goal_tol);
+    CU(cudaGetLastError());
+    h->last_launches += 2;
+    CU(cudaMemcpyAsync(h->h_nrun, h->ep_nrun.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (*h->h_nrun <= 0) break;
+  }
+  episode_finish_kernel<<<(unsigned)(((long long)E * 32 + tb - 1) / tb), tb, 0, st>>>(es, h->set, E, N, h->ep_laplen.p);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  if (end_stats(h, st, true)) return 1;
+  // host mirrors of the safe-set bookkeeping
+  CU(cudaMemcpy(h->h_lap_len.data(), h->set.lap_len, sizeof(int) * (size_t)E * h->L, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(h->h_lap_count.data(), h->set.lap_count, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost));
+  if (lap_len) CU(cudaMemcpy(lap_len, h->ep_laplen.p, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost));
+  if (lap_x) CU(cudaMemcpy(lap_x, h->ep_lapx.p, sizeof(double) * (size_t)E * (S + 1) * 4, cudaMemcpyDeviceToHost));
+  if (lap_u) CU(cudaMemcpy(lap_u, h->ep_lapu.p, sizeof(double) * (size_t)E * S * 2, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+/* Per-episode status of the last lap: 0 ok, 1 hit max_sim_steps, 2 playback exhausted, 3 lap not storable. */
+int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status) {
+  if (!h || !status) return fail("null argument");
+  if (!h->ep_ready) return fail("call i2lqr_episodes_begin first");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy(status, h->ep_status.p, sizeof(int) * (size_t)h->E, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int64_t* ilqr_iterations, int64_t* solves) {
+  if (!h) return fail("null handle");
+  if (kernel_ms) *kernel_ms = h->last_ms;
+  if (launches) *launches = h->last_launches;
+  if (ilqr_iterations) *ilqr_iterations = h->last_iters;
+  if (solves) *solves = h->last_solves;
+  return 0;
+}
+
+// Refreshes last_stats after an asynchronous *_device call (synchronises the stream the call ran on).
+int i2lqr_sync_stats(i2lqr_handle* h, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  return finish_stats(h, st);
+}
+
+// FP64 FMA-pipe peak of `device` in TFLOP/s (2 flops per DFMA), best of `reps` timed launches.
+int i2lqr_measure_fp64_peak(int device, int reps, double* tflops) {
+  if (!tflops) return fail("null argument");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return fail("no such CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double* out = nullptr;
+  CU(cudaMalloc(&out, sizeof(double) * threads * blocks));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  double best = 0;
+  for (int r = 0; r < reps + 2; ++r) {
+    CU(cudaEventRecord(a));
+    dfma_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(b));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+    if (r >= 2 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

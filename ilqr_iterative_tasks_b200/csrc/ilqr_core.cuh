@@ -1,0 +1,456 @@
+// ilqr_core.cuh -- device-side iLQR for one candidate terminal state (sm_100a, FP64).
+//
+// One lane owns one candidate.  Everything a candidate needs across iterations lives in a per-lane
+// scratch column (shared memory for short horizons, an L2-resident global slab for long ones) laid out
+// [element][lane] so that a warp's accesses to one element are contiguous; only the value function
+// (Vx, Vxx) and the per-step working set are in registers.
+//
+// What is replaced (paths relative to the reference root):
+//   ilqr            iterative_ilqr/control/iterative_ilqr.py:7-85
+//   backward_pass   iterative_ilqr/control/iterative_ilqr.py:88-130
+//   forward_pass    iterative_ilqr/control/iterative_ilqr.py:133-160
+//   kinetic_bicycle / get_A_matrix / get_B_matrix   iterative_ilqr/systems/kinetic_bicycle.py:10-52
+//   get_cost_derivation / add_control_constraint / repelling_cost_function / get_cost_final
+//                   iterative_ilqr/control/ilqr_helper.py:9-64,83-150
+//
+// Structure that is exploited (the reference multiplies dense 4x4 / 4x2 arrays):
+//   A_k = I + [[0,0,al,be],[0,0,ga,de],[0,0,0,0],[0,0,0,0]],  B_k = [[b0,0],[b1,0],[dt,0],[0,dt]],
+//   Vxx symmetric (10 unique entries), l_uu diagonal and l_x / l_xx confined to the position block when
+//   matrix_Q = matrix_R = 0 (the reference's default, kQR = false).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace i2lqr {
+
+// Parameter block in kernel-argument (constant-bank) space, derived on the host from i2lqr_params.
+struct KParams {
+  int N;               // current horizon
+  int N_param;         // ilqr_param.num_horizon (terminal obstacle advance, ilqr_helper.py:134-139)
+  int K, L;            // num_ss_points, num_ss_iter
+  int max_iter;        // max_ilqr_iter
+  int max_relax;       // max_relax_iter
+  int has_qr;          // matrix_Q != 0 or matrix_R != 0
+  int pad0;
+  double dt, dt2;      // timestep, timestep**2
+  double a_max, d_lim; // clip bounds
+  double eps, lamb0, lamb_factor, max_lamb;
+  double cg, ch, cq2;  // control barrier: q1*q2, q1*q2^2, q2
+  double og, oh, oq2;  // obstacle barrier: q1*q2, q1*q2^2, q2
+  double one_margin;   // 1 + safety_margin
+  double xtarget[4];
+  double Qf[10], Qf2[10];  // symmetric upper triangles of Qterminal and 2*Qterminal (00 01 02 03 11 12 13 22 23 33)
+  double Q[10], Q2[10];    // matrix_Q and 2*matrix_Q
+  double R[3], R2[3];      // matrix_R and 2*matrix_R (00 01 11)
+};
+
+struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
+  double x, y, width, height, spd;
+  int32_t moving_option, present;
+};
+
+// Per-lane scratch column: element e lives at base[e * stride].
+struct Scratch {
+  double* base;
+  int stride;
+  __device__ __forceinline__ double ld(int e) const { return base[(size_t)e * stride]; }
+  __device__ __forceinline__ void st(int e, double v) const { base[(size_t)e * stride] = v; }
+};
+// Scratch layout for horizon N (18 N doubles per candidate):
+//   cur slot k (8):  [0..1] u_k   [2..5] x_{k+1}   [6] cos(theta_{k+1})  [7] sin(theta_{k+1})
+//   new slot k (10): gains [0..1] k_k, [2..9] K_k (row-major 2x4) after the backward pass; the forward pass
+//                    consumes the gains of step k and overwrites the slot with the trial trajectory in the
+//                    cur-slot format (first 8 entries).
+__host__ __device__ __forceinline__ int scratch_doubles(int N) { return 18 * N; }
+#define I2_CUR(k) ((k)*8)
+#define I2_NEW(N, k) ((N)*8 + (k)*10)
+
+// Registers that persist over a candidate's iterations.
+struct Cand {
+  double x0[4], c0, s0;  // initial state, cos / sin of its heading
+  double xt[4];          // terminal target (safe-set point)
+  double lamb, J;        // LM regularisation, cost of the current trajectory
+  double ox, oy, oP0, oP1, ospd;  // obstacle centre, 1/width^2, 1/height^2, speed
+  int omode, opresent;
+  int iters;
+};
+
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// v^T M v for symmetric M stored as upper triangle
+__device__ __forceinline__ double quad4(const double* M, double a, double b, double c, double d) {
+  double r0 = M[0] * a + M[1] * b + M[2] * c + M[3] * d;
+  double r1 = M[1] * a + M[4] * b + M[5] * c + M[6] * d;
+  double r2 = M[2] * a + M[5] * b + M[7] * c + M[8] * d;
+  double r3 = M[3] * a + M[6] * b + M[8] * c + M[9] * d;
+  return r0 * a + r1 * b + r2 * c + r3 * d;
+}
+__device__ __forceinline__ double quad2(const double* M, double a, double b) {
+  return (M[0] * a + M[1] * b) * a + (M[1] * a + M[2] * b) * b;
+}
+
+// Obstacle ellipse barrier at position (px,py), `step` stages ahead: gradient (2) and Gauss-Newton Hessian
+// (00,01,11) of q1*exp(q2*h), h = 1 + margin - d^T P d   (ilqr_helper.py:32-51,118-149, :59-64).
+__device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c, double px, double py, int step,
+                                                 double& g0, double& g1, double& h00, double& h01, double& h11) {
+  double cx = c.ox, cy = c.oy;
+  if (c.omode == 1) cy = c.oy + step * c.ospd;
+  if (c.omode == 2) cx = c.ox - step * c.ospd;
+  double d0 = px - cx, d1 = py - cy;
+  double h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
+  double hd0 = (-2.0 * c.oP0) * d0, hd1 = (-2.0 * c.oP1) * d1;
+  double e = exp(p.oq2 * h);
+  double c1 = p.og * e, c2 = p.oh * e;
+  g0 = c1 * hd0;
+  g1 = c1 * hd1;
+  h00 = c2 * (hd0 * hd0);
+  h01 = c2 * (hd0 * hd1);
+  h11 = c2 * (hd1 * hd1);
+}
+
+// Regularised inverse of the 2x2 Quu (iterative_ilqr.py:118-123): symmetric eigen-decomposition by one
+// Jacobi rotation (numerically stable when |b| << |a-d|), negative eigenvalues clamped to
+// zero, + lamb, V diag(1/e) V^T.
+__device__ __forceinline__ void quu_inverse(double a, double b, double d, double lamb, double& i00, double& i01,
+                                            double& i11) {
+  double c = 1.0, s = 0.0, e1 = a, e2 = d;
+  if (b != 0.0) {
+    double tau = (d - a) / (2.0 * b);
+    double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+    c = 1.0 / sqrt(1.0 + t * t);
+    s = t * c;
+    e1 = a - t * b;
+    e2 = d + t * b;
+  }
+  e1 = (e1 < 0.0 ? 0.0 : e1) + lamb;
+  e2 = (e2 < 0.0 ? 0.0 : e2) + lamb;
+  double r1 = 1.0 / e1, r2 = 1.0 / e2;
+  i00 = c * r1 * c + s * r2 * s;
+  i01 = s * r2 * c - c * r1 * s;
+  i11 = s * r1 * s + c * r2 * c;
+}
+
+// Terminal cost (x_N - x_t)^T Qf (x_N - x_t)
+__device__ __forceinline__ double terminal_cost(const KParams& p, const Cand& c, const double* xN) {
+  return quad4(p.Qf, xN[0] - c.xt[0], xN[1] - c.xt[1], xN[2] - c.xt[2], xN[3] - c.xt[3]);
+}
+
+// Candidate start (utils/base.py:405-410 + the first rollout of iterative_ilqr.py:32-48).  With u0 == null the
+// inputs are zero (what calc_input passes): heading and speed stay put and every stage reuses
+// cos/sin(theta_0).  u0 (2,N) is the warm start of a direct `ilqr()` call.
+template <bool kQR>
+__device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const Scratch& s, const double* u0) {
+  const int N = p.N;
+  double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
+  double cs = c.c0, sn = c.s0;
+  double J = 0.0;
+  for (int k = 0; k < N; ++k) {
+    double ua = 0.0, ud = 0.0;
+    if (u0 != nullptr) {
+      ua = clipd(u0[k], -p.a_max, p.a_max);
+      ud = clipd(u0[N + k], -p.d_lim, p.d_lim);
+    }
+    if (kQR) {
+      const double l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
+      J = J + l_state + quad2(p.R, ua, ud);
+    }
+    const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
+    x[0] = x[0] + cs * sd;
+    x[1] = x[1] + sn * sd;
+    x[2] = x[2] + ua * p.dt;
+    x[3] = x[3] + ud * p.dt;
+    if (u0 != nullptr) sincos(x[3], &sn, &cs);
+    s.st(I2_CUR(k) + 0, ua);
+    s.st(I2_CUR(k) + 1, ud);
+    s.st(I2_CUR(k) + 2, x[0]);
+    s.st(I2_CUR(k) + 3, x[1]);
+    s.st(I2_CUR(k) + 4, x[2]);
+    s.st(I2_CUR(k) + 5, x[3]);
+    s.st(I2_CUR(k) + 6, cs);
+    s.st(I2_CUR(k) + 7, sn);
+  }
+  c.J = J + terminal_cost(p, c, x);
+  c.iters = 0;
+}
+
+// Backward Riccati pass over the current trajectory; leaves the gains in the new-slots.
+template <bool kQR>
+__device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, const Scratch& s) {
+  const int N = p.N;
+  const double dt = p.dt;
+  // ---- value function at the horizon end: get_cost_final (ilqr_helper.py:106-150)
+  double xN[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) xN[i] = s.ld(I2_CUR(N - 1) + 2 + i);
+  double Vx0, Vx1, Vx2, Vx3;
+  {
+    double e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
+    Vx0 = p.Qf2[0] * e0 + p.Qf2[1] * e1 + p.Qf2[2] * e2 + p.Qf2[3] * e3;
+    Vx1 = p.Qf2[1] * e0 + p.Qf2[4] * e1 + p.Qf2[5] * e2 + p.Qf2[6] * e3;
+    Vx2 = p.Qf2[2] * e0 + p.Qf2[5] * e1 + p.Qf2[7] * e2 + p.Qf2[8] * e3;
+    Vx3 = p.Qf2[3] * e0 + p.Qf2[6] * e1 + p.Qf2[8] * e2 + p.Qf2[9] * e3;
+  }
+  double V00 = p.Qf2[0], V01 = p.Qf2[1], V02 = p.Qf2[2], V03 = p.Qf2[3], V11 = p.Qf2[4], V12 = p.Qf2[5],
+         V13 = p.Qf2[6], V22 = p.Qf2[7], V23 = p.Qf2[8], V33 = p.Qf2[9];
+  if (c.opresent) {
+    double g0, g1, h00, h01, h11;
+    obstacle_barrier(p, c, xN[0], xN[1], p.N_param, g0, g1, h00, h01, h11);
+    Vx0 += g0;
+    Vx1 += g1;
+    V00 += h00;
+    V01 += h01;
+    V11 += h11;
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    // ---- trajectory at stage k
+    const double ua = s.ld(I2_CUR(k) + 0), ud = s.ld(I2_CUR(k) + 1);
+    const double v1 = s.ld(I2_CUR(k) + 4);                               // v_{k+1}
+    const double cs = s.ld(I2_CUR(k) + 6), sn = s.ld(I2_CUR(k) + 7);     // cos / sin theta_{k+1}
+    double xk[4];
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xk[i] = c.x0[i];
+    } else {
+      xk[0] = s.ld(I2_CUR(k - 1) + 2);
+      xk[1] = s.ld(I2_CUR(k - 1) + 3);
+      if (kQR) {
+        xk[2] = s.ld(I2_CUR(k - 1) + 4);
+        xk[3] = s.ld(I2_CUR(k - 1) + 5);
+      }
+    }
+    // ---- linearisation at (v_{k+1}, theta_{k+1}, a_k): iterative_ilqr.py:92-99, kinetic_bicycle.py:30-52
+    const double sp = v1 * dt + (ua * p.dt2) / 2.0;
+    const double al = cs * dt, be = -sp * sn, ga = sn * dt, de = sp * cs;
+    const double b0 = p.dt2 * cs / 2.0, b1 = p.dt2 * sn / 2.0;
+    // ---- stage cost derivatives: ilqr_helper.py:25-55, input barriers :83-103
+    double lu0, lu1, luu00, luu11, luu01 = 0.0;
+    {
+      const double e1 = exp(p.cq2 * (ua - p.a_max)), e2 = exp(p.cq2 * (-p.a_max - ua));
+      const double e3 = exp(p.cq2 * (ud - p.d_lim)), e4 = exp(p.cq2 * (-p.d_lim - ud));
+      lu0 = p.cg * e1 - p.cg * e2;
+      lu1 = p.cg * e3 - p.cg * e4;
+      luu00 = p.ch * e1 + p.ch * e2;
+      luu11 = p.ch * e3 + p.ch * e4;
+    }
+    double lx0 = 0.0, lx1 = 0.0, lx2 = 0.0, lx3 = 0.0;
+    double l00 = 0.0, l01 = 0.0, l11 = 0.0;
+    if (kQR) {
+      lu0 = (p.R2[0] * ua + p.R2[1] * ud) + lu0;
+      lu1 = (p.R2[1] * ua + p.R2[2] * ud) + lu1;
+      luu00 += p.R2[0];
+      luu01 = p.R2[1];
+      luu11 += p.R2[2];
+      const double d0 = xk[0] - p.xtarget[0], d1 = xk[1] - p.xtarget[1], d2 = xk[2] - p.xtarget[2],
+                   d3 = xk[3] - p.xtarget[3];
+      lx0 = p.Q2[0] * d0 + p.Q2[1] * d1 + p.Q2[2] * d2 + p.Q2[3] * d3;
+      lx1 = p.Q2[1] * d0 + p.Q2[4] * d1 + p.Q2[5] * d2 + p.Q2[6] * d3;
+      lx2 = p.Q2[2] * d0 + p.Q2[5] * d1 + p.Q2[7] * d2 + p.Q2[8] * d3;
+      lx3 = p.Q2[3] * d0 + p.Q2[6] * d1 + p.Q2[8] * d2 + p.Q2[9] * d3;
+      l00 = p.Q2[0];
+      l01 = p.Q2[1];
+      l11 = p.Q2[4];
+    }
+    if (c.opresent) {
+      double g0, g1, h00, h01, h11;
+      obstacle_barrier(p, c, xk[0], xk[1], k, g0, g1, h00, h01, h11);
+      lx0 += g0;
+      lx1 += g1;
+      l00 += h00;
+      l01 += h01;
+      l11 += h11;
+    }
+    // ---- Q-function: iterative_ilqr.py:112-116
+    const double Qx0 = lx0 + Vx0, Qx1 = lx1 + Vx1;
+    const double Qx2 = lx2 + (al * Vx0 + ga * Vx1 + Vx2), Qx3 = lx3 + (be * Vx0 + de * Vx1 + Vx3);
+    const double Qu0 = lu0 + (b0 * Vx0 + b1 * Vx1 + dt * Vx2), Qu1 = lu1 + dt * Vx3;
+    const double G0 = b0 * V00 + b1 * V01 + dt * V02, G1 = b0 * V01 + b1 * V11 + dt * V12;
+    const double G2 = b0 * V02 + b1 * V12 + dt * V22, G3 = b0 * V03 + b1 * V13 + dt * V23;
+    const double H0 = dt * V03, H1 = dt * V13, H2 = dt * V23, H3 = dt * V33;
+    const double Quu00 = luu00 + (G0 * b0 + G1 * b1 + G2 * dt);
+    const double Quu01 = luu01 + G3 * dt;
+    const double Quu10 = luu01 + (H0 * b0 + H1 * b1 + H2 * dt);
+    const double Quu11 = luu11 + H3 * dt;
+    const double X02 = al * G0 + ga * G1 + G2, X03 = be * G0 + de * G1 + G3;  // Qux row 0 = [G0 G1 X02 X03]
+    const double X12 = al * H0 + ga * H1 + H2, X13 = be * H0 + de * H1 + H3;  // Qux row 1 = [H0 H1 X12 X13]
+    const double W02 = al * V00 + ga * V01 + V02, W12 = al * V01 + ga * V11 + V12, W22 = al * V02 + ga * V12 + V22;
+    const double W03 = be * V00 + de * V01 + V03, W13 = be * V01 + de * V11 + V13, W23 = be * V02 + de * V12 + V23;
+    const double W33 = be * V03 + de * V13 + V33;
+    double M00 = l00 + V00, M01 = l01 + V01, M11 = l11 + V11;
+    double M02 = W02, M03 = W03, M12 = W12, M13 = W13;
+    double M22 = al * W02 + ga * W12 + W22, M23 = al * W03 + ga * W13 + W23, M33 = be * W03 + de * W13 + W33;
+    if (kQR) {
+      M02 += p.Q2[2];
+      M03 += p.Q2[3];
+      M12 += p.Q2[5];
+      M13 += p.Q2[6];
+      M22 += p.Q2[7];
+      M23 += p.Q2[8];
+      M33 += p.Q2[9];
+    }
+    // ---- regularised inverse and gains: iterative_ilqr.py:118-126
+    double i00, i01, i11;
+    quu_inverse(Quu00, (Quu01 + Quu10) / 2.0, Quu11, c.lamb, i00, i01, i11);
+    const double k0 = -(i00 * Qu0 + i01 * Qu1), k1 = -(i01 * Qu0 + i11 * Qu1);
+    const double K00 = -(i00 * G0 + i01 * H0), K01 = -(i00 * G1 + i01 * H1);
+    const double K02 = -(i00 * X02 + i01 * X12), K03 = -(i00 * X03 + i01 * X13);
+    const double K10 = -(i01 * G0 + i11 * H0), K11 = -(i01 * G1 + i11 * H1);
+    const double K12 = -(i01 * X02 + i11 * X12), K13 = -(i01 * X03 + i11 * X13);
+    s.st(I2_NEW(N, k) + 0, k0);
+    s.st(I2_NEW(N, k) + 1, k1);
+    s.st(I2_NEW(N, k) + 2, K00);
+    s.st(I2_NEW(N, k) + 3, K01);
+    s.st(I2_NEW(N, k) + 4, K02);
+    s.st(I2_NEW(N, k) + 5, K03);
+    s.st(I2_NEW(N, k) + 6, K10);
+    s.st(I2_NEW(N, k) + 7, K11);
+    s.st(I2_NEW(N, k) + 8, K12);
+    s.st(I2_NEW(N, k) + 9, K13);
+    // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
+    const double P00 = K00 * Quu00 + K10 * Quu10, P01 = K00 * Quu01 + K10 * Quu11;
+    const double P10 = K01 * Quu00 + K11 * Quu10, P11 = K01 * Quu01 + K11 * Quu11;
+    const double P20 = K02 * Quu00 + K12 * Quu10, P21 = K02 * Quu01 + K12 * Quu11;
+    const double P30 = K03 * Quu00 + K13 * Quu10, P31 = K03 * Quu01 + K13 * Quu11;
+    Vx0 = Qx0 - (P00 * k0 + P01 * k1);
+    Vx1 = Qx1 - (P10 * k0 + P11 * k1);
+    Vx2 = Qx2 - (P20 * k0 + P21 * k1);
+    Vx3 = Qx3 - (P30 * k0 + P31 * k1);
+    V00 = M00 - (P00 * K00 + P01 * K10);
+    V01 = M01 - (P00 * K01 + P01 * K11);
+    V02 = M02 - (P00 * K02 + P01 * K12);
+    V03 = M03 - (P00 * K03 + P01 * K13);
+    V11 = M11 - (P10 * K01 + P11 * K11);
+    V12 = M12 - (P10 * K02 + P11 * K12);
+    V13 = M13 - (P10 * K03 + P11 * K13);
+    V22 = M22 - (P20 * K02 + P21 * K12);
+    V23 = M23 - (P20 * K03 + P21 * K13);
+    V33 = M33 - (P30 * K03 + P31 * K13);
+  }
+}
+
+// Full-step forward pass (iterative_ilqr.py:133-160).  Consumes the gains, leaves the trial trajectory in
+// the new-slots, returns cost_new; Jtarget is the cost the reference would recompute for the trial
+// trajectory at the top of its next iteration (stage cost about xtarget, iterative_ilqr.py:43-48).
+template <bool kQR>
+__device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, const Scratch& s, double& Jtarget) {
+  const int N = p.N;
+  double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
+  double cs = c.c0, sn = c.s0;
+  double Jn = 0.0, Jt = 0.0;
+  for (int k = 0; k < N; ++k) {
+    double xo[4];
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xo[i] = c.x0[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xo[i] = s.ld(I2_CUR(k - 1) + 2 + i);
+    }
+    const double uo0 = s.ld(I2_CUR(k) + 0), uo1 = s.ld(I2_CUR(k) + 1);
+    double g[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) g[i] = s.ld(I2_NEW(N, k) + i);
+    const double d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
+    double ua = uo0 + g[0] + (g[2] * d0 + g[3] * d1 + g[4] * d2 + g[5] * d3);
+    double ud = uo1 + g[1] + (g[6] * d0 + g[7] * d1 + g[8] * d2 + g[9] * d3);
+    ua = clipd(ua, -p.a_max, p.a_max);
+    ud = clipd(ud, -p.d_lim, p.d_lim);
+    if (kQR) {
+      const double l_ctrl = quad2(p.R, ua, ud);
+      Jn = Jn + quad4(p.Q, x[0] - c.xt[0], x[1] - c.xt[1], x[2] - c.xt[2], x[3] - c.xt[3]) + l_ctrl;
+      Jt = Jt + quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]) + l_ctrl;
+    }
+    const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
+    x[0] = x[0] + cs * sd;
+    x[1] = x[1] + sn * sd;
+    x[2] = x[2] + ua * p.dt;
+    x[3] = x[3] + ud * p.dt;
+    sincos(x[3], &sn, &cs);
+    s.st(I2_NEW(N, k) + 0, ua);
+    s.st(I2_NEW(N, k) + 1, ud);
+    s.st(I2_NEW(N, k) + 2, x[0]);
+    s.st(I2_NEW(N, k) + 3, x[1]);
+    s.st(I2_NEW(N, k) + 4, x[2]);
+    s.st(I2_NEW(N, k) + 5, x[3]);
+    s.st(I2_NEW(N, k) + 6, cs);
+    s.st(I2_NEW(N, k) + 7, sn);
+  }
+  const double T = terminal_cost(p, c, x);
+  Jtarget = Jt + T;
+  return Jn + T;
+}
+
+// One iLQR iteration with the accept / reject and lambda schedule of iterative_ilqr.py:74-84.
+// Returns true when the candidate's loop ends.
+template <bool kQR>
+__device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s) {
+  backward_pass<kQR>(p, c, s);
+  double Jt;
+  const double Jn = forward_pass<kQR>(p, c, s, Jt);
+  c.iters++;
+  bool done = false;
+  if (Jn < c.J) {
+    const int N = p.N;
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s.st(I2_CUR(k) + i, s.ld(I2_NEW(N, k) + i));
+    }
+    c.lamb /= p.lamb_factor;
+    done = fabs((Jn - c.J) / c.J) < p.eps;
+    c.J = kQR ? Jt : Jn;
+  } else {
+    c.lamb *= p.lamb_factor;
+    done = c.lamb > p.max_lamb;
+  }
+  return done || c.iters >= p.max_iter;
+}
+
+// Relax-cost ladder (utils/base.py:427-437); `scale` = 10**it of the outer iteration.
+__device__ __forceinline__ double relax_cost(const KParams& p, const double* xN, const double* xt, double qfun,
+                                             double scale) {
+  const double e0 = xN[0] - xt[0], e1 = xN[1] - xt[1], e2 = xN[2] - xt[2], e3 = xN[3] - xt[3];
+  const double r = sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
+  for (int i = 1; i <= p.max_relax; ++i) {
+    if (r <= 80.0 * i / scale) return qfun + p.N + 100 * i;
+    if (r > 80.0 * p.max_relax / scale) return INFINITY;
+  }
+  return NAN;
+}
+
+// Result in the reference's array layout: xvar (4, N+1), uvar (2, N), time on the last axis.
+__device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c, const Scratch& s, double* xvar,
+                                                double* uvar) {
+  const int N = p.N;
+  if (xvar) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xvar[i * (N + 1)] = c.x0[i];
+    for (int k = 0; k < N; ++k) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xvar[i * (N + 1) + k + 1] = s.ld(I2_CUR(k) + 2 + i);
+    }
+  }
+  if (uvar) {
+    for (int k = 0; k < N; ++k) {
+      uvar[k] = s.ld(I2_CUR(k) + 0);
+      uvar[N + k] = s.ld(I2_CUR(k) + 1);
+    }
+  }
+}
+
+__device__ __forceinline__ void load_obstacle(Cand& c, const DevObstacle* o) {
+  if (o != nullptr && o->present) {
+    c.ox = o->x;
+    c.oy = o->y;
+    c.oP0 = 1.0 / (o->width * o->width);
+    c.oP1 = 1.0 / (o->height * o->height);
+    c.ospd = o->spd;
+    c.omode = o->moving_option;
+    c.opresent = 1;
+  } else {
+    c.ox = c.oy = c.oP0 = c.oP1 = c.ospd = 0.0;
+    c.omode = 0;
+    c.opresent = 0;
+  }
+}
+
+}  // namespace i2lqr

@@ -1,0 +1,492 @@
+// kernels.cuh -- the sm_100a kernels of the i2LQR control solve.
+//
+//   K1  knn_kernel      safe-set K-nearest selection   (iLqr.select_close_ss, utils/base.py:332-341)
+//   K2  solve_kernel    persistent batched iLQR, one lane per candidate / per lambda chain
+//                       (control/iterative_ilqr.py:7-160 + the candidate loop of utils/base.py:403-455)
+//   K3  winner_kernel   lexicographic winner + result gather (utils/base.py:462-478)
+//   K4  plant_kernel    batched closed-loop episode step (utils/base.py:157-213, 708-726)
+#pragma once
+#include "ilqr_core.cuh"
+
+namespace i2lqr {
+
+constexpr int kOuter = 3;  // calc_input's outer iterations (utils/base.py:384, break at :472-478)
+
+// Device-resident safe sets: per episode a ring of L lap slots, each SoA [4][Tcap].
+struct SafeSet {
+  double* ss;      // [E][L][4][Tcap]
+  int* lap_len;    // [E][L]
+  int* lap_count;  // [E]  laps ever added; absolute lap a lives in slot a % L
+  int L, Tcap;
+  __device__ __forceinline__ const double* lap(int e, int slot) const {
+    return ss + ((size_t)e * L + slot) * 4 * (size_t)Tcap;
+  }
+};
+
+struct Work {
+  int mode;                    // 0 = flat candidates, 1 = lambda chains of a controller step
+  long long n_items;           // candidates (mode 0) or chains = E*L (mode 1)
+  unsigned long long* counter; // work-fetch counter (zeroed before launch)
+  unsigned long long* stats;   // [0] += executed iLQR iterations, [1] += finished candidate solves
+  double* gscratch;            // global scratch slab when the horizon does not fit shared memory
+  long long gstride;
+  // ---- mode 0
+  const double* x0;            // (B,4)
+  const double* x_term;        // (B,4)
+  const double* lamb_in;       // (B) or null (= param.lamb)
+  const DevObstacle* obs;      // n_obs entries
+  long long n_obs;             // 0, 1 or B
+  const double* u_init;        // (B,2,N) warm start or null
+  double* uvar;                // (B,2,N)
+  double* xvar;                // (B,4,N+1)
+  double* lamb_out;            // (B)
+  int* iters;                  // (B)
+  // ---- mode 1
+  int it;                      // outer iteration 0..2
+  double scale;                // 10**it
+  SafeSet set;
+  const double* x;             // (E,4) current states
+  const DevObstacle* ep_obs;   // (E)
+  const int* active;           // (E) or null: episodes that solve this step
+  const long long* sel_idx;    // (E,3,L,K)
+  const int* sel_cnt;          // (E,L)
+  double* cand_x;              // (E,L,K,4,N+1)
+  double* cand_u;              // (E,L,K,2,N)
+  double* cand_cost;           // (E,3,L,K)
+  double* cand_lamb;           // (E,3,L,K)
+  int* cand_iters;             // (E,3,L,K)
+};
+
+// ------------------------------------------------------------------------------------------------ K2
+// Persistent kernel.  Every lane runs a small state machine: FETCH an item with a warp-aggregated atomic,
+// INIT a candidate, RUN one iLQR iteration per trip, finalise, and either take the next candidate of its
+// chain (lambda carried, utils/base.py:393,414) or fetch again.  A warp therefore always executes the same
+// code -- one iteration -- on up to 32 different candidates regardless of how many iterations each needs.
+enum : int { ST_FETCH = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
+
+template <bool kQR, bool kSmem>
+__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
+  extern __shared__ double smem[];
+  Scratch s;
+  if (kSmem) {
+    s.base = smem + threadIdx.x;
+    s.stride = blockDim.x;
+  } else {
+    s.base = w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    s.stride = (int)w.gstride;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  const int N = p.N;
+  Cand c;
+  int state = ST_FETCH;
+  long long item = 0;
+  int rank = 0, cnt = 0;        // position in the chain
+  int ep = 0, lrel = 0, slot = 0, T = 0;
+  const double* lap = nullptr;
+  long long jsel = 0;
+  unsigned long long my_iters = 0, my_solves = 0;
+
+  for (;;) {
+    // ---- FETCH
+    const unsigned want = __ballot_sync(0xffffffffu, state == ST_FETCH);
+    if (want) {
+      unsigned long long base = 0;
+      const int leader = __ffs(want) - 1;
+      if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (state == ST_FETCH) {
+        item = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+        if (item >= w.n_items) {
+          state = ST_DONE;
+        } else if (w.mode == 0) {
+          rank = 0;
+          cnt = 1;
+          c.lamb = w.lamb_in ? w.lamb_in[item] : p.lamb0;
+          load_obstacle(c, w.n_obs == 0 ? nullptr : (w.n_obs == 1 ? w.obs : w.obs + item));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) c.x0[i] = w.x0[item * 4 + i];
+          sincos(c.x0[3], &c.s0, &c.c0);
+          state = ST_INIT;
+        } else {
+          ep = (int)(item / w.set.L);
+          lrel = (int)(item % w.set.L);
+          cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
+          if (cnt == 0) {
+            state = ST_FETCH;  // unused lap slot or inactive episode: take another item next trip
+          } else {
+            const int count = w.set.lap_count[ep];
+            const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
+            slot = (min_iter + lrel) % w.set.L;
+            T = w.set.lap_len[(size_t)ep * w.set.L + slot];
+            lap = w.set.lap(ep, slot);
+            rank = 0;
+            c.lamb = p.lamb0;  // utils/base.py:393
+            load_obstacle(c, w.ep_obs + ep);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c.x0[i] = w.x[(size_t)ep * 4 + i];
+            sincos(c.x0[3], &c.s0, &c.c0);
+            state = ST_INIT;
+          }
+        }
+      }
+    }
+    if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+    // ---- INIT
+    if (state == ST_INIT) {
+      if (w.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.xt[i] = w.x_term[item * 4 + i];
+      } else {
+        jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.xt[i] = lap[(size_t)i * w.set.Tcap + jsel];
+      }
+      init_candidate<kQR>(p, c, s, (w.mode == 0 && w.u_init != nullptr) ? w.u_init + item * 2 * N : nullptr);
+      state = ST_RUN;
+    }
+    // ---- RUN
+    if (state == ST_RUN) {
+      const bool done = ilqr_iteration<kQR>(p, c, s);
+      if (done) {
+        my_iters += (unsigned long long)c.iters;
+        my_solves += 1;
+        if (w.mode == 0) {
+          store_candidate(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr,
+                          w.uvar ? w.uvar + item * 2 * N : nullptr);
+          if (w.lamb_out) w.lamb_out[item] = c.lamb;
+          if (w.iters) w.iters[item] = c.iters;
+          state = ST_FETCH;
+        } else {
+          const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
+          store_candidate(p, c, s, w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
+          double xN[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xN[i] = s.ld(I2_CUR(N - 1) + 2 + i);
+          const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
+          w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
+          w.cand_lamb[tslot] = c.lamb;
+          w.cand_iters[tslot] = c.iters;
+          ++rank;
+          state = rank < cnt ? ST_INIT : ST_FETCH;  // lambda is carried to the lap's next candidate
+        }
+      }
+    }
+  }
+  // ---- statistics: one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    my_iters += __shfl_xor_sync(0xffffffffu, my_iters, o);
+    my_solves += __shfl_xor_sync(0xffffffffu, my_solves, o);
+  }
+  if (lane == 0 && w.stats != nullptr && my_solves) {
+    atomicAdd(w.stats + 0, my_iters);
+    atomicAdd(w.stats + 1, my_solves);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// One warp per (episode, active lap).  The lap's SoA rows are read coalesced, the 1-norm distances
+// ((|dx|+|dy|)+|dv|)+|dtheta| (same association as scipy's norm, bit-exact) are staged in
+// shared memory, and K rounds of a warp-shuffle arg-min on the key (distance, index) emit the indices in
+// rank order -- the order is semantically significant (lambda-chain order, winner rule).
+struct KnnArgs {
+  SafeSet set;
+  int K, it, n_episodes;
+  const double* x;        // (E,4) current states              (outer iteration 0)
+  const double* x_pred;   // (E,4,N+1) previous winner          (outer iterations 1,2: its last column)
+  int N;
+  const int* active;      // (E) or null
+  long long* sel_idx;     // (E,3,L,K)
+  int* sel_cnt;           // (E,L)
+  // single-query form (i2lqr_select_knn): episode / absolute lap / explicit x0
+  int q_episode, q_lap;
+  const double* q_x0;
+  long long* q_idx;
+  int* q_cnt;
+};
+
+__global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
+  extern __shared__ double dist_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  double* dist = dist_smem + (size_t)wib * a.set.Tcap;
+  const long long wid = (long long)blockIdx.x * warps_per_block + wib;
+  int e, lrel, slot;
+  double g[4];
+  long long* out;
+  int* out_cnt;
+  if (a.q_x0 != nullptr) {
+    if (wid != 0) return;
+    e = a.q_episode;
+    slot = a.q_lap % a.set.L;
+    lrel = 0;
+    for (int i = 0; i < 4; ++i) g[i] = a.q_x0[i];
+    out = a.q_idx;
+    out_cnt = a.q_cnt;
+  } else {
+    if (wid >= (long long)a.n_episodes * a.set.L) return;
+    e = (int)(wid / a.set.L);
+    lrel = (int)(wid % a.set.L);
+    const int count = a.set.lap_count[e];
+    const int n_act = count < a.set.L ? count : a.set.L;
+    out_cnt = a.sel_cnt + (size_t)e * a.set.L + lrel;
+    if (lrel >= n_act || (a.active != nullptr && !a.active[e])) {
+      if (lane == 0) *out_cnt = 0;
+      return;
+    }
+    const int min_iter = count - a.set.L > 0 ? count - a.set.L : 0;
+    slot = (min_iter + lrel) % a.set.L;
+    for (int i = 0; i < 4; ++i)  // x_guess: utils/base.py:398-401
+      g[i] = a.it == 0 ? a.x[(size_t)e * 4 + i] : a.x_pred[((size_t)e * 4 + i) * (a.N + 1) + a.N];
+    out = a.sel_idx + (((size_t)e * kOuter + a.it) * a.set.L + lrel) * a.K;
+  }
+  const int T = a.set.lap_len[(size_t)e * a.set.L + slot];
+  const double* lap = a.set.lap(e, slot);
+  const size_t Tc = a.set.Tcap;
+  for (int j = lane; j < T; j += 32)
+    dist[j] = ((fabs(lap[j] - g[0]) + fabs(lap[Tc + j] - g[1])) + fabs(lap[2 * Tc + j] - g[2])) +
+              fabs(lap[3 * Tc + j] - g[3]);
+  __syncwarp();
+  const int n = a.K < T ? a.K : T;
+  double dprev = -INFINITY;
+  int jprev = -1;
+  for (int r = 0; r < n; ++r) {
+    double dbest = INFINITY;
+    int jbest = 0x7fffffff;
+    for (int j = lane; j < T; j += 32) {
+      const double d = dist[j];
+      const bool after = d > dprev || (d == dprev && j > jprev);
+      if (after && (d < dbest || (d == dbest && j < jbest))) {
+        dbest = d;
+        jbest = j;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double d2 = __shfl_xor_sync(0xffffffffu, dbest, o);
+      const int j2 = __shfl_xor_sync(0xffffffffu, jbest, o);
+      if (d2 < dbest || (d2 == dbest && j2 < jbest)) {
+        dbest = d2;
+        jbest = j2;
+      }
+    }
+    if (lane == 0) out[r] = jbest;
+    dprev = dbest;
+    jprev = jbest;
+  }
+  if (lane == 0) {
+    *out_cnt = n;
+    for (int r = n; r < a.K; ++r) out[r] = -1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// One thread per episode: `min(cost_list)` is Python's lexicographic list comparison over the per-lap cost
+// vectors (first differing element decides, a prefix is smaller), then the first arg-min inside the
+// winning lap (utils/base.py:462-465); the winner's trajectory becomes x_pred / u_pred.
+struct WinnerArgs {
+  int n_episodes, it, L, K, N;
+  const int* lap_count;
+  const int* lap_len;      // (E,L)
+  const int* active;
+  const int* sel_cnt;      // (E,L)
+  const long long* sel_idx;
+  const double* cand_cost; // (E,3,L,K)
+  const double* cand_x;
+  const double* cand_u;
+  double* u;               // (E,2)
+  double* x_pred;          // (E,4,N+1)
+  double* u_pred;          // (E,2,N)
+  int* winner_lap;
+  int* winner_rank;
+  long long* winner_idx;
+  double* winner_cost;
+  int* shrink;
+};
+
+__global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
+  // one warp per episode: lane 0 decides, all lanes copy
+  const int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= a.n_episodes) return;
+  if (a.active != nullptr && !a.active[e]) return;
+  const int count = a.lap_count[e];
+  const int n_act = count < a.L ? count : a.L;
+  const int min_iter = count - a.L > 0 ? count - a.L : 0;
+  int bl = 0, br = 0;
+  if (lane == 0) {
+    const double* cost = a.cand_cost + ((size_t)e * kOuter + a.it) * a.L * a.K;
+    const int* cnt = a.sel_cnt + (size_t)e * a.L;
+    for (int l = 1; l < n_act; ++l) {
+      const double* ca = cost + (size_t)l * a.K;
+      const double* cb = cost + (size_t)bl * a.K;
+      const int na = cnt[l], nb = cnt[bl];
+      const int n = na < nb ? na : nb;
+      bool less = na < nb;
+      for (int i = 0; i < n; ++i)
+        if (ca[i] != cb[i]) {
+          less = ca[i] < cb[i];
+          break;
+        }
+      if (less) bl = l;
+    }
+    const double* cv = cost + (size_t)bl * a.K;
+    for (int r = 1; r < cnt[bl]; ++r)
+      if (cv[r] < cv[br]) br = r;
+    const long long j = a.sel_idx[(((size_t)e * kOuter + a.it) * a.L + bl) * a.K + br];
+    a.winner_lap[e] = min_iter + bl;
+    a.winner_rank[e] = br;
+    a.winner_idx[e] = j;
+    a.winner_cost[e] = cv[br];
+    const int T = a.lap_len[(size_t)e * a.L + (min_iter + bl) % a.L];
+    a.shrink[e] = (j + 1) > (long long)(T - 1);  // utils/base.py:474-477
+  }
+  bl = __shfl_sync(0xffffffffu, bl, 0);
+  br = __shfl_sync(0xffffffffu, br, 0);
+  const size_t cslot = ((size_t)e * a.L + bl) * a.K + br;
+  const int nx = 4 * (a.N + 1), nu = 2 * a.N;
+  for (int i = lane; i < nx; i += 32) a.x_pred[(size_t)e * nx + i] = a.cand_x[cslot * nx + i];
+  for (int i = lane; i < nu; i += 32) a.u_pred[(size_t)e * nu + i] = a.cand_u[cslot * nu + i];
+  if (lane < 2) a.u[(size_t)e * 2 + lane] = a.cand_u[cslot * nu + (size_t)lane * a.N];
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// Batched closed-loop episodes: the plant, obstacle motion, termination test, playback bookkeeping and
+// the lap append all stay on the device (Simulator.sim utils/base.py:708-726, KineticBicycle.forward_one_step
+// :157-213, Obstacle.update_obstacle / reset_obstacle :50-64, calc_input's playback branch :377-382,
+// iterative_ilqr/tests/ilqr_test.py:56-60).
+struct EpisodeState {
+  double* x;            // (E,4) plant state == controller state
+  double* upred;        // (E,2,N) u_pred of the last solve step (playback source)
+  int* step;            // steps taken in the current lap
+  int* done;            // lap finished
+  int* horizon;         // controller num_horizon (N when solving, < N while playing back)
+  int* pb;              // next column of upred to play back
+  int* active;          // solves this step
+  int* status;          // 0 ok, 1 lap hit max_sim_steps, 2 playback ran out of inputs, 3 lap too short / long to store
+  double* lap_x;        // (E,S+1,4)
+  double* lap_u;        // (E,S,2)
+  int S;
+  DevObstacle* obs;     // current obstacle per episode (moves)
+  const DevObstacle* obs0;
+  const double* goal;   // (4)
+  int* n_running;       // episodes whose lap is still running
+};
+
+__global__ void episode_pre_kernel(EpisodeState s, int E, int N_param) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  s.active[e] = (!s.done[e] && s.horizon[e] == N_param) ? 1 : 0;
+}
+
+__global__ void episode_post_kernel(EpisodeState s, const __grid_constant__ KParams p, const double* u_solve,
+                                    const double* upred_solve, const int* shrink, int E, int sim_i, double goal_tol) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E || s.done[e]) return;
+  const int N = p.N;
+  double ua, ud;
+  if (s.active[e]) {
+    ua = u_solve[(size_t)e * 2];
+    ud = u_solve[(size_t)e * 2 + 1];
+    for (int i = 0; i < 2 * N; ++i) s.upred[(size_t)e * 2 * N + i] = upred_solve[(size_t)e * 2 * N + i];
+    s.pb[e] = 1;
+    if (shrink[e]) s.horizon[e] = N - 1;  // utils/base.py:474-477
+  } else {
+    const int c = s.pb[e];
+    if (c >= N) {  // the reference would index an empty u_old here (IndexError)
+      s.status[e] = 2;
+      s.done[e] = 1;
+      atomicSub(s.n_running, 1);
+      return;
+    }
+    ua = s.upred[(size_t)e * 2 * N + c];      // utils/base.py:378-381
+    ud = s.upred[(size_t)e * 2 * N + N + c];
+    s.pb[e] = c + 1;
+    s.horizon[e] -= 1;
+  }
+  // plant: kinetic_bicycle (systems/kinetic_bicycle.py:10-27), noise off
+  double* x = s.x + (size_t)e * 4;
+  double sn, cs;
+  sincos(x[3], &sn, &cs);
+  const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
+  const double x0 = x[0] + cs * sd, x1 = x[1] + sn * sd, x2 = x[2] + ua * p.dt, x3 = x[3] + ud * p.dt;
+  x[0] = x0;
+  x[1] = x1;
+  x[2] = x2;
+  x[3] = x3;
+  const int st = s.step[e];
+  double* lx = s.lap_x + ((size_t)e * (s.S + 1) + st + 1) * 4;
+  lx[0] = x0;
+  lx[1] = x1;
+  lx[2] = x2;
+  lx[3] = x3;
+  s.lap_u[((size_t)e * s.S + st) * 2] = ua;
+  s.lap_u[((size_t)e * s.S + st) * 2 + 1] = ud;
+  s.step[e] = st + 1;
+  DevObstacle* o = s.obs + e;
+  if (o->present) {  // Obstacle.update_obstacle
+    if (o->moving_option == 1) o->y += o->spd * p.dt;
+    if (o->moving_option == 2) o->x -= o->spd * p.dt;
+  }
+  const double d0 = x0 - s.goal[0], d1 = x1 - s.goal[1], d2 = x2 - s.goal[2], d3 = x3 - s.goal[3];
+  const bool reached = sqrt(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) <= goal_tol;
+  if (reached || sim_i == s.S - 1) {
+    if (!reached) s.status[e] = 1;
+    s.done[e] = 1;
+    atomicSub(s.n_running, 1);
+  }
+}
+
+// One warp per episode: snap the lap's last row to the goal, append it to the safe-set ring, reset the
+// episode for its next lap (state <- 0 as update_memory_post_iter does, utils/base.py:195).
+__global__ void episode_finish_kernel(EpisodeState s, SafeSet set, int E, int N_param, int* lap_len_out) {
+  const int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= E) return;
+  const int steps = s.step[e];
+  const int T = steps + 1;
+  double* lx = s.lap_x + (size_t)e * (s.S + 1) * 4;
+  if (lane < 4) lx[(size_t)steps * 4 + lane] = s.goal[lane];
+  __syncwarp();
+  const bool storable = T > N_param && T <= set.Tcap;
+  if (storable) {
+    const int count = set.lap_count[e];
+    const int slot = count % set.L;
+    double* dst = set.ss + ((size_t)e * set.L + slot) * 4 * (size_t)set.Tcap;
+    for (int j = lane; j < T; j += 32)
+      for (int i = 0; i < 4; ++i) dst[(size_t)i * set.Tcap + j] = lx[(size_t)j * 4 + i];
+    __syncwarp();
+    if (lane == 0) {
+      set.lap_len[(size_t)e * set.L + slot] = T;
+      set.lap_count[e] = count + 1;
+    }
+  }
+  if (lane == 0) {
+    if (!storable) s.status[e] = 3;
+    lap_len_out[e] = steps;
+    s.step[e] = 0;
+    s.done[e] = 0;
+    s.horizon[e] = N_param;
+    s.pb[e] = 0;
+    s.obs[e] = s.obs0[e];
+    for (int i = 0; i < 4; ++i) s.x[(size_t)e * 4 + i] = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------- FP64 FMA-pipe peak
+// Dependent-free DFMA streams: the measured denominator of the roofline (MEASURED_PEAKS.json carries no
+// FP64 figure).  8 independent accumulators per thread, `iters` rounds of 8 FMAs.
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    r0 = fma(r0, a, b);
+    r1 = fma(r1, a, b);
+    r2 = fma(r2, a, b);
+    r3 = fma(r3, a, b);
+    r4 = fma(r4, a, b);
+    r5 = fma(r5, a, b);
+    r6 = fma(r6, a, b);
+    r7 = fma(r7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+}  // namespace i2lqr

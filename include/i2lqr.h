@@ -38,7 +38,9 @@ typedef struct i2lqr_params {
   int32_t max_ilqr_iter;  /* 150 */
   int32_t max_relax_iter; /* 55 */
   int32_t max_sim_steps;  /* 121, Simulator.sim :709-710 */
-  int32_t reserved0;
+  int32_t obstacle_horizon; /* steps the obstacle is advanced for the terminal barrier: the reference uses
+                               ilqr_param.num_horizon there (control/ilqr_helper.py:134-139) even when ilqr() is
+                               called with another num_horizon; 0 = same as num_horizon */
   int32_t reserved1;
   double matrix_Q[16];         /* default 0 */
   double matrix_R[4];          /* default 0 */
@@ -82,17 +84,19 @@ int i2lqr_set_params(i2lqr_handle* h, const i2lqr_params* p);
 /* ---- flat batch of independent candidate solves ----------------------------------------------------- */
 /* Replaces B calls of control.iterative_ilqr.ilqr (iterative_ilqr/control/iterative_ilqr.py:7-85), each
  * set up as calc_input does (zero uvar, xvar[:,0] = x0: iterative_ilqr/utils/base.py:405-410).
- *   x0, x_term : (B,4)   lamb_in : (B)   obs : n_obs entries, n_obs in {0 (no obstacle), 1 (shared), B}
+ *   x0, x_term : (B,4)   lamb_in : (B) or NULL (= params.lamb)
+ *   obs : n_obs entries, n_obs in {0 (no obstacle), 1 (shared), B}
+ *   uvar_init : (B,2,N) warm-start inputs or NULL (= zeros, what calc_input passes)
  *   uvar : (B,2,N)  xvar : (B,4,N+1)  lamb_out : (B)  iters : (B) executed iLQR iterations
  * Any output pointer may be NULL.  Host-pointer form: H2D, solve, D2H inside the call. */
 int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
-                      const i2lqr_obstacle* obs, int64_t n_obs, double* uvar, double* xvar, double* lamb_out,
-                      int32_t* iters);
+                      const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
+                      double* lamb_out, int32_t* iters);
 /* Same, all pointers resident on the handle's device; runs on `cuda_stream` (NULL = the handle's stream)
  * and does not synchronise. */
 int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term,
-                             const double* lamb_in, const i2lqr_obstacle* obs, int64_t n_obs, double* uvar,
-                             double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream);
+                             const double* lamb_in, const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init,
+                             double* uvar, double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream);
 
 /* ---- safe set --------------------------------------------------------------------------------------- */
 /* Replaces iLqr.add_trajectory (iterative_ilqr/utils/base.py:343-369): x is (T,4); Qfun[j] = T-1-j is
@@ -127,18 +131,29 @@ int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, doub
 /* ---- batched closed-loop episodes (device-resident plant + controller) ------------------------------ */
 /* Replaces Simulator.sim + KineticBicycle.forward_one_step (iterative_ilqr/utils/base.py:157-213,708-726)
  * and the lap post-processing of iterative_ilqr/tests/ilqr_test.py:56-60 for all episodes of the handle.
- * x_init : (E,4) state every lap starts from; goal : (4) the initial lap's last row. */
+ * x_init : (E,4) state the first lap starts from (later laps start from 0, as update_memory_post_iter
+ * resets the plant, :195); goal : (4) the initial lap's last row. */
 int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* goal);
 /* Runs one lap for every episode (at most max_sim_steps controller steps each); on return lap_len[e] is the
  * number of steps taken and the finished lap (last row snapped to the goal) is already appended to the
  * episode's safe set.  lap_x : optional (E, max_sim_steps+1, 4); lap_u : optional (E, max_sim_steps, 2). */
 int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, double* lap_u);
 
+/* Per-episode status of the last lap: 0 reached the goal, 1 stopped at max_sim_steps ("not finished",
+ * :722-726), 2 playback ran out of inputs (IndexError in the reference), 3 lap too short/long to store. */
+int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 /* Device time (CUDA events on the handle's stream) of the kernels of the last compute call, the number
  * of kernels it launched, and the iLQR iterations it executed (for the roofline). */
 int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int64_t* ilqr_iterations,
                      int64_t* solves);
+
+/* Refreshes the statistics after an asynchronous *_device call; synchronises `cuda_stream`. */
+int i2lqr_sync_stats(i2lqr_handle* h, void* cuda_stream);
+/* Dependent-free DFMA micro-benchmark: the measured FP64 FMA-pipe peak of `device` in TFLOP/s (best of
+ * `reps` launches), the roofline denominator for this path (MEASURED_PEAKS.json has no FP64 figure). */
+int i2lqr_measure_fp64_peak(int device, int reps, double* tflops);
 
 #ifdef __cplusplus
 }

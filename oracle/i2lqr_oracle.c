@@ -142,7 +142,7 @@ static void backward_pass(const i2lqr_params* p, const i2lqr_obstacle* o, int N,
       Vx[i] = t;
     }
     for (int i = 0; i < NX * NX; ++i) Vxx[i] = 2 * p->matrix_Qterminal[i];
-    obstacle_barrier(p, o, &X[N * NX], p->num_horizon, Vx, Vxx);
+    obstacle_barrier(p, o, &X[N * NX], p->obstacle_horizon > 0 ? p->obstacle_horizon : p->num_horizon, Vx, Vxx);
   }
   for (int k = N - 1; k >= 0; --k) {
     /* A, B at (v_{k+1}, theta_{k+1}, a_k): control/iterative_ilqr.py:92-99, systems/kinetic_bicycle.py:30-52 */
@@ -230,8 +230,8 @@ static double forward_pass(const i2lqr_params* p, int N, const double* X, const 
 
 /* control/iterative_ilqr.py:7-85 with the candidate initialisation of utils/base.py:405-410.
  * uvar_out (2,N), xvar_out (4,N+1) in the reference's layout (time is the last axis). */
-int orc_ilqr(const i2lqr_params* p, const i2lqr_obstacle* o, const double* x0, const double* xterm, double lamb,
-             double* uvar_out, double* xvar_out, double* lamb_out, int32_t* iters_out) {
+int orc_ilqr_ex(const i2lqr_params* p, const i2lqr_obstacle* o, const double* x0, const double* xterm, double lamb,
+                const double* uvar_init, double* uvar_out, double* xvar_out, double* lamb_out, int32_t* iters_out) {
   int N = p->num_horizon;
   size_t nd = (size_t)(N + 1) * NX * 3 + (size_t)N * NU * 3 + (size_t)N * NU * NX;
   double* mem = (double*)calloc(nd, sizeof(double));
@@ -242,6 +242,9 @@ int orc_ilqr(const i2lqr_params* p, const i2lqr_obstacle* o, const double* x0, c
     X[i] = x0[i];
     dX[i] = x0[i] - p->xtarget[i];
   }
+  if (uvar_init) /* warm start of a direct ilqr() call; calc_input passes zeros (utils/base.py:405) */
+    for (int k = 0; k < N; ++k)
+      for (int i = 0; i < NU; ++i) U[k * NU + i] = uvar_init[i * N + k];
   int iters = 0;
   for (int it = 0; it < p->max_ilqr_iter; ++it) {
     double cost = 0;
@@ -286,12 +289,17 @@ int orc_ilqr(const i2lqr_params* p, const i2lqr_obstacle* o, const double* x0, c
   return 0;
 }
 
+int orc_ilqr(const i2lqr_params* p, const i2lqr_obstacle* o, const double* x0, const double* xterm, double lamb,
+             double* uvar_out, double* xvar_out, double* lamb_out, int32_t* iters_out) {
+  return orc_ilqr_ex(p, o, x0, xterm, lamb, NULL, uvar_out, xvar_out, lamb_out, iters_out);
+}
+
 /* B independent problems on `nthreads` host threads (pthreads, dynamic chunks of 64): the CPU baseline of
  * bench.py.  (This image's gcc has no libgomp, hence no OpenMP.) */
 typedef struct {
   const i2lqr_params* p;
   int64_t B;
-  const double *x0, *x_term, *lamb_in;
+  const double *x0, *x_term, *lamb_in, *u_init;
   const i2lqr_obstacle* obs;
   int64_t n_obs;
   double *uvar, *xvar, *lamb_out;
@@ -309,8 +317,8 @@ static void* batch_worker(void* arg) {
     int64_t b1 = b0 + 64 < j->B ? b0 + 64 : j->B;
     for (int64_t b = b0; b < b1; ++b) {
       const i2lqr_obstacle* o = j->n_obs == 0 ? NULL : (j->n_obs == 1 ? j->obs : j->obs + b);
-      int r = orc_ilqr(j->p, o, j->x0 + b * NX, j->x_term + b * NX, j->lamb_in ? j->lamb_in[b] : j->p->lamb,
-                       j->uvar ? j->uvar + b * NU * N : NULL, j->xvar ? j->xvar + b * NX * (N + 1) : NULL,
+      int r = orc_ilqr_ex(j->p, o, j->x0 + b * NX, j->x_term + b * NX, j->lamb_in ? j->lamb_in[b] : j->p->lamb,
+                       j->u_init ? j->u_init + b * NU * N : NULL, j->uvar ? j->uvar + b * NU * N : NULL, j->xvar ? j->xvar + b * NX * (N + 1) : NULL,
                        j->lamb_out ? j->lamb_out + b : NULL, j->iters ? j->iters + b : NULL);
       if (r) atomic_store(&j->bad, 1);
     }
@@ -319,9 +327,9 @@ static void* batch_worker(void* arg) {
 }
 
 int orc_ilqr_batch(const i2lqr_params* p, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
-                   const i2lqr_obstacle* obs, int64_t n_obs, double* uvar, double* xvar, double* lamb_out,
-                   int32_t* iters, int nthreads) {
-  batch_job job = {p, B, x0, x_term, lamb_in, obs, n_obs, uvar, xvar, lamb_out, iters, 0, 0};
+                   const i2lqr_obstacle* obs, int64_t n_obs, const double* u_init, double* uvar, double* xvar,
+                   double* lamb_out, int32_t* iters, int nthreads) {
+  batch_job job = {p, B, x0, x_term, lamb_in, u_init, obs, n_obs, uvar, xvar, lamb_out, iters, 0, 0};
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];

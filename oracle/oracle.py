@@ -63,7 +63,7 @@ def ilqr(params, x0, x_term, lamb_in, obstacle=None):
     return uvar, xvar, lamb_out.value, iters.value
 
 
-def ilqr_batch(params, x0, x_term, lamb_in, obs=None, nthreads=1):
+def ilqr_batch(params, x0, x_term, lamb_in, obs=None, nthreads=1, uvar_init=None):
     """B independent solves on `nthreads` host threads; obs: None, one Obstacle, or a structured array (B)."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     x_term = np.ascontiguousarray(x_term, dtype=np.float64)
@@ -74,8 +74,9 @@ def ilqr_batch(params, x0, x_term, lamb_in, obs=None, nthreads=1):
     lamb_out = np.zeros(B)
     iters = np.zeros(B, dtype=np.int32)
     optr, n_obs = _obs_ptr(obs)
+    uinit = None if uvar_init is None else np.ascontiguousarray(uvar_init, dtype=np.float64).reshape(B, 2, N)
     rc = lib().orc_ilqr_batch(
-        C.byref(params), C.c_int64(B), _d(x0), _d(x_term), _d(lamb_in), optr, C.c_int64(n_obs),
+        C.byref(params), C.c_int64(B), _d(x0), _d(x_term), _d(lamb_in), optr, C.c_int64(n_obs), _d(uinit),
         _d(uvar), _d(xvar), _d(lamb_out), iters.ctypes.data_as(_ip), C.c_int(nthreads),
     )  # fmt: skip
     assert rc == 0

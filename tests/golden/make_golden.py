@@ -38,19 +38,23 @@ def _param(ref, N, K=8, L=1, Q=None, R=None):
     return ref.base.iLqrParam(**kw)
 
 
-def _run_flat_group(ref, N, B, seed, lamb_choices=None, with_obstacle=True, Q=None, R=None):
+def _run_flat_group(ref, N, B, seed, lamb_choices=None, with_obstacle=True, Q=None, R=None, warm=False):
     data = synth.flat_candidates(B, num_horizon=N, seed=seed)
     rng = np.random.default_rng(seed + 1)
     if lamb_choices is not None:
         data["lamb_in"] = rng.choice(np.array(lamb_choices, dtype=np.float64), size=B)
     param = _param(ref, N, Q=Q, R=R)
+    # warm start of a direct ilqr() call; some inputs lie outside the clip bounds on purpose
+    data["uvar_init"] = rng.standard_normal((B, 2, N)) * np.array([1.5, 0.9])[None, :, None] if warm else np.zeros((B, 2, N))
     uvar = np.zeros((B, 2, N))
     xvar = np.zeros((B, 4, N + 1))
     lamb_out = np.zeros(B)
     iters = np.zeros(B, dtype=np.int32)
     for b in range(B):
         obstacle = ref.make_obstacle(data["obs"][b], data["mode"][b]) if with_obstacle else None
-        u, x, lo, it = ref.call_ilqr(param, N, data["x0"][b], data["x_term"][b], obstacle, float(data["lamb_in"][b]))
+        u, x, lo, it = ref.call_ilqr(
+            param, N, data["x0"][b], data["x_term"][b], obstacle, float(data["lamb_in"][b]), uvar_init=data["uvar_init"][b]
+        )
         uvar[b], xvar[b], lamb_out[b], iters[b] = u, x, lo, it
     out = dict(data)
     out.update(uvar=uvar, xvar=xvar, lamb_out=lamb_out, iters=iters, N=np.int32(N), has_obstacle=np.int32(with_obstacle))
@@ -69,6 +73,7 @@ def make_flat():
     groups["n6_qr"] = _run_flat_group(
         ref, 6, 48, synth.SEED + 13, Q=np.diag([0.1, 0.1, 0.05, 0.01]), R=np.diag([0.05, 0.05])
     )
+    groups["n6_warm"] = _run_flat_group(ref, 6, 48, synth.SEED + 14, warm=True)
     for N, B in ((2, 16), (10, 24), (25, 16), (50, 8), (100, 4), (200, 4)):
         groups["n%d" % N] = _run_flat_group(ref, N, B, synth.SEED + N)
     flat = {}

@@ -94,10 +94,10 @@ class Reference:
         with contextlib.redirect_stdout(io.StringIO()):
             yield
 
-    def call_ilqr(self, param, N, x0, x_term, obstacle, lamb_in, dt=1):
+    def call_ilqr(self, param, N, x0, x_term, obstacle, lamb_in, dt=1, uvar_init=None):
         """One `ilqr()` call set up exactly as calc_input does (iterative_ilqr/utils/base.py:405-426)."""
         base = self.base
-        uvar = np.zeros((2, N))
+        uvar = np.zeros((2, N)) if uvar_init is None else np.array(uvar_init, dtype=np.float64).copy()
         xvar = np.zeros((4, N + 1))
         xvar[:, 0] = x0
         xtarget = np.array([0, 0, 0, 0])

@@ -6,7 +6,7 @@ import numpy as np
 from ilqr_iterative_tasks_b200 import _abi
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FLAT_GROUPS = ["n6", "n6_lamb", "n6_noobs", "n6_qr", "n2", "n10", "n25", "n50", "n100", "n200"]
+FLAT_GROUPS = ["n6", "n6_lamb", "n6_noobs", "n6_qr", "n6_warm", "n2", "n10", "n25", "n50", "n100", "n200"]
 STEP_SCENARIOS = ["stock", "moving_up", "moving_left", "pytest", "static_big", "k64"]
 # FP64 parity bar of BASELINE.json north_star: states / inputs / costs within 1e-9 relative
 RTOL = 1e-9
@@ -21,7 +21,9 @@ def flat_group(g, grp):
     N = int(g[grp + "/N"])
     p = _abi.default_params(num_horizon=N, matrix_Q=g[grp + "/Q"], matrix_R=g[grp + "/R"])
     obs = _abi.obstacle_array(g[grp + "/obs"], g[grp + "/mode"]) if int(g[grp + "/has_obstacle"]) else None
-    inp = {k: g[grp + "/" + k] for k in ("x0", "x_term", "lamb_in")}
+    inp = {k: g[grp + "/" + k] for k in ("x0", "x_term", "lamb_in", "uvar_init")}
+    if not inp["uvar_init"].any():
+        inp["uvar_init"] = None
     exp = {k: g[grp + "/" + k] for k in ("uvar", "xvar", "lamb_out", "iters")}
     return p, inp, obs, exp
 

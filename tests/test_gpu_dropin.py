@@ -1,0 +1,109 @@
+"""The reference-facing Python API (drop-in module tree) on the GPU: `utils.base.iLqr`,
+`control.iterative_ilqr.ilqr`, and the device-resident episode batch, against golden closed-loop runs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_SCRIPT = r"""
+import sys, json, numpy as np
+sys.path.insert(0, {root!r})
+import ilqr_iterative_tasks_b200 as pkg
+pkg.install_dropin()
+from utils import base            # the drop-in, same import line as the reference's scripts
+from control.iterative_ilqr import ilqr
+g = np.load({golden!r})
+K, L, N = int(g["K"]), int(g["L"]), int(g["N"])
+dt = 1
+ego = base.KineticBicycle(False, system_param=base.KineticBicycleParam())
+ego.set_state([0, 0, 0, 0]); ego.set_timestep(dt); ego.get_traj(); ego.set_zero_noise()
+obstacle = base.Obstacle(31, -3, 8, 6)
+param = base.iLqrParam(num_ss_points=K, num_ss_iter=L, timestep=dt, num_horizon=N)
+ctrl = base.iLqr(param, obstacle=obstacle, system_param=base.KineticBicycleParam())
+ctrl.add_trajectory(ego.xcl, ego.ucl); ctrl.set_timestep(dt); ego.set_ctrl_policy(ctrl)
+sim = base.Simulator(); sim.set_robotic(ego); sim.set_timestep(dt); sim.set_traj()
+laps = int(g["n_laps"]) - 1
+for lap in range(laps):
+    sim.sim(lap, sim_time=50)
+    ego.data["state"][-1][-1, :] = ego.xcl[-1, :]
+    ctrl.add_trajectory(ego.data["state"][-1], ego.data["input"][-1])
+res = {{"lens": [int(len(s)) for s in ego.data["state"]]}}
+err = 0.0
+for i in range(laps):
+    ref = g["lap%d" % (i + 1)]
+    got = np.asarray(ego.data["state"][i])
+    if got.shape == ref.shape:
+        err = max(err, float(np.abs(got - ref).max()))
+res["max_abs_err"] = err
+res["ref_lens"] = [int(len(g["lap%d" % (i + 1)])) for i in range(laps)]
+# select_close_ss through the class API
+idx = ctrl.select_close_ss(ctrl.iter - 1, ego.xcl[3])
+res["knn_ok"] = bool(len(idx) == K)
+# L1 function with a warm start
+gf = np.load({flat!r})
+b = 5
+p2 = base.iLqrParam(num_horizon=6, timestep=1)
+ob = base.Obstacle(*[float(v) for v in gf["n6_warm/obs"][b][:4]], spd=float(gf["n6_warm/obs"][b][4]) if int(gf["n6_warm/mode"][b]) else None,
+                   timestep=1, moving_option=int(gf["n6_warm/mode"][b]) or None)
+xv = np.zeros((4, 7)); xv[:, 0] = gf["n6_warm/x0"][b]
+u, x, lamb = ilqr(p2, 6, np.zeros(4), 1, ob, base.KineticBicycleParam(), gf["n6_warm/x_term"][b], np.zeros((4, 7)),
+                  gf["n6_warm/uvar_init"][b].copy(), xv, float(gf["n6_warm/lamb_in"][b]))
+res["l1_err"] = float(np.abs(x - gf["n6_warm/xvar"][b]).max())
+res["l1_lamb_ok"] = bool(lamb == float(gf["n6_warm/lamb_out"][b]))
+print("RESULT" + json.dumps(res))
+"""
+
+
+def test_dropin_closed_loop_stock_scenario():
+    """iterative_ilqr/tests/ilqr_test.py semantics through the drop-in classes; closed loop, so compared at a
+    looser tolerance than the per-step replays (rounding differences grow along the lap)."""
+    import json
+
+    code = _SCRIPT.format(root=ROOT, golden=os.path.join(H.GOLDEN, "steps_stock.npz"), flat=os.path.join(H.GOLDEN, "ilqr_flat.npz"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT")][0][6:])
+    assert res["lens"] == res["ref_lens"], res
+    assert res["max_abs_err"] < 1e-6, res
+    assert res["knn_ok"] and res["l1_lamb_ok"] and res["l1_err"] < 1e-9 * 50, res
+
+
+@pytest.mark.parametrize("name", ["stock", "moving_up"])
+def test_episode_batch_matches_reference_closed_loop(name):
+    """K4: device-resident closed loop for several identical episodes == the reference's lap lengths and
+    trajectories (closed-loop tolerance)."""
+    from ilqr_iterative_tasks_b200 import _abi, episodes
+
+    g = H.load("steps_%s.npz" % name)
+    p = H.step_params(g)
+    E = 3
+    laps = int(g["n_laps"]) - 1
+    first = g["lap_first_step"]
+
+    def obstacle_for(lap):
+        s = int(first[lap])
+        o = H.step_obstacle(g, s)
+        arr = np.zeros(E, dtype=_abi.OBSTACLE_DTYPE)
+        if o is not None:
+            arr[:] = np.frombuffer(bytes(o), dtype=_abi.OBSTACLE_DTYPE)[0]
+        return arr
+
+    eb = episodes.EpisodeBatch(p, np.zeros((E, 4)), obstacles=obstacle_for(0), initial_lap=g["lap0"])
+    for lap in range(laps):
+        eb.set_obstacles(obstacle_for(lap))
+        lens, lx, lu = eb.run_lap(want_traj=True)
+        ref = g["lap%d" % (lap + 1)]
+        assert (lens == len(ref) - 1).all(), (lap, lens, len(ref) - 1)
+        assert (eb.status() == 0).all()
+        for e in range(E):
+            got = lx[e, : len(ref)]
+            assert np.abs(got - ref).max() < 1e-6, (lap, e, np.abs(got - ref).max())
+            assert np.abs(lu[e, : len(ref) - 1] - g["lap_inputs%d" % (lap + 1)]).max() < 1e-6
+    eb.close()

@@ -1,0 +1,214 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle and the
+golden vectors minted from the Python reference.  Discrete results exact; floats within 1e-9 relative."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from ilqr_iterative_tasks_b200 import engine
+
+    return engine
+
+
+def _check_flat(out, exp, tag=""):
+    bad_it = int((out["iters"] != exp["iters"]).sum())
+    bad_l = int((out["lamb_out"] != exp["lamb_out"]).sum())
+    ex = H.rel_err(out["xvar"], exp["xvar"]).max()
+    eu = H.rel_err(out["uvar"], exp["uvar"]).max()
+    assert bad_it == 0, "%s: %d iteration-count mismatches" % (tag, bad_it)
+    assert bad_l == 0, "%s: %d lamb_out mismatches" % (tag, bad_l)
+    assert ex <= H.RTOL and eu <= H.RTOL, "%s: rel err x %.3e u %.3e" % (tag, ex, eu)
+
+
+@pytest.mark.parametrize("grp", H.FLAT_GROUPS)
+def test_flat_batch_vs_reference_golden(eng_mod, grp):
+    g = H.load("ilqr_flat.npz")
+    p, inp, obs, exp = H.flat_group(g, grp)
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(inp["x0"], inp["x_term"], inp["lamb_in"], obs, uvar_init=inp["uvar_init"])
+    _check_flat(out, exp, grp)
+    st = e.last_stats()
+    assert st["solves"] == len(exp["iters"]) and st["ilqr_iterations"] == int(exp["iters"].sum())
+    assert st["launches"] == 1
+    e.close()
+
+
+def test_flat_batch_vs_oracle_sample(eng_mod):
+    """Config 5 generator, a 4096-candidate sample against the oracle."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    d = synth.flat_candidates(4096, 6)
+    p = _abi.default_params()
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
+    same = (out["iters"] == iters) & (out["lamb_out"] == lamb)
+    # a chaotic iteration may flip an accept/reject on a last-bit difference of sin/cos/exp; none expected here
+    assert same.mean() >= 0.999, "discrete path diverged for %d of 4096" % int((~same).sum())
+    ex = H.rel_err(out["xvar"][same], x[same]).max()
+    eu = H.rel_err(out["uvar"][same], u[same]).max()
+    assert ex <= H.RTOL and eu <= H.RTOL
+    e.close()
+
+
+def test_shared_and_absent_obstacle(eng_mod):
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    d = synth.flat_candidates(512, 6, seed=5)
+    p = _abi.default_params()
+    e = eng_mod.Engine(p)
+    one = _abi.Obstacle(3.0, 0.5, 3.0, 2.0, 0.4, 1, 1)
+    out = e.solve_batch(d["x0"], d["x_term"], None, one)
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], np.ones(512), one, nthreads=8)
+    _check_flat(out, {"iters": iters, "lamb_out": lamb, "xvar": x, "uvar": u}, "shared obstacle")
+    out = e.solve_batch(d["x0"], d["x_term"], None, None)
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], np.ones(512), None, nthreads=8)
+    _check_flat(out, {"iters": iters, "lamb_out": lamb, "xvar": x, "uvar": u}, "no obstacle")
+    # empty batch is a no-op
+    out = e.solve_batch(np.zeros((0, 4)), np.zeros((0, 4)))
+    assert out["xvar"].shape == (0, 4, 7)
+    e.close()
+
+
+def test_knn_vs_reference_golden(eng_mod):
+    from ilqr_iterative_tasks_b200 import _abi
+
+    g = H.load("knn.npz")
+    for c in range(int(g["n_cases"])):
+        lap, K = g["c%d/lap" % c], int(g["c%d/K" % c])
+        p = _abi.default_params(num_horizon=2, num_ss_points=K)
+        e = eng_mod.Engine(p, n_episodes=1, lap_capacity=max(8, lap.shape[0]))
+        e.add_lap(0, lap)
+        idx = e.select_knn(0, 0, g["c%d/x0" % c], K)
+        assert np.array_equal(idx, g["c%d/idx" % c]), "case %d" % c
+        e.close()
+
+
+@pytest.mark.parametrize("name", H.STEP_SCENARIOS)
+def test_controller_step_vs_reference_golden(eng_mod, name):
+    """Every recorded `calc_input` of a closed-loop reference run, replayed from its recorded inputs."""
+    g = H.load("steps_%s.npz" % name)
+    p = H.step_params(g)
+    N = p.num_horizon
+    e = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+    added = 0
+    for si, s in enumerate(g["solve_ids"]):
+        n_laps = int(g["step/n_laps"][s])
+        while added < n_laps:
+            e.add_lap(0, g["lap%d" % added])
+            added += 1
+        e.set_obstacle(0, H.step_obstacle(g, s))
+        out = e.solve_step(g["step/x"][s].reshape(1, 4))
+        tr = e.step_trace(1)
+        tag = "%s step %d" % (name, s)
+        assert np.array_equal(tr["sel_idx"][0], g["solve/sel_idx"][si]), tag
+        assert np.array_equal(tr["cand_iters"][0], g["solve/c_iters"][si]), tag
+        assert np.array_equal(np.nan_to_num(tr["cand_lamb"][0], nan=-1.0), np.nan_to_num(g["solve/c_lamb"][si], nan=-1.0)), tag
+        assert bool(out["shrink"][0]) == (int(g["step/num_horizon_after"][s]) < N), tag
+        xr, ur = g["solve/x_pred"][si], g["solve/u_pred"][si]
+        assert np.abs(out["x_pred"][0] - xr).max() <= H.RTOL * max(1.0, np.abs(xr).max()), tag
+        assert np.abs(out["u_pred"][0] - ur).max() <= H.RTOL * max(1.0, np.abs(ur).max()), tag
+        assert np.abs(out["u"][0] - g["step/u"][s]).max() <= H.RTOL * 2, tag
+    e.close()
+
+
+def test_controller_step_synthetic_horizons(eng_mod):
+    """Config 4b: one full calc_input per horizon (shared-memory and global-scratch kernels)."""
+    from ilqr_iterative_tasks_b200 import _abi
+
+    g = H.load("step_synth.npz")
+    for N in g["horizons"]:
+        k = "n%d/" % N
+        p = _abi.default_params(num_horizon=int(N), num_ss_points=8, num_ss_iter=1)
+        e = eng_mod.Engine(p, n_episodes=1, lap_capacity=g[k + "lap"].shape[0])
+        e.add_lap(0, g[k + "lap"])
+        e.set_obstacle(0, _abi.Obstacle(*[float(v) for v in g[k + "obs"]], int(g[k + "mode"]), 1))
+        out = e.solve_step(g[k + "x"].reshape(1, 4))
+        tr = e.step_trace(1)
+        assert np.array_equal(tr["cand_iters"][0].ravel(), g[k + "c_iters"]), "N=%d" % N
+        assert np.array_equal(tr["cand_lamb"][0].ravel(), g[k + "c_lamb"]), "N=%d" % N
+        assert np.abs(out["x_pred"][0] - g[k + "x_pred"]).max() <= H.RTOL * max(1.0, np.abs(g[k + "x_pred"]).max())
+        assert np.abs(out["u_pred"][0] - g[k + "u_pred"]).max() <= H.RTOL * 2
+        e.close()
+
+
+def test_multi_episode_step_equals_single(eng_mod):
+    """E episodes in one call == E single-episode calls (the batch axis must not couple episodes)."""
+    g = H.load("steps_stock.npz")
+    p = H.step_params(g)
+    ids = [int(s) for s in g["solve_ids"][[3, 20, 40, 60, 61, 62]]]
+    E = len(ids)
+    big = eng_mod.Engine(p, n_episodes=E, lap_capacity=128)
+    singles = []
+    for k, s in enumerate(ids):
+        one = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+        for l in range(int(g["step/n_laps"][s])):
+            big.add_lap(k, g["lap%d" % l])
+            one.add_lap(0, g["lap%d" % l])
+        big.set_obstacle(k, H.step_obstacle(g, s))
+        one.set_obstacle(0, H.step_obstacle(g, s))
+        singles.append(one.solve_step(g["step/x"][s].reshape(1, 4)))
+        one.close()
+    out = big.solve_step(g["step/x"][ids])
+    for k in range(E):
+        for key in ("u", "x_pred", "u_pred", "winner_lap", "winner_rank", "winner_idx", "winner_cost", "shrink"):
+            assert np.array_equal(out[key][k], singles[k][key][0]), (k, key)
+    big.close()
+
+
+def test_full_size_properties(eng_mod):
+    """BASELINE config 5 at full size (2^20 candidates): size-independent properties.
+    determinism (bit-identical reruns), permutation equivariance (results do not depend on which lane or in
+    which order a candidate is scheduled), counters consistent, every solve terminated by a reference rule."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+
+    B = 1 << 20
+    d = synth.flat_candidates(B, 6)
+    p = _abi.default_params()
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e = eng_mod.Engine(p)
+    a = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    st = e.last_stats()
+    assert st["solves"] == B and st["ilqr_iterations"] == int(a["iters"].sum())
+    assert a["iters"].min() >= 1 and a["iters"].max() <= p.max_ilqr_iter
+    assert np.isfinite(a["xvar"]).all() and np.isfinite(a["uvar"]).all()
+    assert (np.abs(a["uvar"][:, 0]) <= p.a_max).all() and (np.abs(a["uvar"][:, 1]) <= p.delta_lim).all()
+    assert np.array_equal(a["xvar"][:, :, 0], d["x0"])
+    b = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    perm = np.random.default_rng(1).permutation(B)
+    c = e.solve_batch(d["x0"][perm], d["x_term"][perm], d["lamb_in"][perm], obs[perm])
+    for k in a:
+        assert np.array_equal(a[k][perm], c[k]), k
+    # lamb_out is lamb_in times a power of ten reached through the reference's /10, *10 sequence
+    ratio = np.log10(a["lamb_out"])
+    assert np.abs(ratio - np.round(ratio)).max() < 1e-9
+    e.close()
+
+
+def test_error_paths(eng_mod):
+    from ilqr_iterative_tasks_b200 import _abi
+
+    p = _abi.default_params()
+    e = eng_mod.Engine(p, n_episodes=1, lap_capacity=32)
+    with pytest.raises(RuntimeError):
+        e.add_lap(0, np.zeros((6, 4)))  # not longer than the horizon (utils/base.py:348)
+    with pytest.raises(RuntimeError):
+        e.add_lap(0, np.zeros((64, 4)))  # over capacity
+    with pytest.raises(RuntimeError):
+        e.solve_step(np.zeros((1, 4)))  # no lap stored
+    with pytest.raises(RuntimeError):
+        e.set_obstacle(0, _abi.Obstacle(0, 0, 1, 1, 0.5, 0, 1))  # spd != 0 without moving_option
+    bad = _abi.default_params(matrix_Q=np.array([[0, 1, 0, 0]] + [[0] * 4] * 3, dtype=float))
+    with pytest.raises(RuntimeError):
+        eng_mod.Engine(bad)
+    e.close()

@@ -16,7 +16,7 @@ from tests import helpers as H
 def test_ilqr_matches_reference(grp):
     g = H.load("ilqr_flat.npz")
     p, inp, obs, exp = H.flat_group(g, grp)
-    u, x, lamb, iters = oracle.ilqr_batch(p, inp["x0"], inp["x_term"], inp["lamb_in"], obs, nthreads=4)
+    u, x, lamb, iters = oracle.ilqr_batch(p, inp["x0"], inp["x_term"], inp["lamb_in"], obs, nthreads=4, uvar_init=inp["uvar_init"])
     assert np.array_equal(iters, exp["iters"])
     assert np.array_equal(lamb, exp["lamb_out"])  # bit-exact: same /10, *10 sequence on doubles
     assert H.rel_err(x, exp["xvar"]).max() <= H.RTOL

@@ -18,7 +18,9 @@
 //   Vxx symmetric (10 unique entries), l_uu diagonal and l_x / l_xx confined to the position block when
 //   matrix_Q = matrix_R = 0 (the reference's default, kQR = false).
 #pragma once
+#ifndef I2LQR_HOST_BUILD
 #include <cuda_runtime.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -37,6 +39,7 @@ struct KParams {
   double a_max, d_lim; // clip bounds
   double eps, lamb0, lamb_factor, max_lamb;
   double cg, ch, cq2;  // control barrier: q1*q2, q1*q2^2, q2
+  double ca_lo, cd_lo; // exp(-2*q2*a_max), exp(-2*q2*delta_lim)
   double og, oh, oq2;  // obstacle barrier: q1*q2, q1*q2^2, q2
   double one_margin;   // 1 + safety_margin
   double xtarget[4];
@@ -50,10 +53,17 @@ struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
   int32_t moving_option, present;
 };
 
-// Per-lane scratch column: element e lives at base[e * stride].
-struct Scratch {
+// Per-lane scratch column: element e lives at base[e * stride].  In shared memory the stride is the block
+// size, a compile-time constant, so element offsets fold into the LDS/STS immediates.
+template <int kStride>
+struct SmemScratch {
   double* base;
-  int stride;
+  __device__ __forceinline__ double ld(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void st(int e, double v) const { base[e * kStride] = v; }
+};
+struct GlobalScratch {
+  double* base;
+  long long stride;
   __device__ __forceinline__ double ld(int e) const { return base[(size_t)e * stride]; }
   __device__ __forceinline__ void st(int e, double v) const { base[(size_t)e * stride] = v; }
 };
@@ -109,11 +119,21 @@ __device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c
   h11 = c2 * (hd1 * hd1);
 }
 
-// Regularised inverse of the 2x2 Quu (iterative_ilqr.py:118-123): symmetric eigen-decomposition by one
-// Jacobi rotation (numerically stable when |b| << |a-d|), negative eigenvalues clamped to
-// zero, + lamb, V diag(1/e) V^T.
+// Regularised inverse of the 2x2 Quu (iterative_ilqr.py:118-123): eigen-decompose, clamp negative
+// eigenvalues to zero, add lamb, V diag(1/e) V^T.  When both eigenvalues are non-negative (always, in the
+// reference's own runs: SURVEY.md 8a, a5) the clamp is the identity and the result is exactly
+// (Quu + lamb I)^-1, evaluated here in closed form with one reciprocal.  Otherwise the symmetric
+// eigen-decomposition is done by one Jacobi rotation (stable when |b| << |a-d|).
 __device__ __forceinline__ void quu_inverse(double a, double b, double d, double lamb, double& i00, double& i01,
                                             double& i11) {
+  if (a * d - b * b >= 0.0 && a + d >= 0.0) {
+    const double al = a + lamb, dl = d + lamb;
+    const double r = 1.0 / (al * dl - b * b);
+    i00 = dl * r;
+    i01 = -b * r;
+    i11 = al * r;
+    return;
+  }
   double c = 1.0, s = 0.0, e1 = a, e2 = d;
   if (b != 0.0) {
     double tau = (d - a) / (2.0 * b);
@@ -139,7 +159,7 @@ __device__ __forceinline__ double terminal_cost(const KParams& p, const Cand& c,
 // Candidate start (utils/base.py:405-410 + the first rollout of iterative_ilqr.py:32-48).  With u0 == null the
 // inputs are zero (what calc_input passes): heading and speed stay put and every stage reuses
 // cos/sin(theta_0).  u0 (2,N) is the warm start of a direct `ilqr()` call.
-template <bool kQR>
+template <bool kQR, class Scratch>
 __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const Scratch& s, const double* u0) {
   const int N = p.N;
   double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
@@ -175,7 +195,7 @@ __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const 
 }
 
 // Backward Riccati pass over the current trajectory; leaves the gains in the new-slots.
-template <bool kQR>
+template <bool kQR, class Scratch>
 __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, const Scratch& s) {
   const int N = p.N;
   const double dt = p.dt;
@@ -226,8 +246,10 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     // ---- stage cost derivatives: ilqr_helper.py:25-55, input barriers :83-103
     double lu0, lu1, luu00, luu11, luu01 = 0.0;
     {
-      const double e1 = exp(p.cq2 * (ua - p.a_max)), e2 = exp(p.cq2 * (-p.a_max - ua));
-      const double e3 = exp(p.cq2 * (ud - p.d_lim)), e4 = exp(p.cq2 * (-p.d_lim - ud));
+      // the lower-bound barriers are the reciprocals of the upper-bound ones up to a constant:
+      // exp(q2(-ubar - u)) = exp(-2 q2 ubar) / exp(q2(u - ubar)) -- two exp + two reciprocals instead of four exp
+      const double e1 = exp(p.cq2 * (ua - p.a_max)), e3 = exp(p.cq2 * (ud - p.d_lim));
+      const double e2 = p.ca_lo * (1.0 / e1), e4 = p.cd_lo * (1.0 / e3);
       lu0 = p.cg * e1 - p.cg * e2;
       lu1 = p.cg * e3 - p.cg * e4;
       luu00 = p.ch * e1 + p.ch * e2;
@@ -331,7 +353,7 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
 // Full-step forward pass (iterative_ilqr.py:133-160).  Consumes the gains, leaves the trial trajectory in
 // the new-slots, returns cost_new; Jtarget is the cost the reference would recompute for the trial
 // trajectory at the top of its next iteration (stage cost about xtarget, iterative_ilqr.py:43-48).
-template <bool kQR>
+template <bool kQR, class Scratch>
 __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, const Scratch& s, double& Jtarget) {
   const int N = p.N;
   double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
@@ -382,7 +404,7 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 
 // One iLQR iteration with the accept / reject and lambda schedule of iterative_ilqr.py:74-84.
 // Returns true when the candidate's loop ends.
-template <bool kQR>
+template <bool kQR, class Scratch>
 __device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s) {
   backward_pass<kQR>(p, c, s);
   double Jt;
@@ -418,6 +440,7 @@ __device__ __forceinline__ double relax_cost(const KParams& p, const double* xN,
 }
 
 // Result in the reference's array layout: xvar (4, N+1), uvar (2, N), time on the last axis.
+template <class Scratch>
 __device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c, const Scratch& s, double* xvar,
                                                 double* uvar) {
   const int N = p.N;

@@ -6,6 +6,8 @@
 //   K3  winner_kernel   lexicographic winner + result gather (utils/base.py:462-478)
 //   K4  plant_kernel    batched closed-loop episode step (utils/base.py:157-213, 708-726)
 #pragma once
+#include <type_traits>
+
 #include "ilqr_core.cuh"
 
 namespace i2lqr {
@@ -64,16 +66,18 @@ struct Work {
 // code -- one iteration -- on up to 32 different candidates regardless of how many iterations each needs.
 enum : int { ST_FETCH = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
 
+constexpr int kSolveThreads = 128;  // block size of solve_kernel == shared-memory scratch stride
+
 template <bool kQR, bool kSmem>
-__global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
+__global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
   extern __shared__ double smem[];
-  Scratch s;
-  if (kSmem) {
+  using ScratchT = typename std::conditional<kSmem, SmemScratch<kSolveThreads>, GlobalScratch>::type;
+  ScratchT s;
+  if constexpr (kSmem) {
     s.base = smem + threadIdx.x;
-    s.stride = blockDim.x;
   } else {
     s.base = w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    s.stride = (int)w.gstride;
+    s.stride = w.gstride;
   }
   const unsigned lane = threadIdx.x & 31u;
   const int N = p.N;
@@ -144,6 +148,10 @@ __global__ void __launch_bounds__(128) solve_kernel(const __grid_constant__ KPar
       init_candidate<kQR>(p, c, s, (w.mode == 0 && w.u_init != nullptr) ? w.u_init + item * 2 * N : nullptr);
       state = ST_RUN;
     }
+    // Every lane of the warp is still in this loop (finished lanes idle until the collective break), so a
+    // full-mask barrier is legal here; without it the freshly initialised lanes run the whole iteration
+    // below as a separate divergent pass (measured: 15.5 of 32 lanes active per issued instruction).
+    __syncwarp();
     // ---- RUN
     if (state == ST_RUN) {
       const bool done = ilqr_iteration<kQR>(p, c, s);

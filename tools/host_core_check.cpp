@@ -1,0 +1,48 @@
+// Developer tool (not product, not shipped in any library): compiles csrc/ilqr_core.cuh for the HOST so that
+// algorithmic rewrites of the device code (closed-form inverse, fused exponentials, ...) can be checked
+// against the golden vectors here, where there is no GPU.  Host libm and host FMA contraction differ from the
+// device by ulps, so this only screens for discrete-path regressions before a GPU run.
+//   g++ -O2 -mfma -ffp-contract=fast -std=c++17 -shared -fPIC -o /tmp/libhostcore.so tools/host_core_check.cpp
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+static inline void sincos_host(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+#define sincos sincos_host
+#define I2LQR_HOST_BUILD 1
+#include "../ilqr_iterative_tasks_b200/csrc/ilqr_core.cuh"
+#include "../ilqr_iterative_tasks_b200/csrc/kparams.h"
+using namespace i2lqr;
+
+extern "C" const char* host_fill_kparams(const i2lqr_params* p, KParams* k) { return fill_kparams(*p, k); }
+extern "C" int host_kparams_size() { return (int)sizeof(KParams); }
+
+extern "C" int host_solve(const KParams* kp, int64_t B, const double* x0, const double* xt, const double* lamb_in,
+                          const i2lqr_obstacle* obs, int64_t n_obs, const double* u_init, double* uvar, double* xvar,
+                          double* lamb_out, int32_t* iters) {
+  const KParams& p = *kp;
+  std::vector<double> mem(scratch_doubles(p.N));
+  GlobalScratch s{mem.data(), 1};
+  for (int64_t b = 0; b < B; ++b) {
+    Cand c;
+    for (int i = 0; i < 4; ++i) { c.x0[i] = x0[b * 4 + i]; c.xt[i] = xt[b * 4 + i]; }
+    sincos(c.x0[3], &c.s0, &c.c0);
+    c.lamb = lamb_in ? lamb_in[b] : p.lamb0;
+    load_obstacle(c, n_obs == 0 ? nullptr : reinterpret_cast<const DevObstacle*>(n_obs == 1 ? obs : obs + b));
+    const double* u0 = u_init ? u_init + b * 2 * p.N : nullptr;
+    if (p.has_qr) {
+      init_candidate<true>(p, c, s, u0);
+      while (!ilqr_iteration<true>(p, c, s)) {}
+    } else {
+      init_candidate<false>(p, c, s, u0);
+      while (!ilqr_iteration<false>(p, c, s)) {}
+    }
+    store_candidate(p, c, s, xvar + b * 4 * (p.N + 1), uvar + b * 2 * p.N);
+    lamb_out[b] = c.lamb;
+    iters[b] = c.iters;
+  }
+  return 0;
+}

@@ -6,8 +6,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/i2lqr.h"
@@ -71,8 +73,11 @@ struct i2lqr_handle {
   // statistics of the last compute call
   double last_ms = 0;
   long long last_launches = 0, last_iters = 0, last_solves = 0;
-  // work-fetch counter + stats (3 x u64)
+  // statistics words + work-fetch counters
   DevBuf<unsigned long long> ctl;
+  int ctl_next = 0;
+  cudaStream_t aux[2] = {nullptr, nullptr};  // extra streams of the chunked host pipeline
+  cudaEvent_t aux_done[2] = {nullptr, nullptr};
   DevBuf<double> gscratch;
   // flat batch staging
   DevBuf<double> b_x0, b_xt, b_lamb, b_uvar, b_xvar, b_lamb_out, b_uinit;
@@ -106,23 +111,35 @@ int make_kparams(const i2lqr_params& p, KParams* k) {
 
 constexpr int kThreads = kSolveThreads;
 constexpr size_t kSmemLimit = 227 * 1024;
+constexpr int kCtlSlots = 16;   // fetch counters: one per launch that may be in flight concurrently
+constexpr int kCtlWords = 2 + kCtlSlots;  // ctl[0] executed iterations, ctl[1] finished solves, then the counters
+constexpr int kAuxStreams = 2;
 
 // Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
 int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st) {
   const KParams& kp = h->kp;
   const size_t per_block = (size_t)kThreads * scratch_doubles(kp.N) * sizeof(double);
   const bool use_smem = per_block <= kSmemLimit;
-  CU(h->ctl.ensure(4));
-  CU(cudaMemsetAsync(h->ctl.p, 0, sizeof(unsigned long long), st));
-  w.counter = h->ctl.p;
-  w.stats = h->ctl.p + 1;
+  CU(h->ctl.ensure(kCtlWords));
+  const int slot = h->ctl_next;
+  h->ctl_next = (slot + 1) % kCtlSlots;
+  CU(cudaMemsetAsync(h->ctl.p + 2 + slot, 0, sizeof(unsigned long long), st));
+  w.counter = h->ctl.p + 2 + slot;
+  w.stats = h->ctl.p;
   const long long lanes_needed = w.mode == 0 ? w.n_items : w.n_items;  // one lane per item
   long long blocks_needed = (lanes_needed + kThreads - 1) / kThreads;
   if (blocks_needed < 1) blocks_needed = 1;
-  auto kern = kp.has_qr ? (use_smem ? solve_kernel<true, true> : solve_kernel<true, false>)
-                        : (use_smem ? solve_kernel<false, true> : solve_kernel<false, false>);
+  auto pick = [&](auto mode) {
+    constexpr int M = decltype(mode)::value;
+    return kp.has_qr ? (use_smem ? solve_kernel<true, true, M> : solve_kernel<true, false, M>)
+                     : (use_smem ? solve_kernel<false, true, M> : solve_kernel<false, false, M>);
+  };
+  auto kern = w.mode == 0 ? pick(std::integral_constant<int, 0>()) : pick(std::integral_constant<int, 1>());
   int per_sm = 0;
   size_t smem = use_smem ? per_block : 0;
+  // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
+  static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
+  if (use_smem && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
   if (use_smem) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
@@ -141,8 +158,8 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st) {
 
 int begin_stats(i2lqr_handle* h, cudaStream_t st) {
   h->last_launches = 0;
-  CU(h->ctl.ensure(4));
-  CU(cudaMemsetAsync(h->ctl.p, 0, 4 * sizeof(unsigned long long), st));
+  CU(h->ctl.ensure(kCtlWords));
+  CU(cudaMemsetAsync(h->ctl.p, 0, 2 * sizeof(unsigned long long), st));
   CU(cudaEventRecord(h->ev0, st));
   return 0;
 }
@@ -150,7 +167,7 @@ int begin_stats(i2lqr_handle* h, cudaStream_t st) {
 // Waits for `st` and reads back the device-side counters and the ev0..ev1 kernel time.
 int finish_stats(i2lqr_handle* h, cudaStream_t st) {
   unsigned long long s[2];
-  CU(cudaMemcpyAsync(s, h->ctl.p + 1, sizeof s, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s, h->ctl.p, sizeof s, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -259,7 +276,12 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
-  CU(h->ctl.ensure(4));
+  for (int i = 0; i < kAuxStreams; ++i) {
+    CU(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming));
+  }
+  CU(h->ctl.ensure(kCtlWords));
+  CU(cudaMemset(h->ctl.p, 0, kCtlWords * sizeof(unsigned long long)));
   if (n_episodes > 0) {
     if (lap_capacity <= p->num_horizon) return fail("lap_capacity must exceed num_horizon");
     const size_t ss_n = (size_t)h->E * h->L * 4 * h->Tcap;
@@ -302,89 +324,119 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (h->set.lap_count) cudaFree(h->set.lap_count);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  for (int i = 0; i < kAuxStreams; ++i) {
+    if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
+    if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+  }
   cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ flat batch
+namespace {
+int check_batch_args(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const i2lqr_obstacle* obs,
+                     int64_t n_obs) {
+  if (!h) return fail("null handle");
+  if (B < 0) return fail("negative batch");
+  if (B > 0 && (!x0 || !x_term)) return fail("x0 and x_term are required");
+  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
+  if (n_obs != 0 && !obs) return fail("obs is null but n_obs != 0");
+  return 0;
+}
+
+// One launch over rows [lo, lo+n) of device-resident arrays.
+int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const double* x_term, const double* lamb_in,
+                const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
+                double* lamb_out, int32_t* iters, cudaStream_t st) {
+  const int N = h->kp.N;
+  Work w{};
+  w.mode = 0;
+  w.n_items = n;
+  w.x0 = x0 + lo * 4;
+  w.x_term = x_term + lo * 4;
+  w.lamb_in = lamb_in ? lamb_in + lo : nullptr;
+  w.obs = reinterpret_cast<const DevObstacle*>(obs) + (n_obs > 1 ? lo : 0);
+  w.n_obs = n_obs > 1 ? n : n_obs;
+  w.u_init = uvar_init ? uvar_init + lo * 2 * N : nullptr;
+  w.uvar = uvar ? uvar + lo * 2 * N : nullptr;
+  w.xvar = xvar ? xvar + lo * 4 * (N + 1) : nullptr;
+  w.lamb_out = lamb_out ? lamb_out + lo : nullptr;
+  w.iters = iters ? iters + lo : nullptr;
+  return launch_solve(h, w, st);
+}
+}  // namespace
+
 int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
                              const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar,
                              double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream) {
-  if (!h) return fail("null handle");
-  if (B < 0) return fail("negative batch");
-  if (B > 0 && (!x0 || !x_term)) return fail("x0 and x_term are required");
-  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
-  if (n_obs != 0 && !obs) return fail("obs is null but n_obs != 0");
+  if (check_batch_args(h, B, x0, x_term, obs, n_obs)) return 1;
   CU(cudaSetDevice(h->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   if (begin_stats(h, st)) return 1;
-  if (B > 0) {
-    Work w{};
-    w.mode = 0;
-    w.n_items = B;
-    w.x0 = x0;
-    w.x_term = x_term;
-    w.lamb_in = lamb_in;
-    w.obs = reinterpret_cast<const DevObstacle*>(obs);
-    w.n_obs = n_obs;
-    w.u_init = uvar_init;
-    w.uvar = uvar;
-    w.xvar = xvar;
-    w.lamb_out = lamb_out;
-    w.iters = iters;
-    if (launch_solve(h, w, st)) return 1;
-  }
+  if (B > 0 && launch_flat(h, 0, B, x0, x_term, lamb_in, obs, n_obs, uvar_init, uvar, xvar, lamb_out, iters, st)) return 1;
   return end_stats(h, st, false);
 }
 
+// Host-pointer form.  The batch is cut into chunks that flow through three streams -- H2D of chunk i+1, the
+// solve of chunk i and D2H of chunk i-1 overlap (full-duplex PCIe when the caller's buffers are pinned;
+// pageable buffers still work, the copies then serialise).
 int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
                       const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
                       double* lamb_out, int32_t* iters) {
-  if (!h) return fail("null handle");
-  if (B < 0) return fail("negative batch");
-  if (B > 0 && (!x0 || !x_term)) return fail("x0 and x_term are required");
-  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
-  if (n_obs != 0 && !obs) return fail("obs is null but n_obs != 0");
+  if (check_batch_args(h, B, x0, x_term, obs, n_obs)) return 1;
   CU(cudaSetDevice(h->device));
-  cudaStream_t st = h->stream;
   const int N = h->kp.N;
   const size_t nb = (size_t)B;
   if (B > 0) {
     CU(h->b_x0.ensure(nb * 4));
     CU(h->b_xt.ensure(nb * 4));
-    CU(cudaMemcpyAsync(h->b_x0.p, x0, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(h->b_xt.p, x_term, nb * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (lamb_in) {
-      CU(h->b_lamb.ensure(nb));
-      CU(cudaMemcpyAsync(h->b_lamb.p, lamb_in, nb * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
-    if (n_obs) {
-      CU(h->b_obs.ensure((size_t)n_obs));
-      CU(cudaMemcpyAsync(h->b_obs.p, obs, (size_t)n_obs * sizeof(DevObstacle), cudaMemcpyHostToDevice, st));
-    }
-    if (uvar_init) {
-      CU(h->b_uinit.ensure(nb * 2 * N));
-      CU(cudaMemcpyAsync(h->b_uinit.p, uvar_init, nb * 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
+    if (lamb_in) CU(h->b_lamb.ensure(nb));
+    if (n_obs) CU(h->b_obs.ensure((size_t)n_obs));
+    if (uvar_init) CU(h->b_uinit.ensure(nb * 2 * N));
     if (uvar) CU(h->b_uvar.ensure(nb * 2 * N));
     if (xvar) CU(h->b_xvar.ensure(nb * 4 * (N + 1)));
     if (lamb_out) CU(h->b_lamb_out.ensure(nb));
     if (iters) CU(h->b_iters.ensure(nb));
   }
-  if (i2lqr_solve_batch_device(h, B, h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr,
-                               reinterpret_cast<const i2lqr_obstacle*>(h->b_obs.p), n_obs,
-                               uvar_init ? h->b_uinit.p : nullptr, uvar ? h->b_uvar.p : nullptr,
-                               xvar ? h->b_xvar.p : nullptr, lamb_out ? h->b_lamb_out.p : nullptr,
-                               iters ? h->b_iters.p : nullptr, st))
-    return 1;
+  cudaStream_t main = h->stream;
+  if (begin_stats(h, main)) return 1;
   if (B > 0) {
-    if (uvar) CU(cudaMemcpyAsync(uvar, h->b_uvar.p, nb * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (xvar) CU(cudaMemcpyAsync(xvar, h->b_xvar.p, nb * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (lamb_out) CU(cudaMemcpyAsync(lamb_out, h->b_lamb_out.p, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (iters) CU(cudaMemcpyAsync(iters, h->b_iters.p, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_obs == 1) CU(cudaMemcpyAsync(h->b_obs.p, obs, sizeof(DevObstacle), cudaMemcpyHostToDevice, main));
+    CU(cudaEventRecord(h->ev0, main));  // aux streams start after the statistics reset (and the shared obstacle)
+    cudaStream_t streams[1 + kAuxStreams] = {main, h->aux[0], h->aux[1]};
+    for (int i = 0; i < kAuxStreams; ++i) CU(cudaStreamWaitEvent(h->aux[i], h->ev0, 0));
+    const int64_t min_chunk = 32768;
+    int64_t n_chunks = std::min<int64_t>(12, std::max<int64_t>(1, B / min_chunk));
+    const int64_t chunk = (B + n_chunks - 1) / n_chunks;
+    const auto* d_obs = reinterpret_cast<const i2lqr_obstacle*>(h->b_obs.p);
+    for (int64_t c = 0, lo = 0; lo < B; ++c, lo += chunk) {
+      const int64_t n = std::min<int64_t>(chunk, B - lo);
+      const size_t un = (size_t)n, ulo = (size_t)lo;
+      cudaStream_t st = streams[c % (1 + kAuxStreams)];
+      CU(cudaMemcpyAsync(h->b_x0.p + ulo * 4, x0 + ulo * 4, un * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(h->b_xt.p + ulo * 4, x_term + ulo * 4, un * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (lamb_in) CU(cudaMemcpyAsync(h->b_lamb.p + ulo, lamb_in + ulo, un * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (n_obs > 1) CU(cudaMemcpyAsync(h->b_obs.p + ulo, obs + ulo, un * sizeof(DevObstacle), cudaMemcpyHostToDevice, st));
+      if (uvar_init)
+        CU(cudaMemcpyAsync(h->b_uinit.p + ulo * 2 * N, uvar_init + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (launch_flat(h, lo, n, h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr, d_obs, n_obs,
+                      uvar_init ? h->b_uinit.p : nullptr, uvar ? h->b_uvar.p : nullptr, xvar ? h->b_xvar.p : nullptr,
+                      lamb_out ? h->b_lamb_out.p : nullptr, iters ? h->b_iters.p : nullptr, st))
+        return 1;
+      if (uvar) CU(cudaMemcpyAsync(uvar + ulo * 2 * N, h->b_uvar.p + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (xvar)
+        CU(cudaMemcpyAsync(xvar + ulo * 4 * (N + 1), h->b_xvar.p + ulo * 4 * (N + 1), un * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (lamb_out) CU(cudaMemcpyAsync(lamb_out + ulo, h->b_lamb_out.p + ulo, un * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (iters) CU(cudaMemcpyAsync(iters + ulo, h->b_iters.p + ulo, un * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kAuxStreams; ++i) {
+      CU(cudaEventRecord(h->aux_done[i], h->aux[i]));
+      CU(cudaStreamWaitEvent(main, h->aux_done[i], 0));
+    }
   }
-  return finish_stats(h, st);
+  CU(cudaEventRecord(h->ev1, main));  // here: whole pipeline (copies included), see i2lqr_last_stats
+  return finish_stats(h, main);
 }
 
 // -------------------------------------------------------------------------------------------- safe set

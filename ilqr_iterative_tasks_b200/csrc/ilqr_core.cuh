@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fastmath.cuh"
+
 namespace i2lqr {
 
 // Parameter block in kernel-argument (constant-bank) space, derived on the host from i2lqr_params.
@@ -110,7 +112,7 @@ __device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c
   double d0 = px - cx, d1 = py - cy;
   double h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
   double hd0 = (-2.0 * c.oP0) * d0, hd1 = (-2.0 * c.oP1) * d1;
-  double e = exp(p.oq2 * h);
+  double e = exp_fast(p.oq2 * h);
   double c1 = p.og * e, c2 = p.oh * e;
   g0 = c1 * hd0;
   g1 = c1 * hd1;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void quu_inverse(double a, double b, double d, double
                                             double& i11) {
   if (a * d - b * b >= 0.0 && a + d >= 0.0) {
     const double al = a + lamb, dl = d + lamb;
-    const double r = 1.0 / (al * dl - b * b);
+    const double r = rcp_fast(al * dl - b * b);
     i00 = dl * r;
     i01 = -b * r;
     i11 = al * r;
@@ -159,12 +161,13 @@ __device__ __forceinline__ double terminal_cost(const KParams& p, const Cand& c,
 // Candidate start (utils/base.py:405-410 + the first rollout of iterative_ilqr.py:32-48).  With u0 == null the
 // inputs are zero (what calc_input passes): heading and speed stay put and every stage reuses
 // cos/sin(theta_0).  u0 (2,N) is the warm start of a direct `ilqr()` call.
-template <bool kQR, class Scratch>
+template <bool kQR, int kN, class Scratch>
 __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const Scratch& s, const double* u0) {
-  const int N = p.N;
+  const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
   double cs = c.c0, sn = c.s0;
   double J = 0.0;
+#pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
     double ua = 0.0, ud = 0.0;
     if (u0 != nullptr) {
@@ -180,7 +183,7 @@ __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const 
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
-    if (u0 != nullptr) sincos(x[3], &sn, &cs);
+    if (u0 != nullptr) sincos_fast(x[3], &sn, &cs);
     s.st(I2_CUR(k) + 0, ua);
     s.st(I2_CUR(k) + 1, ud);
     s.st(I2_CUR(k) + 2, x[0]);
@@ -195,9 +198,9 @@ __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const 
 }
 
 // Backward Riccati pass over the current trajectory; leaves the gains in the new-slots.
-template <bool kQR, class Scratch>
+template <bool kQR, int kN, class Scratch>
 __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, const Scratch& s) {
-  const int N = p.N;
+  const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   const double dt = p.dt;
   // ---- value function at the horizon end: get_cost_final (ilqr_helper.py:106-150)
   double xN[4];
@@ -222,6 +225,7 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     V01 += h01;
     V11 += h11;
   }
+#pragma unroll(kN > 0 ? kN : 1)
   for (int k = N - 1; k >= 0; --k) {
     // ---- trajectory at stage k
     const double ua = s.ld(I2_CUR(k) + 0), ud = s.ld(I2_CUR(k) + 1);
@@ -248,8 +252,8 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     {
       // the lower-bound barriers are the reciprocals of the upper-bound ones up to a constant:
       // exp(q2(-ubar - u)) = exp(-2 q2 ubar) / exp(q2(u - ubar)) -- two exp + two reciprocals instead of four exp
-      const double e1 = exp(p.cq2 * (ua - p.a_max)), e3 = exp(p.cq2 * (ud - p.d_lim));
-      const double e2 = p.ca_lo * (1.0 / e1), e4 = p.cd_lo * (1.0 / e3);
+      const double e1 = exp_fast(p.cq2 * (ua - p.a_max)), e3 = exp_fast(p.cq2 * (ud - p.d_lim));
+      const double e2 = p.ca_lo * rcp_fast(e1), e4 = p.cd_lo * rcp_fast(e3);
       lu0 = p.cg * e1 - p.cg * e2;
       lu1 = p.cg * e3 - p.cg * e4;
       luu00 = p.ch * e1 + p.ch * e2;
@@ -353,12 +357,13 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
 // Full-step forward pass (iterative_ilqr.py:133-160).  Consumes the gains, leaves the trial trajectory in
 // the new-slots, returns cost_new; Jtarget is the cost the reference would recompute for the trial
 // trajectory at the top of its next iteration (stage cost about xtarget, iterative_ilqr.py:43-48).
-template <bool kQR, class Scratch>
+template <bool kQR, int kN, class Scratch>
 __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, const Scratch& s, double& Jtarget) {
-  const int N = p.N;
+  const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
   double cs = c.c0, sn = c.s0;
   double Jn = 0.0, Jt = 0.0;
+#pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
     double xo[4];
     if (k == 0) {
@@ -387,7 +392,7 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
-    sincos(x[3], &sn, &cs);
+    sincos_fast(x[3], &sn, &cs);
     s.st(I2_NEW(N, k) + 0, ua);
     s.st(I2_NEW(N, k) + 1, ud);
     s.st(I2_NEW(N, k) + 2, x[0]);
@@ -404,16 +409,17 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 
 // One iLQR iteration with the accept / reject and lambda schedule of iterative_ilqr.py:74-84.
 // Returns true when the candidate's loop ends.
-template <bool kQR, class Scratch>
+template <bool kQR, int kN, class Scratch>
 __device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s) {
-  backward_pass<kQR>(p, c, s);
+  backward_pass<kQR, kN>(p, c, s);
   double Jt;
-  const double Jn = forward_pass<kQR>(p, c, s, Jt);
+  const double Jn = forward_pass<kQR, kN>(p, c, s, Jt);
   c.iters++;
   bool done = false;
   if (Jn < c.J) {
-    const int N = p.N;
-    for (int k = 0; k < N; ++k) {
+    const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
+  #pragma unroll(kN > 0 ? kN : 1)
+  for (int k = 0; k < N; ++k) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) s.st(I2_CUR(k) + i, s.ld(I2_NEW(N, k) + i));
     }
@@ -440,20 +446,22 @@ __device__ __forceinline__ double relax_cost(const KParams& p, const double* xN,
 }
 
 // Result in the reference's array layout: xvar (4, N+1), uvar (2, N), time on the last axis.
-template <class Scratch>
+template <int kN, class Scratch>
 __device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c, const Scratch& s, double* xvar,
                                                 double* uvar) {
-  const int N = p.N;
+  const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   if (xvar) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) xvar[i * (N + 1)] = c.x0[i];
-    for (int k = 0; k < N; ++k) {
+  #pragma unroll(kN > 0 ? kN : 1)
+  for (int k = 0; k < N; ++k) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xvar[i * (N + 1) + k + 1] = s.ld(I2_CUR(k) + 2 + i);
     }
   }
   if (uvar) {
-    for (int k = 0; k < N; ++k) {
+  #pragma unroll(kN > 0 ? kN : 1)
+  for (int k = 0; k < N; ++k) {
       uvar[k] = s.ld(I2_CUR(k) + 0);
       uvar[N + k] = s.ld(I2_CUR(k) + 1);
     }

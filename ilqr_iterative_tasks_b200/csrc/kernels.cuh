@@ -60,15 +60,18 @@ struct Work {
 };
 
 // ------------------------------------------------------------------------------------------------ K2
-// Persistent kernel.  Every lane runs a small state machine: FETCH an item with a warp-aggregated atomic,
-// INIT a candidate, RUN one iLQR iteration per trip, finalise, and either take the next candidate of its
-// chain (lambda carried, utils/base.py:393,414) or fetch again.  A warp therefore always executes the same
-// code -- one iteration -- on up to 32 different candidates regardless of how many iterations each needs.
-enum : int { ST_FETCH = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
-
+// Persistent kernel, one lane per candidate.  Every lane runs a small state machine -- take a candidate,
+// INIT it, RUN one iLQR iteration per trip of the warp loop, finalise -- so a warp always executes the same
+// code (one iteration) on up to 32 different candidates regardless of how many iterations each needs
+// (1..150).  kMode 0: flat batch; the NEXT candidate of every lane (index from a warp-aggregated atomic and
+// its inputs) is prefetched into registers while the current one iterates, so the global-load latency of
+// the few lanes that switch candidates in a trip never stalls the warp.  kMode 1: lambda chains of a
+// controller step; a lane walks the K candidates of its (episode, lap) in rank order carrying lambda
+// (utils/base.py:393,414).
+enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
 constexpr int kSolveThreads = 128;  // block size of solve_kernel == shared-memory scratch stride
 
-template <bool kQR, bool kSmem>
+template <bool kQR, bool kSmem, int kMode>
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
   extern __shared__ double smem[];
   using ScratchT = typename std::conditional<kSmem, SmemScratch<kSolveThreads>, GlobalScratch>::type;
@@ -79,94 +82,132 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
     s.base = w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     s.stride = w.gstride;
   }
+  constexpr int kN = 0;  // stage loops stay rolled: the fully unrolled N=6 body measured 1.4x slower (I-cache, spills)
   const unsigned lane = threadIdx.x & 31u;
   const int N = p.N;
   Cand c;
-  int state = ST_FETCH;
+  int state = ST_NEED;
   long long item = 0;
-  int rank = 0, cnt = 0;        // position in the chain
-  int ep = 0, lrel = 0, slot = 0, T = 0;
-  const double* lap = nullptr;
-  long long jsel = 0;
   unsigned long long my_iters = 0, my_solves = 0;
 
-  for (;;) {
-    // ---- FETCH
-    const unsigned want = __ballot_sync(0xffffffffu, state == ST_FETCH);
-    if (want) {
-      unsigned long long base = 0;
-      const int leader = __ffs(want) - 1;
-      if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (state == ST_FETCH) {
-        item = (long long)(base + __popc(want & ((1u << lane) - 1u)));
-        if (item >= w.n_items) {
-          state = ST_DONE;
-        } else if (w.mode == 0) {
-          rank = 0;
-          cnt = 1;
-          c.lamb = w.lamb_in ? w.lamb_in[item] : p.lamb0;
-          load_obstacle(c, w.n_obs == 0 ? nullptr : (w.n_obs == 1 ? w.obs : w.obs + item));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) c.x0[i] = w.x0[item * 4 + i];
-          sincos(c.x0[3], &c.s0, &c.c0);
-          state = ST_INIT;
-        } else {
-          ep = (int)(item / w.set.L);
-          lrel = (int)(item % w.set.L);
-          cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
-          if (cnt == 0) {
-            state = ST_FETCH;  // unused lap slot or inactive episode: take another item next trip
+  if constexpr (kMode == 0) {
+    // ---- prefetched next candidate
+    bool have_next = false, exhausted = false;
+    long long n_item = 0;
+    double n_x0[4], n_xt[4], n_lamb = p.lamb0;
+    DevObstacle n_obs;
+    n_obs.present = 0;
+    for (;;) {
+      // (a) lanes without a pending candidate fetch an index and issue its loads (consumed trips later)
+      const unsigned want = __ballot_sync(0xffffffffu, !have_next && !exhausted);
+      if (want) {
+        unsigned long long base = 0;
+        const int leader = __ffs(want) - 1;
+        if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (!have_next && !exhausted) {
+          n_item = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+          if (n_item >= w.n_items) {
+            exhausted = true;
           } else {
-            const int count = w.set.lap_count[ep];
-            const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
-            slot = (min_iter + lrel) % w.set.L;
-            T = w.set.lap_len[(size_t)ep * w.set.L + slot];
-            lap = w.set.lap(ep, slot);
-            rank = 0;
-            c.lamb = p.lamb0;  // utils/base.py:393
-            load_obstacle(c, w.ep_obs + ep);
+            have_next = true;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) c.x0[i] = w.x[(size_t)ep * 4 + i];
-            sincos(c.x0[3], &c.s0, &c.c0);
-            state = ST_INIT;
+            for (int i = 0; i < 4; ++i) {
+              n_x0[i] = w.x0[n_item * 4 + i];
+              n_xt[i] = w.x_term[n_item * 4 + i];
+            }
+            if (w.lamb_in) n_lamb = w.lamb_in[n_item];
+            if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : n_item];
           }
         }
       }
-    }
-    if (__all_sync(0xffffffffu, state == ST_DONE)) break;
-    // ---- INIT
-    if (state == ST_INIT) {
-      if (w.mode == 0) {
+      // (b) lanes that need a candidate take the prefetched one
+      if (state == ST_NEED) {
+        if (have_next) {
+          item = n_item;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.xt[i] = w.x_term[item * 4 + i];
-      } else {
+          for (int i = 0; i < 4; ++i) {
+            c.x0[i] = n_x0[i];
+            c.xt[i] = n_xt[i];
+          }
+          c.lamb = n_lamb;
+          load_obstacle(c, w.n_obs != 0 ? &n_obs : nullptr);
+          sincos_fast(c.x0[3], &c.s0, &c.c0);
+          init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
+          have_next = false;
+          state = ST_RUN;
+        } else if (exhausted) {
+          state = ST_DONE;
+        }
+      }
+      if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+      // Every lane of the warp is still in this loop (finished lanes idle until the collective break), so the
+      // full-mask vote above also reconverges the warp before the iteration; without that the freshly
+      // initialised lanes run the whole iteration as a separate divergent pass (measured: 15.5 of 32
+      // lanes active per issued instruction).
+      if (state == ST_RUN) {
+        if (ilqr_iteration<kQR, kN>(p, c, s)) {
+          my_iters += (unsigned long long)c.iters;
+          my_solves += 1;
+          store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
+          if (w.lamb_out) w.lamb_out[item] = c.lamb;
+          if (w.iters) w.iters[item] = c.iters;
+          state = ST_NEED;
+        }
+      }
+    }
+  } else {
+    int rank = 0, cnt = 0;  // position in the chain
+    int ep = 0, lrel = 0, slot = 0, T = 0;
+    const double* lap = nullptr;
+    long long jsel = 0;
+    for (;;) {
+      const unsigned want = __ballot_sync(0xffffffffu, state == ST_NEED);
+      if (want) {
+        unsigned long long base = 0;
+        const int leader = __ffs(want) - 1;
+        if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (state == ST_NEED) {
+          item = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+          if (item >= w.n_items) {
+            state = ST_DONE;
+          } else {
+            ep = (int)(item / w.set.L);
+            lrel = (int)(item % w.set.L);
+            cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
+            if (cnt > 0) {  // else: unused lap slot or inactive episode, take another item next trip
+              const int count = w.set.lap_count[ep];
+              const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
+              slot = (min_iter + lrel) % w.set.L;
+              T = w.set.lap_len[(size_t)ep * w.set.L + slot];
+              lap = w.set.lap(ep, slot);
+              rank = 0;
+              c.lamb = p.lamb0;  // utils/base.py:393
+              load_obstacle(c, w.ep_obs + ep);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) c.x0[i] = w.x[(size_t)ep * 4 + i];
+              sincos_fast(c.x0[3], &c.s0, &c.c0);
+              state = ST_INIT;
+            }
+          }
+        }
+      }
+      if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+      if (state == ST_INIT) {
         jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
 #pragma unroll
         for (int i = 0; i < 4; ++i) c.xt[i] = lap[(size_t)i * w.set.Tcap + jsel];
+        init_candidate<kQR, kN>(p, c, s, nullptr);
+        state = ST_RUN;
       }
-      init_candidate<kQR>(p, c, s, (w.mode == 0 && w.u_init != nullptr) ? w.u_init + item * 2 * N : nullptr);
-      state = ST_RUN;
-    }
-    // Every lane of the warp is still in this loop (finished lanes idle until the collective break), so a
-    // full-mask barrier is legal here; without it the freshly initialised lanes run the whole iteration
-    // below as a separate divergent pass (measured: 15.5 of 32 lanes active per issued instruction).
-    __syncwarp();
-    // ---- RUN
-    if (state == ST_RUN) {
-      const bool done = ilqr_iteration<kQR>(p, c, s);
-      if (done) {
-        my_iters += (unsigned long long)c.iters;
-        my_solves += 1;
-        if (w.mode == 0) {
-          store_candidate(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr,
-                          w.uvar ? w.uvar + item * 2 * N : nullptr);
-          if (w.lamb_out) w.lamb_out[item] = c.lamb;
-          if (w.iters) w.iters[item] = c.iters;
-          state = ST_FETCH;
-        } else {
+      __syncwarp();  // reconverge before the iteration (see kMode 0)
+      if (state == ST_RUN) {
+        if (ilqr_iteration<kQR, kN>(p, c, s)) {
+          my_iters += (unsigned long long)c.iters;
+          my_solves += 1;
           const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
-          store_candidate(p, c, s, w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
+          store_candidate<kN>(p, c, s, w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
           double xN[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) xN[i] = s.ld(I2_CUR(N - 1) + 2 + i);
@@ -175,7 +216,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
           w.cand_lamb[tslot] = c.lamb;
           w.cand_iters[tslot] = c.iters;
           ++rank;
-          state = rank < cnt ? ST_INIT : ST_FETCH;  // lambda is carried to the lap's next candidate
+          state = rank < cnt ? ST_INIT : ST_NEED;  // lambda is carried to the lap's next candidate
         }
       }
     }
@@ -413,7 +454,7 @@ __global__ void episode_post_kernel(EpisodeState s, const __grid_constant__ KPar
   // plant: kinetic_bicycle (systems/kinetic_bicycle.py:10-27), noise off
   double* x = s.x + (size_t)e * 4;
   double sn, cs;
-  sincos(x[3], &sn, &cs);
+  sincos_fast(x[3], &sn, &cs);
   const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
   const double x0 = x[0] + cs * sd, x1 = x[1] + sn * sd, x2 = x[2] + ua * p.dt, x3 = x[3] + ud * p.dt;
   x[0] = x0;

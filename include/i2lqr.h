@@ -144,8 +144,10 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
 int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status);
 
 /* ---- instrumentation -------------------------------------------------------------------------------- */
-/* Device time (CUDA events on the handle's stream) of the kernels of the last compute call, the number
- * of kernels it launched, and the iLQR iterations it executed (for the roofline). */
+/* Device time (CUDA events on the stream of the call) of the last compute call, the number of kernels it
+ * launched, and the iLQR iterations / solves it executed (device-side counters, for the roofline).  For
+ * i2lqr_solve_batch the time spans the whole chunked pipeline (copies included); for the *_device form and
+ * the controller step it spans the kernels only. */
 int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int64_t* ilqr_iterations,
                      int64_t* solves);
 

@@ -10,8 +10,6 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-static inline void sincos_host(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
-#define sincos sincos_host
 #define I2LQR_HOST_BUILD 1
 #include "../ilqr_iterative_tasks_b200/csrc/ilqr_core.cuh"
 #include "../ilqr_iterative_tasks_b200/csrc/kparams.h"
@@ -29,20 +27,23 @@ extern "C" int host_solve(const KParams* kp, int64_t B, const double* x0, const 
   for (int64_t b = 0; b < B; ++b) {
     Cand c;
     for (int i = 0; i < 4; ++i) { c.x0[i] = x0[b * 4 + i]; c.xt[i] = xt[b * 4 + i]; }
-    sincos(c.x0[3], &c.s0, &c.c0);
+    sincos_fast(c.x0[3], &c.s0, &c.c0);
     c.lamb = lamb_in ? lamb_in[b] : p.lamb0;
     load_obstacle(c, n_obs == 0 ? nullptr : reinterpret_cast<const DevObstacle*>(n_obs == 1 ? obs : obs + b));
     const double* u0 = u_init ? u_init + b * 2 * p.N : nullptr;
     if (p.has_qr) {
-      init_candidate<true>(p, c, s, u0);
-      while (!ilqr_iteration<true>(p, c, s)) {}
+      init_candidate<true, 0>(p, c, s, u0);
+      while (!ilqr_iteration<true, 0>(p, c, s)) {}
     } else {
-      init_candidate<false>(p, c, s, u0);
-      while (!ilqr_iteration<false>(p, c, s)) {}
+      init_candidate<false, 0>(p, c, s, u0);
+      while (!ilqr_iteration<false, 0>(p, c, s)) {}
     }
-    store_candidate(p, c, s, xvar + b * 4 * (p.N + 1), uvar + b * 2 * p.N);
+    store_candidate<0>(p, c, s, xvar + b * 4 * (p.N + 1), uvar + b * 2 * p.N);
     lamb_out[b] = c.lamb;
     iters[b] = c.iters;
   }
   return 0;
 }
+
+extern "C" void host_exp_fast(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = exp_fast(x[i]); }
+extern "C" void host_sincos_fast(const double* x, double* s, double* c, int64_t n) { for (int64_t i = 0; i < n; ++i) sincos_fast(x[i], s + i, c + i); }

@@ -34,6 +34,24 @@ def solve(p, x0, xt, lamb, obs, uinit=None):
     return u, x, lo, it
 
 
+def ulps(a, ref):
+    return np.abs(a - ref) / np.spacing(np.abs(ref))
+
+
+rng = np.random.default_rng(0)
+for lo, hi in ((-12, 3), (-700, -600), (-50, 50), (700, 709)):
+    xs = rng.uniform(lo, hi, 200000)
+    ys = np.empty_like(xs)
+    lib.host_exp_fast(xs.ctypes.data_as(dp), ys.ctypes.data_as(dp), C.c_int64(xs.size))
+    ref = np.exp(xs)
+    ok = ref > 1e-300
+    print("exp_fast [%g,%g]: max ulp vs numpy %.2f" % (lo, hi, ulps(ys[ok], ref[ok]).max()))
+for span in (1.0, 10.0, 1000.0, 9.9e4):
+    xs = rng.uniform(-span, span, 200000)
+    s = np.empty_like(xs); c = np.empty_like(xs)
+    lib.host_sincos_fast(xs.ctypes.data_as(dp), s.ctypes.data_as(dp), c.ctypes.data_as(dp), C.c_int64(xs.size))
+    print("sincos_fast |x|<%g: max ulp sin %.2f cos %.2f" % (span, ulps(s, np.sin(xs)).max(), ulps(c, np.cos(xs)).max()))
+
 g = H.load("ilqr_flat.npz")
 for grp in H.FLAT_GROUPS:
     p, inp, obs, exp = H.flat_group(g, grp)

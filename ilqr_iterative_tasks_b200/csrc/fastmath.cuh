@@ -56,39 +56,49 @@ I2_HD double rcp_fast(double x) {
 #endif
 }
 
-// exp(x), x clamped to [-745, 709]: k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite), degree-13 Taylor
-// polynomial on |r| <= ln2/2 (truncation < 2^-57), scaled by 2^k in two halves so that results in the
-// denormal range degrade gracefully to 0.
-I2_HD double exp_fast(double x) {
-  x = x < -745.0 ? -745.0 : (x > 709.0 ? 709.0 : x);
+// Polynomial coefficients live in constant memory so that they reach the FP64 pipe as c[bank][offset]
+// operands instead of being rebuilt from 32-bit immediates inside the stage loops.
+#ifdef __CUDACC__
+#define I2_CONST __constant__
+#else
+#define I2_CONST static const
+#endif
+I2_CONST double kExpEven[6] = {1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 40320.0, 1.0 / 720.0, 1.0 / 24.0, 0.5};
+I2_CONST double kExpOdd[6] = {1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 362880.0, 1.0 / 5040.0, 1.0 / 120.0, 1.0 / 6.0};
+I2_CONST double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                            -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01};
+I2_CONST double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+                            2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+
+// exp(x) for x already inside (-708, 709): k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite),
+// degree-13 Taylor polynomial on |r| <= ln2/2 (truncation < 2^-57, even / odd halves evaluated side by
+// side to halve the dependent chain), scaled by 2^k in two halves so that results in the denormal range
+// degrade gracefully to 0.
+I2_HD double exp_fast_bounded(double x) {
   const double magic = 6755399441055744.0;  // 2^52 + 2^51
   const double t = fma_(x, 1.4426950408889634, magic);
   const int k = (int)(double_to_bits(t) & 0xffffffffLL);  // low word of the magic sum = rint(x log2 e)
   const double kf = t - magic;
   double r = fma_(kf, -6.93147180369123816490e-01, x);
   r = fma_(kf, -1.90821492927058770002e-10, r);
-  // Estrin-style split keeps the dependent chain short: even / odd halves in r^2
   const double r2 = r * r;
-  double pe = 1.0 / 479001600.0;             // 1/12!
-  pe = fma_(pe, r2, 1.0 / 3628800.0);        // 1/10!
-  pe = fma_(pe, r2, 1.0 / 40320.0);          // 1/8!
-  pe = fma_(pe, r2, 1.0 / 720.0);            // 1/6!
-  pe = fma_(pe, r2, 1.0 / 24.0);             // 1/4!
-  pe = fma_(pe, r2, 0.5);                    // 1/2!
-  double po = 1.0 / 6227020800.0;            // 1/13!
-  po = fma_(po, r2, 1.0 / 39916800.0);       // 1/11!
-  po = fma_(po, r2, 1.0 / 362880.0);         // 1/9!
-  po = fma_(po, r2, 1.0 / 5040.0);           // 1/7!
-  po = fma_(po, r2, 1.0 / 120.0);            // 1/5!
-  po = fma_(po, r2, 1.0 / 6.0);              // 1/3!
+  double pe = kExpEven[0], po = kExpOdd[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+    pe = fma_(pe, r2, kExpEven[i]);
+    po = fma_(po, r2, kExpOdd[i]);
+  }
   // exp(r) = 1 + r + r^2 (pe + r po)
   const double q = fma_(po, r, pe);
-  const double p = fma_(q * r2, 1.0, r) + 1.0;
+  const double pr = fma_(q, r2, r) + 1.0;
   const int k1 = k >> 1, k2 = k - k1;
   const double s1 = bits_to_double((long long)(k1 + 1023) << 52);
   const double s2 = bits_to_double((long long)(k2 + 1023) << 52);
-  return (p * s1) * s2;
+  return (pr * s1) * s2;
 }
+// x <= ~700 guaranteed by the caller, arbitrary below (underflows to 0)
+I2_HD double exp_fast_lo(double x) { return exp_fast_bounded(fmax(x, -745.0)); }
+I2_HD double exp_fast(double x) { return exp_fast_bounded(fmin(fmax(x, -745.0), 709.0)); }
 
 // sin and cos of x for |x| <= 1e5 (larger or non-finite arguments take the library path): quadrant
 // reduction with a three-term pi/2 (k * P1, k * P2 exact for |k| < 2^20), fdlibm kernel polynomials
@@ -111,21 +121,14 @@ I2_HD void sincos_fast(double x, double* sn, double* cs) {
   r = fma_(kf, -6.07710050630396597660e-11, r);          // pio2_2  (next 33 bits)
   r = fma_(kf, -2.02226624879595063154e-21, r);          // pio2_3
   const double z = r * r;
-  // __kernel_sin
-  double ps = 1.58969099521155010221e-10;
-  ps = fma_(ps, z, -2.50507602534068634195e-08);
-  ps = fma_(ps, z, 2.75573137070700676789e-06);
-  ps = fma_(ps, z, -1.98412698298579493134e-04);
-  ps = fma_(ps, z, 8.33333333332248946124e-03);
-  ps = fma_(ps, z, -1.66666666666666324348e-01);
+  // __kernel_sin / __kernel_cos polynomials, evaluated side by side
+  double ps = kSinC[0], pc = kCosC[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i) {
+    ps = fma_(ps, z, kSinC[i]);
+    pc = fma_(pc, z, kCosC[i]);
+  }
   const double s = fma_(ps * z, r, r);
-  // __kernel_cos
-  double pc = -1.13596475577881948265e-11;
-  pc = fma_(pc, z, 2.08757232129817482790e-09);
-  pc = fma_(pc, z, -2.75573143513906633035e-07);
-  pc = fma_(pc, z, 2.48015872894767294178e-05);
-  pc = fma_(pc, z, -1.38888888888741095749e-03);
-  pc = fma_(pc, z, 4.16666666666666019037e-02);
   const double c = fma_(pc * z, z, fma_(-0.5, z, 1.0));
   const bool swap = (k & 1) != 0;
   const double ss = swap ? c : s, cc = swap ? s : c;

@@ -83,8 +83,9 @@ struct Cand {
   double x0[4], c0, s0;  // initial state, cos / sin of its heading
   double xt[4];          // terminal target (safe-set point)
   double lamb, J;        // LM regularisation, cost of the current trajectory
-  double ox, oy, oP0, oP1, ospd;  // obstacle centre, 1/width^2, 1/height^2, speed
-  int omode, opresent;
+  // obstacle: centre, 1/width^2, 1/height^2, per-stage drift of the centre (left / up), barrier scales.
+  // `obstacle is None` is encoded as zero scales and zero P so that the same straight-line code runs.
+  double ox, oy, oP0, oP1, osx, osy, og, oh;
   int iters;
 };
 
@@ -104,16 +105,16 @@ __device__ __forceinline__ double quad2(const double* M, double a, double b) {
 
 // Obstacle ellipse barrier at position (px,py), `step` stages ahead: gradient (2) and Gauss-Newton Hessian
 // (00,01,11) of q1*exp(q2*h), h = 1 + margin - d^T P d   (ilqr_helper.py:32-51,118-149, :59-64).
+// The centre is (x_o - step*spd, y_o) when moving left, (x_o, y_o + step*spd) when moving up.
 __device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c, double px, double py, int step,
                                                  double& g0, double& g1, double& h00, double& h01, double& h11) {
-  double cx = c.ox, cy = c.oy;
-  if (c.omode == 1) cy = c.oy + step * c.ospd;
-  if (c.omode == 2) cx = c.ox - step * c.ospd;
-  double d0 = px - cx, d1 = py - cy;
-  double h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
-  double hd0 = (-2.0 * c.oP0) * d0, hd1 = (-2.0 * c.oP1) * d1;
-  double e = exp_fast(p.oq2 * h);
-  double c1 = p.og * e, c2 = p.oh * e;
+  const double st = (double)step;
+  const double cx = c.ox - st * c.osx, cy = c.oy + st * c.osy;
+  const double d0 = px - cx, d1 = py - cy;
+  const double h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
+  const double hd0 = (-2.0 * c.oP0) * d0, hd1 = (-2.0 * c.oP1) * d1;
+  const double e = exp_fast_lo(p.oq2 * h);  // h <= 1 + margin: only underflow needs guarding
+  const double c1 = c.og * e, c2 = c.oh * e;
   g0 = c1 * hd0;
   g1 = c1 * hd1;
   h00 = c2 * (hd0 * hd0);
@@ -216,7 +217,7 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
   }
   double V00 = p.Qf2[0], V01 = p.Qf2[1], V02 = p.Qf2[2], V03 = p.Qf2[3], V11 = p.Qf2[4], V12 = p.Qf2[5],
          V13 = p.Qf2[6], V22 = p.Qf2[7], V23 = p.Qf2[8], V33 = p.Qf2[9];
-  if (c.opresent) {
+  {
     double g0, g1, h00, h01, h11;
     obstacle_barrier(p, c, xN[0], xN[1], p.N_param, g0, g1, h00, h01, h11);
     Vx0 += g0;
@@ -248,80 +249,89 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     const double al = cs * dt, be = -sp * sn, ga = sn * dt, de = sp * cs;
     const double b0 = p.dt2 * cs / 2.0, b1 = p.dt2 * sn / 2.0;
     // ---- stage cost derivatives: ilqr_helper.py:25-55, input barriers :83-103
-    double lu0, lu1, luu00, luu11, luu01 = 0.0;
+    double lu0, lu1, luu00, luu11;
     {
       // the lower-bound barriers are the reciprocals of the upper-bound ones up to a constant:
-      // exp(q2(-ubar - u)) = exp(-2 q2 ubar) / exp(q2(u - ubar)) -- two exp + two reciprocals instead of four exp
-      const double e1 = exp_fast(p.cq2 * (ua - p.a_max)), e3 = exp_fast(p.cq2 * (ud - p.d_lim));
+      // exp(q2(-ubar - u)) = exp(-2 q2 ubar) / exp(q2(u - ubar)) -- two exp + two reciprocals instead of four exp;
+      // u is clipped, so the exponents lie in [-2 q2 ubar, 0] and need no range guard
+      const double e1 = exp_fast_bounded(p.cq2 * (ua - p.a_max)), e3 = exp_fast_bounded(p.cq2 * (ud - p.d_lim));
       const double e2 = p.ca_lo * rcp_fast(e1), e4 = p.cd_lo * rcp_fast(e3);
       lu0 = p.cg * e1 - p.cg * e2;
       lu1 = p.cg * e3 - p.cg * e4;
       luu00 = p.ch * e1 + p.ch * e2;
       luu11 = p.ch * e3 + p.ch * e4;
     }
-    double lx0 = 0.0, lx1 = 0.0, lx2 = 0.0, lx3 = 0.0;
-    double l00 = 0.0, l01 = 0.0, l11 = 0.0;
+    double g0, g1, l00, l01, l11;  // obstacle barrier: gradient and Hessian of the position block
+    obstacle_barrier(p, c, xk[0], xk[1], k, g0, g1, l00, l01, l11);
+    // ---- Q-function (iterative_ilqr.py:112-116), products written as nested fma chains
+    const double G0 = fma(dt, V02, fma(b1, V01, b0 * V00)), G1 = fma(dt, V12, fma(b1, V11, b0 * V01));
+    const double G2 = fma(dt, V22, fma(b1, V12, b0 * V02)), G3 = fma(dt, V23, fma(b1, V13, b0 * V03));
+    const double H0 = dt * V03, H1 = dt * V13, H2 = dt * V23, H3 = dt * V33;
+    const double X02 = fma(al, G0, fma(ga, G1, G2)), X03 = fma(be, G0, fma(de, G1, G3));  // Qux row 0 = [G0 G1 X02 X03]
+    const double X12 = fma(al, H0, fma(ga, H1, H2)), X13 = fma(be, H0, fma(de, H1, H3));  // Qux row 1 = [H0 H1 X12 X13]
+    const double W02 = fma(al, V00, fma(ga, V01, V02)), W12 = fma(al, V01, fma(ga, V11, V12));
+    const double W22 = fma(al, V02, fma(ga, V12, V22)), W03 = fma(be, V00, fma(de, V01, V03));
+    const double W13 = fma(be, V01, fma(de, V11, V13)), W23 = fma(be, V02, fma(de, V12, V23));
+    const double W33 = fma(be, V03, fma(de, V13, V33));
+    double Qx0, Qx1, Qx2, Qx3, Qu0, Qu1, Quu00, Quu01, Quu10, Quu11;
+    double M00, M01, M02, M03, M11, M12, M13, M22, M23, M33;
     if (kQR) {
+      const double d0 = xk[0] - p.xtarget[0], d1 = xk[1] - p.xtarget[1], d2 = xk[2] - p.xtarget[2],
+                   d3 = xk[3] - p.xtarget[3];
+      const double lx0 = (p.Q2[0] * d0 + p.Q2[1] * d1 + p.Q2[2] * d2 + p.Q2[3] * d3) + g0;
+      const double lx1 = (p.Q2[1] * d0 + p.Q2[4] * d1 + p.Q2[5] * d2 + p.Q2[6] * d3) + g1;
+      const double lx2 = p.Q2[2] * d0 + p.Q2[5] * d1 + p.Q2[7] * d2 + p.Q2[8] * d3;
+      const double lx3 = p.Q2[3] * d0 + p.Q2[6] * d1 + p.Q2[8] * d2 + p.Q2[9] * d3;
       lu0 = (p.R2[0] * ua + p.R2[1] * ud) + lu0;
       lu1 = (p.R2[1] * ua + p.R2[2] * ud) + lu1;
       luu00 += p.R2[0];
-      luu01 = p.R2[1];
       luu11 += p.R2[2];
-      const double d0 = xk[0] - p.xtarget[0], d1 = xk[1] - p.xtarget[1], d2 = xk[2] - p.xtarget[2],
-                   d3 = xk[3] - p.xtarget[3];
-      lx0 = p.Q2[0] * d0 + p.Q2[1] * d1 + p.Q2[2] * d2 + p.Q2[3] * d3;
-      lx1 = p.Q2[1] * d0 + p.Q2[4] * d1 + p.Q2[5] * d2 + p.Q2[6] * d3;
-      lx2 = p.Q2[2] * d0 + p.Q2[5] * d1 + p.Q2[7] * d2 + p.Q2[8] * d3;
-      lx3 = p.Q2[3] * d0 + p.Q2[6] * d1 + p.Q2[8] * d2 + p.Q2[9] * d3;
-      l00 = p.Q2[0];
-      l01 = p.Q2[1];
-      l11 = p.Q2[4];
+      Qx0 = lx0 + Vx0;
+      Qx1 = lx1 + Vx1;
+      Qx2 = lx2 + fma(al, Vx0, fma(ga, Vx1, Vx2));
+      Qx3 = lx3 + fma(be, Vx0, fma(de, Vx1, Vx3));
+      Quu01 = fma(G3, dt, p.R2[1]);
+      Quu10 = p.R2[1] + fma(H2, dt, fma(H1, b1, H0 * b0));
+      M00 = (p.Q2[0] + l00) + V00;
+      M01 = (p.Q2[1] + l01) + V01;
+      M11 = (p.Q2[4] + l11) + V11;
+      M02 = p.Q2[2] + W02;
+      M03 = p.Q2[3] + W03;
+      M12 = p.Q2[5] + W12;
+      M13 = p.Q2[6] + W13;
+      M22 = p.Q2[7] + fma(al, W02, fma(ga, W12, W22));
+      M23 = p.Q2[8] + fma(al, W03, fma(ga, W13, W23));
+      M33 = p.Q2[9] + fma(be, W03, fma(de, W13, W33));
+    } else {  // matrix_Q = matrix_R = 0: l_x, l_xx live in the position block only, l_uu is diagonal
+      Qx0 = g0 + Vx0;
+      Qx1 = g1 + Vx1;
+      Qx2 = fma(al, Vx0, fma(ga, Vx1, Vx2));
+      Qx3 = fma(be, Vx0, fma(de, Vx1, Vx3));
+      Quu01 = G3 * dt;
+      Quu10 = fma(H2, dt, fma(H1, b1, H0 * b0));
+      M00 = l00 + V00;
+      M01 = l01 + V01;
+      M11 = l11 + V11;
+      M02 = W02;
+      M03 = W03;
+      M12 = W12;
+      M13 = W13;
+      M22 = fma(al, W02, fma(ga, W12, W22));
+      M23 = fma(al, W03, fma(ga, W13, W23));
+      M33 = fma(be, W03, fma(de, W13, W33));
     }
-    if (c.opresent) {
-      double g0, g1, h00, h01, h11;
-      obstacle_barrier(p, c, xk[0], xk[1], k, g0, g1, h00, h01, h11);
-      lx0 += g0;
-      lx1 += g1;
-      l00 += h00;
-      l01 += h01;
-      l11 += h11;
-    }
-    // ---- Q-function: iterative_ilqr.py:112-116
-    const double Qx0 = lx0 + Vx0, Qx1 = lx1 + Vx1;
-    const double Qx2 = lx2 + (al * Vx0 + ga * Vx1 + Vx2), Qx3 = lx3 + (be * Vx0 + de * Vx1 + Vx3);
-    const double Qu0 = lu0 + (b0 * Vx0 + b1 * Vx1 + dt * Vx2), Qu1 = lu1 + dt * Vx3;
-    const double G0 = b0 * V00 + b1 * V01 + dt * V02, G1 = b0 * V01 + b1 * V11 + dt * V12;
-    const double G2 = b0 * V02 + b1 * V12 + dt * V22, G3 = b0 * V03 + b1 * V13 + dt * V23;
-    const double H0 = dt * V03, H1 = dt * V13, H2 = dt * V23, H3 = dt * V33;
-    const double Quu00 = luu00 + (G0 * b0 + G1 * b1 + G2 * dt);
-    const double Quu01 = luu01 + G3 * dt;
-    const double Quu10 = luu01 + (H0 * b0 + H1 * b1 + H2 * dt);
-    const double Quu11 = luu11 + H3 * dt;
-    const double X02 = al * G0 + ga * G1 + G2, X03 = be * G0 + de * G1 + G3;  // Qux row 0 = [G0 G1 X02 X03]
-    const double X12 = al * H0 + ga * H1 + H2, X13 = be * H0 + de * H1 + H3;  // Qux row 1 = [H0 H1 X12 X13]
-    const double W02 = al * V00 + ga * V01 + V02, W12 = al * V01 + ga * V11 + V12, W22 = al * V02 + ga * V12 + V22;
-    const double W03 = be * V00 + de * V01 + V03, W13 = be * V01 + de * V11 + V13, W23 = be * V02 + de * V12 + V23;
-    const double W33 = be * V03 + de * V13 + V33;
-    double M00 = l00 + V00, M01 = l01 + V01, M11 = l11 + V11;
-    double M02 = W02, M03 = W03, M12 = W12, M13 = W13;
-    double M22 = al * W02 + ga * W12 + W22, M23 = al * W03 + ga * W13 + W23, M33 = be * W03 + de * W13 + W33;
-    if (kQR) {
-      M02 += p.Q2[2];
-      M03 += p.Q2[3];
-      M12 += p.Q2[5];
-      M13 += p.Q2[6];
-      M22 += p.Q2[7];
-      M23 += p.Q2[8];
-      M33 += p.Q2[9];
-    }
+    Qu0 = fma(dt, Vx2, fma(b1, Vx1, fma(b0, Vx0, lu0)));
+    Qu1 = fma(dt, Vx3, lu1);
+    Quu00 = fma(G2, dt, fma(G1, b1, fma(G0, b0, luu00)));
+    Quu11 = fma(H3, dt, luu11);
     // ---- regularised inverse and gains: iterative_ilqr.py:118-126
     double i00, i01, i11;
     quu_inverse(Quu00, (Quu01 + Quu10) / 2.0, Quu11, c.lamb, i00, i01, i11);
-    const double k0 = -(i00 * Qu0 + i01 * Qu1), k1 = -(i01 * Qu0 + i11 * Qu1);
-    const double K00 = -(i00 * G0 + i01 * H0), K01 = -(i00 * G1 + i01 * H1);
-    const double K02 = -(i00 * X02 + i01 * X12), K03 = -(i00 * X03 + i01 * X13);
-    const double K10 = -(i01 * G0 + i11 * H0), K11 = -(i01 * G1 + i11 * H1);
-    const double K12 = -(i01 * X02 + i11 * X12), K13 = -(i01 * X03 + i11 * X13);
+    const double k0 = -fma(i01, Qu1, i00 * Qu0), k1 = -fma(i11, Qu1, i01 * Qu0);
+    const double K00 = -fma(i01, H0, i00 * G0), K01 = -fma(i01, H1, i00 * G1);
+    const double K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
+    const double K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
+    const double K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
     s.st(I2_NEW(N, k) + 0, k0);
     s.st(I2_NEW(N, k) + 1, k1);
     s.st(I2_NEW(N, k) + 2, K00);
@@ -333,24 +343,24 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     s.st(I2_NEW(N, k) + 8, K12);
     s.st(I2_NEW(N, k) + 9, K13);
     // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
-    const double P00 = K00 * Quu00 + K10 * Quu10, P01 = K00 * Quu01 + K10 * Quu11;
-    const double P10 = K01 * Quu00 + K11 * Quu10, P11 = K01 * Quu01 + K11 * Quu11;
-    const double P20 = K02 * Quu00 + K12 * Quu10, P21 = K02 * Quu01 + K12 * Quu11;
-    const double P30 = K03 * Quu00 + K13 * Quu10, P31 = K03 * Quu01 + K13 * Quu11;
-    Vx0 = Qx0 - (P00 * k0 + P01 * k1);
-    Vx1 = Qx1 - (P10 * k0 + P11 * k1);
-    Vx2 = Qx2 - (P20 * k0 + P21 * k1);
-    Vx3 = Qx3 - (P30 * k0 + P31 * k1);
-    V00 = M00 - (P00 * K00 + P01 * K10);
-    V01 = M01 - (P00 * K01 + P01 * K11);
-    V02 = M02 - (P00 * K02 + P01 * K12);
-    V03 = M03 - (P00 * K03 + P01 * K13);
-    V11 = M11 - (P10 * K01 + P11 * K11);
-    V12 = M12 - (P10 * K02 + P11 * K12);
-    V13 = M13 - (P10 * K03 + P11 * K13);
-    V22 = M22 - (P20 * K02 + P21 * K12);
-    V23 = M23 - (P20 * K03 + P21 * K13);
-    V33 = M33 - (P30 * K03 + P31 * K13);
+    const double P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
+    const double P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
+    const double P20 = fma(K12, Quu10, K02 * Quu00), P21 = fma(K12, Quu11, K02 * Quu01);
+    const double P30 = fma(K13, Quu10, K03 * Quu00), P31 = fma(K13, Quu11, K03 * Quu01);
+    Vx0 = fma(-P01, k1, fma(-P00, k0, Qx0));
+    Vx1 = fma(-P11, k1, fma(-P10, k0, Qx1));
+    Vx2 = fma(-P21, k1, fma(-P20, k0, Qx2));
+    Vx3 = fma(-P31, k1, fma(-P30, k0, Qx3));
+    V00 = fma(-P01, K10, fma(-P00, K00, M00));
+    V01 = fma(-P01, K11, fma(-P00, K01, M01));
+    V02 = fma(-P01, K12, fma(-P00, K02, M02));
+    V03 = fma(-P01, K13, fma(-P00, K03, M03));
+    V11 = fma(-P11, K11, fma(-P10, K01, M11));
+    V12 = fma(-P11, K12, fma(-P10, K02, M12));
+    V13 = fma(-P11, K13, fma(-P10, K03, M13));
+    V22 = fma(-P21, K12, fma(-P20, K02, M22));
+    V23 = fma(-P21, K13, fma(-P20, K03, M23));
+    V33 = fma(-P31, K13, fma(-P30, K03, M33));
   }
 }
 
@@ -378,8 +388,8 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 #pragma unroll
     for (int i = 0; i < 10; ++i) g[i] = s.ld(I2_NEW(N, k) + i);
     const double d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
-    double ua = uo0 + g[0] + (g[2] * d0 + g[3] * d1 + g[4] * d2 + g[5] * d3);
-    double ud = uo1 + g[1] + (g[6] * d0 + g[7] * d1 + g[8] * d2 + g[9] * d3);
+    double ua = (uo0 + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
+    double ud = (uo1 + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
     ua = clipd(ua, -p.a_max, p.a_max);
     ud = clipd(ud, -p.d_lim, p.d_lim);
     if (kQR) {
@@ -468,19 +478,18 @@ __device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c,
   }
 }
 
-__device__ __forceinline__ void load_obstacle(Cand& c, const DevObstacle* o) {
+__device__ __forceinline__ void load_obstacle(const KParams& p, Cand& c, const DevObstacle* o) {
   if (o != nullptr && o->present) {
     c.ox = o->x;
     c.oy = o->y;
     c.oP0 = 1.0 / (o->width * o->width);
     c.oP1 = 1.0 / (o->height * o->height);
-    c.ospd = o->spd;
-    c.omode = o->moving_option;
-    c.opresent = 1;
+    c.osx = o->moving_option == 2 ? o->spd : 0.0;
+    c.osy = o->moving_option == 1 ? o->spd : 0.0;
+    c.og = p.og;
+    c.oh = p.oh;
   } else {
-    c.ox = c.oy = c.oP0 = c.oP1 = c.ospd = 0.0;
-    c.omode = 0;
-    c.opresent = 0;
+    c.ox = c.oy = c.oP0 = c.oP1 = c.osx = c.osy = c.og = c.oh = 0.0;
   }
 }
 

@@ -69,7 +69,7 @@ struct Work {
 // controller step; a lane walks the K candidates of its (episode, lap) in rank order carrying lambda
 // (utils/base.py:393,414).
 enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
-constexpr int kSolveThreads = 128;  // block size of solve_kernel == shared-memory scratch stride
+constexpr int kSolveThreads = 32;   // block size of solve_kernel == shared-memory scratch stride
 
 template <bool kQR, bool kSmem, int kMode>
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
             c.xt[i] = n_xt[i];
           }
           c.lamb = n_lamb;
-          load_obstacle(c, w.n_obs != 0 ? &n_obs : nullptr);
+          load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
           sincos_fast(c.x0[3], &c.s0, &c.c0);
           init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
           have_next = false;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
               lap = w.set.lap(ep, slot);
               rank = 0;
               c.lamb = p.lamb0;  // utils/base.py:393
-              load_obstacle(c, w.ep_obs + ep);
+              load_obstacle(p, c, w.ep_obs + ep);
 #pragma unroll
               for (int i = 0; i < 4; ++i) c.x0[i] = w.x[(size_t)ep * 4 + i];
               sincos_fast(c.x0[3], &c.s0, &c.c0);

@@ -29,7 +29,7 @@ extern "C" int host_solve(const KParams* kp, int64_t B, const double* x0, const 
     for (int i = 0; i < 4; ++i) { c.x0[i] = x0[b * 4 + i]; c.xt[i] = xt[b * 4 + i]; }
     sincos_fast(c.x0[3], &c.s0, &c.c0);
     c.lamb = lamb_in ? lamb_in[b] : p.lamb0;
-    load_obstacle(c, n_obs == 0 ? nullptr : reinterpret_cast<const DevObstacle*>(n_obs == 1 ? obs : obs + b));
+    load_obstacle(p, c, n_obs == 0 ? nullptr : reinterpret_cast<const DevObstacle*>(n_obs == 1 ? obs : obs + b));
     const double* u0 = u_init ? u_init + b * 2 * p.N : nullptr;
     if (p.has_qr) {
       init_candidate<true, 0>(p, c, s, u0);

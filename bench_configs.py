@@ -1,0 +1,93 @@
+"""Measurements of the BASELINE.json configs that are not the bench.py headline (config 5):
+
+    python bench_configs.py latency     # config 2: one closed-loop lap, K=64, L=8: per-step latency on 1 GPU
+    python bench_configs.py episodes    # config 3: independent closed-loop episodes (512 per GPU), K=8, L=2
+    python bench_configs.py horizon     # config 4a: horizon sweep N=10..200, flat batch with obstacle barrier
+
+Each prints one JSON line; the committed copies live under profiles/.  All calls go through the C ABI.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from ilqr_iterative_tasks_b200 import _abi, engine, episodes, synth  # noqa: E402
+
+
+def flops_per_iteration(N):
+    return 927 * N + 177
+
+
+def latency(device=0):
+    import bench
+
+    out = bench.latency_probe(device, max_seconds=120.0)
+    out["config"] = "BASELINE config 2"
+    return out
+
+
+def episodes_cfg(device=0, E=512, laps=3):
+    sc = synth.episode_scenarios(4096)
+    rank = int(os.environ.get("RANK", "0"))
+    lo = rank * E
+    p = _abi.default_params(num_ss_points=8, num_ss_iter=2)
+    lap0, _ = synth.initial_lap()
+    obs = _abi.obstacle_array(sc["obs"][lo : lo + E], sc["mode"][lo : lo + E])
+    t0 = time.perf_counter()
+    eb = episodes.EpisodeBatch(p, sc["x0"][lo : lo + E], obstacles=obs, initial_lap=lap0, device=device)
+    setup_s = time.perf_counter() - t0
+    rows = []
+    for lap in range(laps):
+        t0 = time.perf_counter()
+        lens = eb.run_lap()
+        wall = time.perf_counter() - t0
+        st = eb.stats()
+        status = eb.status()
+        rows.append({
+            "lap": lap + 1, "wall_s": wall, "kernel_ms": st["kernel_ms"], "launches": st["launches"],
+            "solves": st["solves"], "ilqr_iterations": st["ilqr_iterations"],
+            "steps_mean": float(lens.mean()), "steps_min": int(lens.min()), "steps_max": int(lens.max()),
+            "reached_goal": int((status == 0).sum()), "solves_per_s": st["solves"] / wall,
+            "episode_steps_per_s": float(lens.sum()) / wall,
+        })  # fmt: skip
+    eb.close()
+    return {
+        "config": "BASELINE config 3 (this GPU's share: %d of 4096 episodes)" % E, "episodes": E, "K": 8, "L": 2, "N": 6,
+        "setup_s": setup_s, "laps": rows,
+        "reference_cpu": "Python reference: ~1.4 s per controller step per episode on one core (BASELINE.md)",
+    }
+
+
+def horizon_sweep(device=0):
+    rows = []
+    peak = engine.measure_fp64_peak(device)
+    for N, B in ((6, 1 << 18), (10, 1 << 17), (25, 1 << 16), (50, 1 << 15), (100, 1 << 14), (200, 1 << 13)):
+        d = synth.flat_candidates(B, N, seed=synth.SEED + N)
+        p = _abi.default_params(num_horizon=N)
+        obs = _abi.obstacle_array(d["obs"], d["mode"])
+        e = engine.Engine(p, device=device)
+        e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, want=("iters",))
+        t0 = time.perf_counter()
+        out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+        wall = time.perf_counter() - t0
+        st = e.last_stats()
+        e.close()
+        tf = st["ilqr_iterations"] * flops_per_iteration(N) / (st["kernel_ms"] * 1e-3) / 1e12
+        rows.append({
+            "N": N, "B": B, "wall_ms": wall * 1e3, "pipeline_ms": st["kernel_ms"], "solves_per_s": B / wall,
+            "iters_per_solve": st["ilqr_iterations"] / B, "algorithmic_tflops": tf, "frac_of_fp64_peak": tf / peak,
+            "finite": bool(np.isfinite(out["xvar"]).all()),
+        })  # fmt: skip
+    return {"config": "BASELINE config 4a: horizon sweep, host-pointer API (copies inside the timed call)", "fp64_peak_tflops": peak, "rows": rows}
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "latency"
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    fn = {"latency": latency, "episodes": episodes_cfg, "horizon": horizon_sweep}[what]
+    print(json.dumps(fn(dev)))

@@ -78,7 +78,7 @@ struct i2lqr_handle {
   int ctl_next = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};  // extra streams of the chunked host pipeline
   cudaEvent_t aux_done[2] = {nullptr, nullptr};
-  DevBuf<double> gscratch;
+  DevBuf<double> gscratch[3];  // one slab per pipeline stream (launches on different streams overlap)
   // flat batch staging
   DevBuf<double> b_x0, b_xt, b_lamb, b_uvar, b_xvar, b_lamb_out, b_uinit;
   DevBuf<DevObstacle> b_obs;
@@ -116,38 +116,45 @@ constexpr int kCtlWords = 2 + kCtlSlots;  // ctl[0] executed iterations, ctl[1] 
 constexpr int kAuxStreams = 2;
 
 // Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
-int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st) {
+int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   const KParams& kp = h->kp;
-  const size_t per_block = (size_t)kThreads * scratch_doubles(kp.N) * sizeof(double);
-  const bool use_smem = per_block <= kSmemLimit;
+  // scratch placement: 0 shared memory (18N doubles per lane), 2 hybrid (8N in shared memory, 10N in an
+  // L2-resident slab: more resident warps), 1 all in the slab (horizons whose trajectory does not fit)
+  static const int force = getenv("I2LQR_SCRATCH") ? atoi(getenv("I2LQR_SCRATCH")) : -1;  // tuning switch
+  const size_t smem_full = (size_t)kThreads * 18 * kp.N * sizeof(double);
+  const size_t smem_cur = (size_t)kThreads * 8 * kp.N * sizeof(double);
+  int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur * 2 <= kSmemLimit ? 2 : 1);
+  if (force >= 0) scratch = force;
+  if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
+  if (scratch == 2 && smem_cur > kSmemLimit) scratch = 1;
   CU(h->ctl.ensure(kCtlWords));
   const int slot = h->ctl_next;
   h->ctl_next = (slot + 1) % kCtlSlots;
   CU(cudaMemsetAsync(h->ctl.p + 2 + slot, 0, sizeof(unsigned long long), st));
   w.counter = h->ctl.p + 2 + slot;
   w.stats = h->ctl.p;
-  const long long lanes_needed = w.mode == 0 ? w.n_items : w.n_items;  // one lane per item
-  long long blocks_needed = (lanes_needed + kThreads - 1) / kThreads;
+  long long blocks_needed = (w.n_items + kThreads - 1) / kThreads;
   if (blocks_needed < 1) blocks_needed = 1;
-  auto pick = [&](auto mode) {
+  using KernelT = void (*)(const KParams, const Work);
+  auto pick = [&](auto mode) -> KernelT {
     constexpr int M = decltype(mode)::value;
-    return kp.has_qr ? (use_smem ? solve_kernel<true, true, M> : solve_kernel<true, false, M>)
-                     : (use_smem ? solve_kernel<false, true, M> : solve_kernel<false, false, M>);
+    if (kp.has_qr) return scratch == 0 ? solve_kernel<true, 0, M> : (scratch == 1 ? solve_kernel<true, 1, M> : solve_kernel<true, 2, M>);
+    return scratch == 0 ? solve_kernel<false, 0, M> : (scratch == 1 ? solve_kernel<false, 1, M> : solve_kernel<false, 2, M>);
   };
-  auto kern = w.mode == 0 ? pick(std::integral_constant<int, 0>()) : pick(std::integral_constant<int, 1>());
+  KernelT kern = w.mode == 0 ? pick(std::integral_constant<int, 0>()) : pick(std::integral_constant<int, 1>());
   int per_sm = 0;
-  size_t smem = use_smem ? per_block : 0;
+  size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
   // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
   static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
-  if (use_smem && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
-  if (use_smem) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 0 && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
-  if (!use_smem) {
-    const size_t need = (size_t)grid * kThreads * scratch_doubles(kp.N);
-    CU(h->gscratch.ensure(need));
-    w.gscratch = h->gscratch.p;
+  if (scratch != 0) {
+    const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
+    CU(h->gscratch[pipe].ensure((size_t)grid * kThreads * per_lane));
+    w.gscratch = h->gscratch[pipe].p;
     w.gstride = grid * kThreads;
   }
   kern<<<(unsigned)grid, kThreads, smem, st>>>(kp, w);
@@ -306,7 +313,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->gscratch, &h->s_x, &h->s_u,
+  for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->gscratch[0], &h->gscratch[1], &h->gscratch[2], &h->s_x, &h->s_u,
                   &h->s_xpred, &h->s_upred, &h->s_cand_x, &h->s_cand_u, &h->s_cand_cost, &h->s_cand_lamb, &h->s_wcost,
                   &h->q_x0})
     b->release();
@@ -348,7 +355,7 @@ int check_batch_args(i2lqr_handle* h, int64_t B, const double* x0, const double*
 // One launch over rows [lo, lo+n) of device-resident arrays.
 int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const double* x_term, const double* lamb_in,
                 const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
-                double* lamb_out, int32_t* iters, cudaStream_t st) {
+                double* lamb_out, int32_t* iters, cudaStream_t st, int pipe = 0) {
   const int N = h->kp.N;
   Work w{};
   w.mode = 0;
@@ -363,7 +370,7 @@ int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const 
   w.xvar = xvar ? xvar + lo * 4 * (N + 1) : nullptr;
   w.lamb_out = lamb_out ? lamb_out + lo : nullptr;
   w.iters = iters ? iters + lo : nullptr;
-  return launch_solve(h, w, st);
+  return launch_solve(h, w, st, pipe);
 }
 }  // namespace
 
@@ -422,7 +429,7 @@ int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double
         CU(cudaMemcpyAsync(h->b_uinit.p + ulo * 2 * N, uvar_init + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
       if (launch_flat(h, lo, n, h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr, d_obs, n_obs,
                       uvar_init ? h->b_uinit.p : nullptr, uvar ? h->b_uvar.p : nullptr, xvar ? h->b_xvar.p : nullptr,
-                      lamb_out ? h->b_lamb_out.p : nullptr, iters ? h->b_iters.p : nullptr, st))
+                      lamb_out ? h->b_lamb_out.p : nullptr, iters ? h->b_iters.p : nullptr, st, (int)(c % (1 + kAuxStreams))))
         return 1;
       if (uvar) CU(cudaMemcpyAsync(uvar + ulo * 2 * N, h->b_uvar.p + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (xvar)

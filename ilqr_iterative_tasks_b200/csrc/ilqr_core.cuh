@@ -55,19 +55,54 @@ struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
   int32_t moving_option, present;
 };
 
-// Per-lane scratch column: element e lives at base[e * stride].  In shared memory the stride is the block
-// size, a compile-time constant, so element offsets fold into the LDS/STS immediates.
+// Per-lane scratch column, element e at base[e * stride]: a "current trajectory" region (8 doubles per
+// stage, ldc/stc) and a "gains / trial trajectory" region (10 doubles per stage, ldg/stg).
+//   SmemScratch   both regions in shared memory; the stride is the block size, a compile-time constant, so
+//                 element offsets fold into the LDS/STS immediates.
+//   GlobalScratch both regions in an L2-resident global slab (long horizons).
+//   HybridScratch current trajectory in shared memory, gains in the global slab: 384 instead of 864 bytes of
+//                 shared memory per lane at N=6, i.e. 12 instead of 8 resident warps per SM.
 template <int kStride>
 struct SmemScratch {
   double* base;
-  __device__ __forceinline__ double ld(int e) const { return base[e * kStride]; }
-  __device__ __forceinline__ void st(int e, double v) const { base[e * kStride] = v; }
+  double* gbase;
+  __device__ __forceinline__ void bind(double* smem_lane, double*, long long, int N) {
+    base = smem_lane;
+    gbase = smem_lane + (size_t)8 * N * kStride;
+  }
+  __device__ __forceinline__ double ldc(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void stc(int e, double v) const { base[e * kStride] = v; }
+  __device__ __forceinline__ double ldg(int e) const { return gbase[e * kStride]; }
+  __device__ __forceinline__ void stg(int e, double v) const { gbase[e * kStride] = v; }
 };
 struct GlobalScratch {
   double* base;
+  double* gbase;
   long long stride;
-  __device__ __forceinline__ double ld(int e) const { return base[(size_t)e * stride]; }
-  __device__ __forceinline__ void st(int e, double v) const { base[(size_t)e * stride] = v; }
+  __device__ __forceinline__ void bind(double*, double* glob_lane, long long gstride, int N) {
+    base = glob_lane;
+    stride = gstride;
+    gbase = glob_lane + (size_t)8 * N * gstride;
+  }
+  __device__ __forceinline__ double ldc(int e) const { return base[(size_t)e * stride]; }
+  __device__ __forceinline__ void stc(int e, double v) const { base[(size_t)e * stride] = v; }
+  __device__ __forceinline__ double ldg(int e) const { return gbase[(size_t)e * stride]; }
+  __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
+};
+template <int kStride>
+struct HybridScratch {
+  double* base;
+  double* gbase;
+  long long stride;
+  __device__ __forceinline__ void bind(double* smem_lane, double* glob_lane, long long gstride, int) {
+    base = smem_lane;
+    gbase = glob_lane;
+    stride = gstride;
+  }
+  __device__ __forceinline__ double ldc(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void stc(int e, double v) const { base[e * kStride] = v; }
+  __device__ __forceinline__ double ldg(int e) const { return gbase[(size_t)e * stride]; }
+  __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
 };
 // Scratch layout for horizon N (18 N doubles per candidate):
 //   cur slot k (8):  [0..1] u_k   [2..5] x_{k+1}   [6] cos(theta_{k+1})  [7] sin(theta_{k+1})
@@ -185,14 +220,14 @@ __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const 
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
     if (u0 != nullptr) sincos_fast(x[3], &sn, &cs);
-    s.st(I2_CUR(k) + 0, ua);
-    s.st(I2_CUR(k) + 1, ud);
-    s.st(I2_CUR(k) + 2, x[0]);
-    s.st(I2_CUR(k) + 3, x[1]);
-    s.st(I2_CUR(k) + 4, x[2]);
-    s.st(I2_CUR(k) + 5, x[3]);
-    s.st(I2_CUR(k) + 6, cs);
-    s.st(I2_CUR(k) + 7, sn);
+    s.stc(I2_CUR(k) + 0, ua);
+    s.stc(I2_CUR(k) + 1, ud);
+    s.stc(I2_CUR(k) + 2, x[0]);
+    s.stc(I2_CUR(k) + 3, x[1]);
+    s.stc(I2_CUR(k) + 4, x[2]);
+    s.stc(I2_CUR(k) + 5, x[3]);
+    s.stc(I2_CUR(k) + 6, cs);
+    s.stc(I2_CUR(k) + 7, sn);
   }
   c.J = J + terminal_cost(p, c, x);
   c.iters = 0;
@@ -206,7 +241,7 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
   // ---- value function at the horizon end: get_cost_final (ilqr_helper.py:106-150)
   double xN[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) xN[i] = s.ld(I2_CUR(N - 1) + 2 + i);
+  for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
   double Vx0, Vx1, Vx2, Vx3;
   {
     double e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
@@ -229,19 +264,19 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = N - 1; k >= 0; --k) {
     // ---- trajectory at stage k
-    const double ua = s.ld(I2_CUR(k) + 0), ud = s.ld(I2_CUR(k) + 1);
-    const double v1 = s.ld(I2_CUR(k) + 4);                               // v_{k+1}
-    const double cs = s.ld(I2_CUR(k) + 6), sn = s.ld(I2_CUR(k) + 7);     // cos / sin theta_{k+1}
+    const double ua = s.ldc(I2_CUR(k) + 0), ud = s.ldc(I2_CUR(k) + 1);
+    const double v1 = s.ldc(I2_CUR(k) + 4);                               // v_{k+1}
+    const double cs = s.ldc(I2_CUR(k) + 6), sn = s.ldc(I2_CUR(k) + 7);     // cos / sin theta_{k+1}
     double xk[4];
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xk[i] = c.x0[i];
     } else {
-      xk[0] = s.ld(I2_CUR(k - 1) + 2);
-      xk[1] = s.ld(I2_CUR(k - 1) + 3);
+      xk[0] = s.ldc(I2_CUR(k - 1) + 2);
+      xk[1] = s.ldc(I2_CUR(k - 1) + 3);
       if (kQR) {
-        xk[2] = s.ld(I2_CUR(k - 1) + 4);
-        xk[3] = s.ld(I2_CUR(k - 1) + 5);
+        xk[2] = s.ldc(I2_CUR(k - 1) + 4);
+        xk[3] = s.ldc(I2_CUR(k - 1) + 5);
       }
     }
     // ---- linearisation at (v_{k+1}, theta_{k+1}, a_k): iterative_ilqr.py:92-99, kinetic_bicycle.py:30-52
@@ -332,16 +367,16 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     const double K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
     const double K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
     const double K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
-    s.st(I2_NEW(N, k) + 0, k0);
-    s.st(I2_NEW(N, k) + 1, k1);
-    s.st(I2_NEW(N, k) + 2, K00);
-    s.st(I2_NEW(N, k) + 3, K01);
-    s.st(I2_NEW(N, k) + 4, K02);
-    s.st(I2_NEW(N, k) + 5, K03);
-    s.st(I2_NEW(N, k) + 6, K10);
-    s.st(I2_NEW(N, k) + 7, K11);
-    s.st(I2_NEW(N, k) + 8, K12);
-    s.st(I2_NEW(N, k) + 9, K13);
+    s.stg(k * 10 + 0, k0);
+    s.stg(k * 10 + 1, k1);
+    s.stg(k * 10 + 2, K00);
+    s.stg(k * 10 + 3, K01);
+    s.stg(k * 10 + 4, K02);
+    s.stg(k * 10 + 5, K03);
+    s.stg(k * 10 + 6, K10);
+    s.stg(k * 10 + 7, K11);
+    s.stg(k * 10 + 8, K12);
+    s.stg(k * 10 + 9, K13);
     // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
     const double P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
     const double P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
@@ -373,20 +408,24 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
   double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
   double cs = c.c0, sn = c.s0;
   double Jn = 0.0, Jt = 0.0;
+  double g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
+#pragma unroll
+  for (int i = 0; i < 10; ++i) g[i] = gn[i] = s.ldg(i);
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
+    if (k + 1 < N) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) gn[i] = s.ldg((k + 1) * 10 + i);
+    }
     double xo[4];
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = c.x0[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xo[i] = s.ld(I2_CUR(k - 1) + 2 + i);
+      for (int i = 0; i < 4; ++i) xo[i] = s.ldc(I2_CUR(k - 1) + 2 + i);
     }
-    const double uo0 = s.ld(I2_CUR(k) + 0), uo1 = s.ld(I2_CUR(k) + 1);
-    double g[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) g[i] = s.ld(I2_NEW(N, k) + i);
+    const double uo0 = s.ldc(I2_CUR(k) + 0), uo1 = s.ldc(I2_CUR(k) + 1);
     const double d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
     double ua = (uo0 + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
     double ud = (uo1 + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
@@ -403,14 +442,16 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
     sincos_fast(x[3], &sn, &cs);
-    s.st(I2_NEW(N, k) + 0, ua);
-    s.st(I2_NEW(N, k) + 1, ud);
-    s.st(I2_NEW(N, k) + 2, x[0]);
-    s.st(I2_NEW(N, k) + 3, x[1]);
-    s.st(I2_NEW(N, k) + 4, x[2]);
-    s.st(I2_NEW(N, k) + 5, x[3]);
-    s.st(I2_NEW(N, k) + 6, cs);
-    s.st(I2_NEW(N, k) + 7, sn);
+    s.stg(k * 10 + 0, ua);
+    s.stg(k * 10 + 1, ud);
+    s.stg(k * 10 + 2, x[0]);
+    s.stg(k * 10 + 3, x[1]);
+    s.stg(k * 10 + 4, x[2]);
+    s.stg(k * 10 + 5, x[3]);
+    s.stg(k * 10 + 6, cs);
+    s.stg(k * 10 + 7, sn);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) g[i] = gn[i];
   }
   const double T = terminal_cost(p, c, x);
   Jtarget = Jt + T;
@@ -431,7 +472,7 @@ __device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const 
   #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s.st(I2_CUR(k) + i, s.ld(I2_NEW(N, k) + i));
+      for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, s.ldg(k * 10 + i));
     }
     c.lamb /= p.lamb_factor;
     done = fabs((Jn - c.J) / c.J) < p.eps;
@@ -466,14 +507,14 @@ __device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c,
   #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xvar[i * (N + 1) + k + 1] = s.ld(I2_CUR(k) + 2 + i);
+      for (int i = 0; i < 4; ++i) xvar[i * (N + 1) + k + 1] = s.ldc(I2_CUR(k) + 2 + i);
     }
   }
   if (uvar) {
   #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
-      uvar[k] = s.ld(I2_CUR(k) + 0);
-      uvar[N + k] = s.ld(I2_CUR(k) + 1);
+      uvar[k] = s.ldc(I2_CUR(k) + 0);
+      uvar[N + k] = s.ldc(I2_CUR(k) + 1);
     }
   }
 }

@@ -71,17 +71,14 @@ struct Work {
 enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
 constexpr int kSolveThreads = 32;   // block size of solve_kernel == shared-memory scratch stride
 
-template <bool kQR, bool kSmem, int kMode>
+template <bool kQR, int kScratch, int kMode>
 __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
   extern __shared__ double smem[];
-  using ScratchT = typename std::conditional<kSmem, SmemScratch<kSolveThreads>, GlobalScratch>::type;
+  // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab)
+  using ScratchT = typename std::conditional<kScratch == 0, SmemScratch<kSolveThreads>,
+                   typename std::conditional<kScratch == 1, GlobalScratch, HybridScratch<kSolveThreads>>::type>::type;
   ScratchT s;
-  if constexpr (kSmem) {
-    s.base = smem + threadIdx.x;
-  } else {
-    s.base = w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    s.stride = w.gstride;
-  }
+  s.bind(smem + threadIdx.x, w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
   constexpr int kN = 0;  // stage loops stay rolled: the fully unrolled N=6 body measured 1.4x slower (I-cache, spills)
   const unsigned lane = threadIdx.x & 31u;
   const int N = p.N;
@@ -210,7 +207,7 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
           store_candidate<kN>(p, c, s, w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
           double xN[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) xN[i] = s.ld(I2_CUR(N - 1) + 2 + i);
+          for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
           const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
           w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
           w.cand_lamb[tslot] = c.lamb;

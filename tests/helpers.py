@@ -45,3 +45,45 @@ def step_obstacle(g, s):
 
 def step_params(g):
     return _abi.default_params(num_horizon=int(g["N"]), num_ss_points=int(g["K"]), num_ss_iter=int(g["L"]))
+
+
+def oracle_closed_loop(params, x0, obs_row, mode, initial_lap, n_laps):
+    """Closed loop of one episode driven by the CPU oracle: the reference's Simulator.sim
+    (iterative_ilqr/utils/base.py:708-726), forward_one_step (:157-213), obstacle motion (:50-64), the
+    controller's playback branch (:377-382) and the lap post-processing of
+    iterative_ilqr/tests/ilqr_test.py:56-60.  Returns the list of laps (each (T,4), last row = goal)."""
+    from oracle import oracle
+
+    N, S, dt = params.num_horizon, params.max_sim_steps, params.timestep
+    laps = [np.asarray(initial_lap, dtype=np.float64)]
+    goal = laps[0][-1]
+    x = np.asarray(x0, dtype=np.float64).copy()
+    for _ in range(n_laps):
+        obs = None if obs_row is None else _abi.Obstacle(*[float(v) for v in obs_row], int(mode), 1)
+        horizon, u_old = N, None
+        states = [x.copy()]
+        for i in range(S):
+            if horizon < N:  # playback
+                u = u_old[:, 0].copy()
+                u_old = u_old[:, 1:]
+                horizon -= 1
+            else:
+                out = oracle.calc_input(params, laps, x, obs)
+                u = out["u"].copy()
+                u_old = out["u_pred"][:, 1:].copy()
+                if out["shrink"]:
+                    horizon -= 1
+            x = oracle.kinetic_bicycle(x, u, dt)
+            states.append(x.copy())
+            if obs is not None:
+                if obs.moving_option == 1:
+                    obs.y += obs.spd * dt
+                if obs.moving_option == 2:
+                    obs.x -= obs.spd * dt
+            if np.linalg.norm(x - goal) <= params.goal_tol:
+                break
+        lap = np.array(states)
+        lap[-1] = goal
+        laps.append(lap)
+        x = np.zeros(4)
+    return laps

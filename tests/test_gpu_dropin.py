@@ -107,3 +107,27 @@ def test_episode_batch_matches_reference_closed_loop(name):
             assert np.abs(got - ref).max() < 1e-6, (lap, e, np.abs(got - ref).max())
             assert np.abs(lu[e, : len(ref) - 1] - g["lap_inputs%d" % (lap + 1)]).max() < 1e-6
     eb.close()
+
+
+def test_episode_batch_random_scenarios_vs_oracle():
+    """BASELINE config 3 shape on a subset: per-episode obstacle (static / up / left) and start state,
+    K=8, L=2, two laps, every episode compared with an oracle-driven closed loop."""
+    from ilqr_iterative_tasks_b200 import _abi, episodes, synth
+
+    E, n_laps = 12, 2
+    sc = synth.episode_scenarios(E)
+    p = _abi.default_params(num_ss_points=8, num_ss_iter=2)
+    lap0, _ = synth.initial_lap()
+    eb = episodes.EpisodeBatch(p, sc["x0"], obstacles=_abi.obstacle_array(sc["obs"], sc["mode"]), initial_lap=lap0)
+    got = []
+    for _ in range(n_laps):
+        lens, lx, _ = eb.run_lap(want_traj=True)
+        got.append((lens.copy(), lx.copy()))
+    eb.close()
+    for e in range(E):
+        ref = H.oracle_closed_loop(p, sc["x0"][e], sc["obs"][e], sc["mode"][e], lap0, n_laps)
+        for lap in range(n_laps):
+            lens, lx = got[lap]
+            assert lens[e] == len(ref[lap + 1]) - 1, (e, lap, lens[e], len(ref[lap + 1]) - 1)
+            err = np.abs(lx[e, : lens[e] + 1] - ref[lap + 1]).max()
+            assert err < 1e-6, (e, lap, err)

@@ -78,6 +78,30 @@ def test_shared_and_absent_obstacle(eng_mod):
     e.close()
 
 
+def test_host_pipeline_long_horizon(eng_mod):
+    """The chunked three-stream host path with the hybrid (shared + global slab) scratch of N=16: several
+    chunks in flight at once must not share working storage."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    B, N = 3 * 32768 + 5, 16
+    d = synth.flat_candidates(B, N, seed=77)
+    p = _abi.default_params(num_horizon=N)
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    again = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    for k in out:
+        assert np.array_equal(out[k], again[k]), k
+    sel = np.random.default_rng(3).choice(B, 4096, replace=False)
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"][sel], d["x_term"][sel], d["lamb_in"][sel], obs[sel], nthreads=8)
+    same = (out["iters"][sel] == iters) & (out["lamb_out"][sel] == lamb)
+    assert same.mean() >= 0.999
+    assert H.rel_err(out["xvar"][sel][same], x[same]).max() <= H.RTOL
+    assert e.last_stats()["solves"] == B
+    e.close()
+
+
 def test_knn_vs_reference_golden(eng_mod):
     from ilqr_iterative_tasks_b200 import _abi
 

@@ -23,7 +23,8 @@ extern "C" int host_solve(const KParams* kp, int64_t B, const double* x0, const 
                           double* lamb_out, int32_t* iters) {
   const KParams& p = *kp;
   std::vector<double> mem(scratch_doubles(p.N));
-  GlobalScratch s{mem.data(), 1};
+  GlobalScratch s;
+  s.bind(nullptr, mem.data(), 1, p.N);
   for (int64_t b = 0; b < B; ++b) {
     Cand c;
     for (int i = 0; i < 4; ++i) { c.x0[i] = x0[b * 4 + i]; c.xt[i] = xt[b * 4 + i]; }

@@ -109,7 +109,6 @@ int make_kparams(const i2lqr_params& p, KParams* k) {
   return err ? fail("%s", err) : 0;
 }
 
-constexpr int kThreads = kSolveThreads;
 constexpr size_t kSmemLimit = 227 * 1024;
 constexpr int kCtlSlots = 16;   // fetch counters: one per launch that may be in flight concurrently
 constexpr int kCtlWords = 2 + kCtlSlots;  // ctl[0] executed iterations, ctl[1] finished solves, then the counters
@@ -118,46 +117,58 @@ constexpr int kAuxStreams = 2;
 // Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
 int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   const KParams& kp = h->kp;
-  // scratch placement: 0 shared memory (18N doubles per lane), 2 hybrid (8N in shared memory, 10N in an
-  // L2-resident slab: more resident warps), 1 all in the slab (horizons whose trajectory does not fit)
+  // scratch placement: 0 shared memory (18N doubles per lane), 3 trajectory in shared memory + gains in tensor
+  // memory (flat batches up to horizon 6: 12 resident warps per SM), 2 hybrid (8N in shared memory, 10N in
+  // an L2-resident slab), 1 all in the slab (horizons whose trajectory does not fit shared memory)
   static const int force = getenv("I2LQR_SCRATCH") ? atoi(getenv("I2LQR_SCRATCH")) : -1;  // tuning switch
-  const size_t smem_full = (size_t)kThreads * 18 * kp.N * sizeof(double);
-  const size_t smem_cur = (size_t)kThreads * 8 * kp.N * sizeof(double);
+  const size_t smem_full = (size_t)kSolveThreads * 18 * kp.N * sizeof(double);
+  const size_t smem_cur = (size_t)kSolveThreads * 8 * kp.N * sizeof(double);
   int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur * 2 <= kSmemLimit ? 2 : 1);
+  const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon;
   if (force >= 0) scratch = force;
+  if (scratch == 3 && !tmem_ok) scratch = 0;
   if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
   if (scratch == 2 && smem_cur > kSmemLimit) scratch = 1;
+  const int threads = scratch == 3 ? kTmemThreads : kSolveThreads;
   CU(h->ctl.ensure(kCtlWords));
   const int slot = h->ctl_next;
   h->ctl_next = (slot + 1) % kCtlSlots;
   CU(cudaMemsetAsync(h->ctl.p + 2 + slot, 0, sizeof(unsigned long long), st));
   w.counter = h->ctl.p + 2 + slot;
   w.stats = h->ctl.p;
-  long long blocks_needed = (w.n_items + kThreads - 1) / kThreads;
+  long long blocks_needed = (w.n_items + threads - 1) / threads;
   if (blocks_needed < 1) blocks_needed = 1;
   using KernelT = void (*)(const KParams, const Work);
   auto pick = [&](auto mode) -> KernelT {
     constexpr int M = decltype(mode)::value;
-    if (kp.has_qr) return scratch == 0 ? solve_kernel<true, 0, M> : (scratch == 1 ? solve_kernel<true, 1, M> : solve_kernel<true, 2, M>);
-    return scratch == 0 ? solve_kernel<false, 0, M> : (scratch == 1 ? solve_kernel<false, 1, M> : solve_kernel<false, 2, M>);
+    constexpr int T = kSolveThreads;
+    if (kp.has_qr) return scratch == 0 ? solve_kernel<true, 0, M, T> : (scratch == 1 ? solve_kernel<true, 1, M, T> : solve_kernel<true, 2, M, T>);
+    return scratch == 0 ? solve_kernel<false, 0, M, T> : (scratch == 1 ? solve_kernel<false, 1, M, T> : solve_kernel<false, 2, M, T>);
   };
   KernelT kern = w.mode == 0 ? pick(std::integral_constant<int, 0>()) : pick(std::integral_constant<int, 1>());
+  if (scratch == 3) kern = solve_kernel<false, 3, 0, kTmemThreads>;
   int per_sm = 0;
-  size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
+  size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : (scratch == 3 ? (size_t)kTmemThreads * 8 * kp.N * sizeof(double) : 0));
   // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
   static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
   if (smem > 0 && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
+  // tensor memory: 512 columns per SM, 128 per CTA; registers (168 x 128 threads) allow three CTAs.  The
+  // occupancy calculator reports 1 for kernels that allocate tensor memory, so the grid is sized by hand.
+  if (scratch == 3) per_sm = 3;
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
-  if (scratch != 0) {
+  if (scratch == 1 || scratch == 2) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
-    CU(h->gscratch[pipe].ensure((size_t)grid * kThreads * per_lane));
+    CU(h->gscratch[pipe].ensure((size_t)grid * threads * per_lane));
     w.gscratch = h->gscratch[pipe].p;
-    w.gstride = grid * kThreads;
+    w.gstride = grid * threads;
   }
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(kp, w);
+  static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[i2lqr] solve launch: scratch %d grid %lld x %d smem %zu per_sm %d items %lld\n", scratch, grid, threads, smem, per_sm, w.n_items);
+  kern<<<(unsigned)grid, threads, smem, st>>>(kp, w);
   CU(cudaGetLastError());
   h->last_launches += 1;
   return 0;

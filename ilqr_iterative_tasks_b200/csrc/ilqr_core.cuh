@@ -62,8 +62,30 @@ struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
 //   GlobalScratch both regions in an L2-resident global slab (long horizons).
 //   HybridScratch current trajectory in shared memory, gains in the global slab: 384 instead of 864 bytes of
 //                 shared memory per lane at N=6, i.e. 12 instead of 8 resident warps per SM.
+// Scalar-addressed gains region shared by the memory-backed scratch types.
+template <class Derived>
+struct GainsByElement {
+  static constexpr bool kAligned = false;
+  __device__ __forceinline__ void stg10(int k, const double (&v)[10]) const {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) static_cast<const Derived*>(this)->stg(k * 10 + i, v[i]);
+  }
+  __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = static_cast<const Derived*>(this)->ldg(k * 10 + i);
+  }
+  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) static_cast<const Derived*>(this)->stg(k * 10 + i, v[i]);
+  }
+  __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = static_cast<const Derived*>(this)->ldg(k * 10 + i);
+  }
+  __device__ __forceinline__ void fence_gains() const {}
+};
 template <int kStride>
-struct SmemScratch {
+struct SmemScratch : GainsByElement<SmemScratch<kStride>> {
   double* base;
   double* gbase;
   __device__ __forceinline__ void bind(double* smem_lane, double*, long long, int N) {
@@ -75,7 +97,7 @@ struct SmemScratch {
   __device__ __forceinline__ double ldg(int e) const { return gbase[e * kStride]; }
   __device__ __forceinline__ void stg(int e, double v) const { gbase[e * kStride] = v; }
 };
-struct GlobalScratch {
+struct GlobalScratch : GainsByElement<GlobalScratch> {
   double* base;
   double* gbase;
   long long stride;
@@ -90,7 +112,7 @@ struct GlobalScratch {
   __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
 };
 template <int kStride>
-struct HybridScratch {
+struct HybridScratch : GainsByElement<HybridScratch<kStride>> {
   double* base;
   double* gbase;
   long long stride;
@@ -104,6 +126,75 @@ struct HybridScratch {
   __device__ __forceinline__ double ldg(int e) const { return gbase[(size_t)e * stride]; }
   __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
 };
+#ifdef __CUDACC__
+// TmemScratch: current trajectory in shared memory, gains / trial trajectory in Blackwell tensor memory
+// (256 KB per SM next to the 228 KB of shared memory).  A warp owns one 32-lane quarter of TMEM; lane l of
+// the warp addresses TMEM lane 32*(warp%4)+l, i.e. each thread gets a private strip of 32-bit columns:
+// 20 columns (10 doubles) per stage.  tcgen05.ld / tcgen05.st are warp-collective (.sync.aligned), which is
+// why ilqr_iteration is executed convergently by all 32 lanes.
+template <int kStride>
+struct TmemScratch {
+  static constexpr bool kAligned = true;
+  double* base;
+  uint32_t taddr;  // (lane quarter << 16) | first column of this CTA's allocation
+  __device__ __forceinline__ void bind_tmem(double* smem_lane, uint32_t tmem_addr) {
+    base = smem_lane;
+    taddr = tmem_addr;
+  }
+  __device__ __forceinline__ double ldc(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void stc(int e, double v) const { base[e * kStride] = v; }
+  static __device__ __forceinline__ void st16(uint32_t a, const double* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(a), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+          "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3])),
+          "r"(__double2loint(v[4])), "r"(__double2hiint(v[4])), "r"(__double2loint(v[5])), "r"(__double2hiint(v[5])),
+          "r"(__double2loint(v[6])), "r"(__double2hiint(v[6])), "r"(__double2loint(v[7])), "r"(__double2hiint(v[7]))
+        : "memory");
+  }
+  static __device__ __forceinline__ void st4(uint32_t a, const double* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :
+                 : "r"(a), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1]))
+                 : "memory");
+  }
+  static __device__ __forceinline__ void ld16(uint32_t a, double* v) {
+    int r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(a)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __hiloint2double(r[2 * i + 1], r[2 * i]);
+  }
+  static __device__ __forceinline__ void ld4(uint32_t a, double* v) {
+    int r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __hiloint2double(r[1], r[0]);
+    v[1] = __hiloint2double(r[3], r[2]);
+  }
+  __device__ __forceinline__ void stg10(int k, const double (&v)[10]) const {
+    st16(taddr + k * 20, v);
+    st4(taddr + k * 20 + 16, v + 8);
+  }
+  __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
+    ld16(taddr + k * 20, v);
+    ld4(taddr + k * 20 + 16, v + 8);
+  }
+  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const { st16(taddr + k * 20, v); }
+  __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const { ld16(taddr + k * 20, v); }
+  // a tcgen05.ld must not overtake the tcgen05.st that produced its data
+  __device__ __forceinline__ void fence_gains() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+#endif
 // Scratch layout for horizon N (18 N doubles per candidate):
 //   cur slot k (8):  [0..1] u_k   [2..5] x_{k+1}   [6] cos(theta_{k+1})  [7] sin(theta_{k+1})
 //   new slot k (10): gains [0..1] k_k, [2..9] K_k (row-major 2x4) after the backward pass; the forward pass
@@ -367,16 +458,10 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     const double K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
     const double K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
     const double K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
-    s.stg(k * 10 + 0, k0);
-    s.stg(k * 10 + 1, k1);
-    s.stg(k * 10 + 2, K00);
-    s.stg(k * 10 + 3, K01);
-    s.stg(k * 10 + 4, K02);
-    s.stg(k * 10 + 5, K03);
-    s.stg(k * 10 + 6, K10);
-    s.stg(k * 10 + 7, K11);
-    s.stg(k * 10 + 8, K12);
-    s.stg(k * 10 + 9, K13);
+    {
+      const double gv[10] = {k0, k1, K00, K01, K02, K03, K10, K11, K12, K13};
+      s.stg10(k, gv);
+    }
     // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
     const double P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
     const double P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
@@ -409,14 +494,12 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
   double cs = c.c0, sn = c.s0;
   double Jn = 0.0, Jt = 0.0;
   double g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
+  s.ldg10(0, g);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) g[i] = gn[i] = s.ldg(i);
+  for (int i = 0; i < 10; ++i) gn[i] = g[i];
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
-    if (k + 1 < N) {
-#pragma unroll
-      for (int i = 0; i < 10; ++i) gn[i] = s.ldg((k + 1) * 10 + i);
-    }
+    if (k + 1 < N) s.ldg10(k + 1, gn);
     double xo[4];
     if (k == 0) {
 #pragma unroll
@@ -442,14 +525,10 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
     sincos_fast(x[3], &sn, &cs);
-    s.stg(k * 10 + 0, ua);
-    s.stg(k * 10 + 1, ud);
-    s.stg(k * 10 + 2, x[0]);
-    s.stg(k * 10 + 3, x[1]);
-    s.stg(k * 10 + 4, x[2]);
-    s.stg(k * 10 + 5, x[3]);
-    s.stg(k * 10 + 6, cs);
-    s.stg(k * 10 + 7, sn);
+    {
+      const double tv[8] = {ua, ud, x[0], x[1], x[2], x[3], cs, sn};
+      s.stg8(k, tv);
+    }
 #pragma unroll
     for (int i = 0; i < 10; ++i) g[i] = gn[i];
   }
@@ -459,21 +538,38 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 }
 
 // One iLQR iteration with the accept / reject and lambda schedule of iterative_ilqr.py:74-84.
-// Returns true when the candidate's loop ends.
+// Returns true when the candidate's loop ends.  Written so that every lane of a warp can execute it
+// convergently (lanes without a live candidate pass live = false and only burn their own scratch): the
+// tensor-memory scratch needs warp-aligned accesses.
 template <bool kQR, int kN, class Scratch>
-__device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s) {
+__device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s, bool live = true) {
   backward_pass<kQR, kN>(p, c, s);
+  s.fence_gains();
   double Jt;
   const double Jn = forward_pass<kQR, kN>(p, c, s, Jt);
-  c.iters++;
-  bool done = false;
-  if (Jn < c.J) {
-    const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
-  #pragma unroll(kN > 0 ? kN : 1)
-  for (int k = 0; k < N; ++k) {
+  s.fence_gains();
+  const int N = kN > 0 ? kN : p.N;
+  const bool accept = live && Jn < c.J;
+  if (Scratch::kAligned || accept) {
+    // trial -> current; the trial of stage k+1 is loaded while stage k is stored
+    double t[8], tn[8];
+    s.ldg8(0, t);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, s.ldg(k * 10 + i));
+    for (int i = 0; i < 8; ++i) tn[i] = t[i];
+    for (int k = 0; k < N; ++k) {
+      if (k + 1 < N) s.ldg8(k + 1, tn);
+      if (accept) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, t[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = tn[i];
     }
+  }
+  if (!live) return false;
+  c.iters++;
+  bool done;
+  if (accept) {
     c.lamb /= p.lamb_factor;
     done = fabs((Jn - c.J) / c.J) < p.eps;
     c.J = kQR ? Jt : Jn;

@@ -6,6 +6,8 @@
 //   K3  winner_kernel   lexicographic winner + result gather (utils/base.py:462-478)
 //   K4  plant_kernel    batched closed-loop episode step (utils/base.py:157-213, 708-726)
 #pragma once
+#include <stdint.h>
+
 #include <type_traits>
 
 #include "ilqr_core.cuh"
@@ -69,20 +71,47 @@ struct Work {
 // controller step; a lane walks the K candidates of its (episode, lap) in rank order carrying lambda
 // (utils/base.py:393,414).
 enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
-constexpr int kSolveThreads = 32;   // block size of solve_kernel == shared-memory scratch stride
+constexpr int kSolveThreads = 32;    // block size of the memory-backed variants (one warp: its SM slot frees as soon as it is done)
+constexpr int kTmemThreads = 128;    // block size of the tensor-memory variant (a CTA's TMEM allocation spans four lane quarters)
+constexpr int kTmemColumns = 128;    // 32-bit TMEM columns per CTA: 20 per stage, N <= 6
+constexpr int kTmemMaxHorizon = 6;
 
-template <bool kQR, int kScratch, int kMode>
-__global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
+// kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab),
+//           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8)
+template <int kScratch, int kThreads>
+struct ScratchSelect {
+  using type = typename std::conditional<kScratch == 0, SmemScratch<kThreads>,
+               typename std::conditional<kScratch == 1, GlobalScratch,
+               typename std::conditional<kScratch == 2, HybridScratch<kThreads>, TmemScratch<kThreads>>::type>::type>::type;
+};
+
+template <bool kQR, int kScratch, int kMode, int kThreads>
+__global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : 1)
+solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
   extern __shared__ double smem[];
-  // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab)
-  using ScratchT = typename std::conditional<kScratch == 0, SmemScratch<kSolveThreads>,
-                   typename std::conditional<kScratch == 1, GlobalScratch, HybridScratch<kSolveThreads>>::type>::type;
+  using ScratchT = typename ScratchSelect<kScratch, kThreads>::type;
   ScratchT s;
-  s.bind(smem + threadIdx.x, w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
+  __shared__ uint32_t tmem_base;
+  if constexpr (kScratch == 3) {
+    if (threadIdx.x < 32) {  // one warp allocates the CTA's tensor-memory columns
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(&tmem_base)),
+                   "r"(kTmemColumns)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    s.bind_tmem(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
+    for (int e = 0; e < 8 * p.N; ++e) s.stc(e, 0.0);  // lanes without a live candidate iterate on zeros
+  } else {
+    s.bind(smem + threadIdx.x, w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
+  }
   constexpr int kN = 0;  // stage loops stay rolled: the fully unrolled N=6 body measured 1.4x slower (I-cache, spills)
   const unsigned lane = threadIdx.x & 31u;
   const int N = p.N;
-  Cand c;
+  Cand c = {};
   int state = ST_NEED;
   long long item = 0;
   unsigned long long my_iters = 0, my_solves = 0;
@@ -142,8 +171,15 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
       // full-mask vote above also reconverges the warp before the iteration; without that the freshly
       // initialised lanes run the whole iteration as a separate divergent pass (measured: 15.5 of 32
       // lanes active per issued instruction).
-      if (state == ST_RUN) {
-        if (ilqr_iteration<kQR, kN>(p, c, s)) {
+      const bool live = state == ST_RUN;
+      bool finished;
+      if constexpr (ScratchT::kAligned) {
+        finished = ilqr_iteration<kQR, kN>(p, c, s, live);  // warp-collective scratch: all 32 lanes go through
+      } else {
+        finished = live && ilqr_iteration<kQR, kN>(p, c, s);
+      }
+      if (live) {
+        if (finished) {
           my_iters += (unsigned long long)c.iters;
           my_solves += 1;
           store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
@@ -226,6 +262,12 @@ __global__ void __launch_bounds__(kSolveThreads) solve_kernel(const __grid_const
   if (lane == 0 && w.stats != nullptr && my_solves) {
     atomicAdd(w.stats + 0, my_iters);
     atomicAdd(w.stats + 1, my_solves);
+  }
+  if constexpr (kScratch == 3) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColumns) : "memory");
   }
 }
 

@@ -78,7 +78,11 @@ struct i2lqr_handle {
   int ctl_next = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};  // extra streams of the chunked host pipeline
   cudaEvent_t aux_done[2] = {nullptr, nullptr};
-  DevBuf<double> gscratch[3];  // one slab per pipeline stream (launches on different streams overlap)
+  DevBuf<double> gscratch[3];
+  // iteration-sliced passes: parked candidates (ping-pong), per pipeline stream
+  DevBuf<double> park_state[3][2];
+  DevBuf<int> park_list[3][2];
+  DevBuf<unsigned long long> park_count[3];  // one slab per pipeline stream (launches on different streams overlap)
   // flat batch staging
   DevBuf<double> b_x0, b_xt, b_lamb, b_uvar, b_xvar, b_lamb_out, b_uinit;
   DevBuf<DevObstacle> b_obs;
@@ -113,6 +117,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 constexpr int kCtlSlots = 16;   // fetch counters: one per launch that may be in flight concurrently
 constexpr int kCtlWords = 2 + kCtlSlots;  // ctl[0] executed iterations, ctl[1] finished solves, then the counters
 constexpr int kAuxStreams = 2;
+constexpr long long kSliceMinBatch = 131072;  // smaller flat batches run as a single pass
 
 // Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
 int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
@@ -125,6 +130,7 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   const size_t smem_cur = (size_t)kSolveThreads * 8 * kp.N * sizeof(double);
   int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur * 2 <= kSmemLimit ? 2 : 1);
   const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon;
+  if (tmem_ok && w.n_items >= 8192) scratch = 3;
   if (force >= 0) scratch = force;
   if (scratch == 3 && !tmem_ok) scratch = 0;
   if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
@@ -158,7 +164,7 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
   // tensor memory: 512 columns per SM, 128 per CTA; registers (168 x 128 threads) allow three CTAs.  The
   // occupancy calculator reports 1 for kernels that allocate tensor memory, so the grid is sized by hand.
-  if (scratch == 3) per_sm = 3;
+  if (scratch == 3) per_sm = 3;  // (a 4-CTA build capped at 128 registers spills and measured 12 % slower)
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
   if (scratch == 1 || scratch == 2) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
@@ -342,6 +348,13 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (h->set.lap_count) cudaFree(h->set.lap_count);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 3; ++i) {
+    h->park_count[i].release();
+    for (int b = 0; b < 2; ++b) {
+      h->park_state[i][b].release();
+      h->park_list[i][b].release();
+    }
+  }
   for (int i = 0; i < kAuxStreams; ++i) {
     if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
@@ -381,7 +394,36 @@ int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const 
   w.xvar = xvar ? xvar + lo * 4 * (N + 1) : nullptr;
   w.lamb_out = lamb_out ? lamb_out + lo : nullptr;
   w.iters = iters ? iters + lo : nullptr;
-  return launch_solve(h, w, st, pipe);
+  // Iteration slicing (see solve_kernel): big batches run as four passes -- candidates still unfinished after
+  // 32 / 64 / 96 iterations are parked and resumed, packed into full warps, by the next pass.
+  static const int cap0 = getenv("I2LQR_ITER_CAP") ? atoi(getenv("I2LQR_ITER_CAP")) : 32;  // tuning switch; 0 = off
+  if (cap0 <= 0 || n < kSliceMinBatch) return launch_solve(h, w, st, pipe);
+  const long long capacity = std::max<long long>(65536, n / 4);
+  const size_t words = (size_t)(8 * N + 4);
+  for (int b = 0; b < 2; ++b) {
+    CU(h->park_state[pipe][b].ensure((size_t)capacity * words));
+    CU(h->park_list[pipe][b].ensure((size_t)capacity));
+  }
+  CU(h->park_count[pipe].ensure(4));
+  CU(cudaMemsetAsync(h->park_count[pipe].p, 0, 4 * sizeof(unsigned long long), st));
+  const int n_pass = 4;
+  for (int ps = 0; ps < n_pass; ++ps) {
+    Work wp = w;
+    wp.pass = ps;
+    wp.iter_cap = ps + 1 < n_pass ? cap0 * (ps + 1) : 0;
+    wp.park_capacity = capacity;
+    wp.park_count = h->park_count[pipe].p + ps;
+    wp.park_list = h->park_list[pipe][ps & 1].p;
+    wp.park_state = h->park_state[pipe][ps & 1].p;
+    if (ps > 0) {
+      wp.resume_count = h->park_count[pipe].p + ps - 1;
+      wp.resume_list = h->park_list[pipe][(ps - 1) & 1].p;
+      wp.resume_state = h->park_state[pipe][(ps - 1) & 1].p;
+      wp.n_items = capacity;  // upper bound for the grid; the kernel reads the real count on the device
+    }
+    if (launch_solve(h, wp, st, pipe)) return 1;
+  }
+  return 0;
 }
 }  // namespace
 

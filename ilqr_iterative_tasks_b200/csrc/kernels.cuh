@@ -45,6 +45,16 @@ struct Work {
   double* xvar;                // (B,4,N+1)
   double* lamb_out;            // (B)
   int* iters;                  // (B)
+  // ---- mode 0, iteration-sliced passes (see solve_kernel)
+  int pass;                    // 0 = fresh candidates, > 0 = resume parked ones
+  int iter_cap;                // park a candidate that reaches this many iterations unfinished (0 = never)
+  long long park_capacity;     // entries the park buffers hold (a lane that finds them full just keeps iterating)
+  const unsigned long long* resume_count;  // device: entries the previous pass tried to park
+  const int* resume_list;      // candidate ids parked by the previous pass
+  const double* resume_state;  // (capacity, 8N+4): current trajectory slots, lambda, J, iterations
+  unsigned long long* park_count;          // device: entries this pass parks
+  int* park_list;
+  double* park_state;
   // ---- mode 1
   int it;                      // outer iteration 0..2
   double scale;                // 10**it
@@ -120,6 +130,13 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
     // ---- prefetched next candidate
     bool have_next = false, exhausted = false;
     long long n_item = 0;
+    long long n_total = w.n_items;
+    if (w.pass > 0) {
+      n_total = (long long)*w.resume_count;
+      if (n_total > w.park_capacity) n_total = w.park_capacity;
+    }
+    const int park_words = 8 * N + 4;
+    long long n_idx = 0, idx = 0;  // position in the pass's work list (== candidate id in pass 0)
     double n_x0[4], n_xt[4], n_lamb = p.lamb0;
     DevObstacle n_obs;
     n_obs.present = 0;
@@ -132,10 +149,11 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
         if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (!have_next && !exhausted) {
-          n_item = (long long)(base + __popc(want & ((1u << lane) - 1u)));
-          if (n_item >= w.n_items) {
+          n_idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+          if (n_idx >= n_total) {
             exhausted = true;
           } else {
+            n_item = w.pass > 0 ? (long long)w.resume_list[n_idx] : n_idx;
             have_next = true;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -151,6 +169,7 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
       if (state == ST_NEED) {
         if (have_next) {
           item = n_item;
+          idx = n_idx;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             c.x0[i] = n_x0[i];
@@ -159,7 +178,15 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
           c.lamb = n_lamb;
           load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
           sincos_fast(c.x0[3], &c.s0, &c.c0);
-          init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
+          if (w.pass == 0) {
+            init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
+          } else {  // resume a candidate parked by the previous pass
+            const double* ps = w.resume_state + (size_t)idx * park_words;
+            for (int e = 0; e < 8 * N; ++e) s.stc(e, ps[e]);
+            c.lamb = ps[8 * N];
+            c.J = ps[8 * N + 1];
+            c.iters = (int)ps[8 * N + 2];
+          }
           have_next = false;
           state = ST_RUN;
         } else if (exhausted) {
@@ -178,13 +205,37 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
       } else {
         finished = live && ilqr_iteration<kQR, kN>(p, c, s);
       }
+      bool park = false;
       if (live) {
         if (finished) {
-          my_iters += (unsigned long long)c.iters;
           my_solves += 1;
           store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
           if (w.lamb_out) w.lamb_out[item] = c.lamb;
           if (w.iters) w.iters[item] = c.iters;
+          state = ST_NEED;
+        } else if (w.iter_cap > 0 && c.iters >= w.iter_cap) {
+          park = true;
+        }
+        my_iters += 1;
+      }
+      // Iteration slicing: a candidate that is still unfinished at the pass's cap is parked (trajectory,
+      // lambda, J, count) and its lane takes the next one.  The following pass resumes the parked ones packed
+      // into full warps, so the few-percent long tail (up to max_ilqr_iter = 150 iterations against a mean
+      // of ~12) no longer runs as hundreds of trips of nearly empty warps.
+      const unsigned parkers = __ballot_sync(0xffffffffu, park);
+      if (parkers) {
+        unsigned long long pbase = 0;
+        const int leader = __ffs(parkers) - 1;
+        if ((int)lane == leader) pbase = atomicAdd(w.park_count, (unsigned long long)__popc(parkers));
+        pbase = __shfl_sync(0xffffffffu, pbase, leader);
+        const long long pslot = (long long)pbase + __popc(parkers & ((1u << lane) - 1u));
+        if (park && pslot < w.park_capacity) {
+          double* ps = w.park_state + (size_t)pslot * park_words;
+          for (int e = 0; e < 8 * N; ++e) ps[e] = s.ldc(e);
+          ps[8 * N] = c.lamb;
+          ps[8 * N + 1] = c.J;
+          ps[8 * N + 2] = (double)c.iters;
+          w.park_list[pslot] = (int)item;
           state = ST_NEED;
         }
       }

@@ -213,6 +213,18 @@ def test_full_size_properties(eng_mod):
     c = e.solve_batch(d["x0"][perm], d["x_term"][perm], d["lamb_in"][perm], obs[perm])
     for k in a:
         assert np.array_equal(a[k][perm], c[k]), k
+    # the big batch runs as iteration-sliced passes (park / resume): check a sample, weighted towards the
+    # candidates that were parked (>= 32 iterations), against the oracle
+    from oracle import oracle
+
+    long_ids = np.flatnonzero(a["iters"] >= 32)[:3000]
+    sel = np.unique(np.concatenate([long_ids, np.random.default_rng(2).choice(B, 3000, replace=False)]))
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"][sel], d["x_term"][sel], d["lamb_in"][sel], obs[sel], nthreads=8)
+    same = (a["iters"][sel] == iters) & (a["lamb_out"][sel] == lamb)
+    assert same.mean() >= 0.999, "discrete path diverged for %d of %d" % (int((~same).sum()), len(sel))
+    assert H.rel_err(a["xvar"][sel][same], x[same]).max() <= H.RTOL
+    assert H.rel_err(a["uvar"][sel][same], u[same]).max() <= H.RTOL
+    assert (a["iters"][sel] >= 32).sum() >= 2000 and a["iters"].max() == p.max_ilqr_iter
     # lamb_out is lamb_in times a power of ten reached through the reference's /10, *10 sequence
     ratio = np.log10(a["lamb_out"])
     assert np.abs(ratio - np.round(ratio)).max() < 1e-9

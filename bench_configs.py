@@ -71,17 +71,43 @@ def horizon_sweep(device=0):
         p = _abi.default_params(num_horizon=N)
         obs = _abi.obstacle_array(d["obs"], d["mode"])
         e = engine.Engine(p, device=device)
-        e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, want=("iters",))
+        import torch
+
+        def pin(a):  # pinned host buffers: pageable memory would serialise and dominate the timing
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+        d = {k: pin(v) for k, v in d.items()}
+        obs = np.frombuffer(pin(obs.view(np.uint8)), dtype=_abi.OBSTACLE_DTYPE)
+        bufs = {"uvar": pin(np.empty((B, 2, N))), "xvar": pin(np.empty((B, 4, N + 1))), "lamb_out": pin(np.empty(B)), "iters": pin(np.empty(B, dtype=np.int32))}
+        e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, out=bufs)
         t0 = time.perf_counter()
-        out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+        out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, out=bufs)
+        out = {k: v.copy() for k, v in out.items()}
         wall = time.perf_counter() - t0
         st = e.last_stats()
         e.close()
         tf = st["ilqr_iterations"] * flops_per_iteration(N) / (st["kernel_ms"] * 1e-3) / 1e12
+        # optional FP32 build: tolerance gate against the FP64 result of the same inputs
+        e32 = engine.Engine(_abi.default_params(num_horizon=N, precision=1), device=device)
+        o32 = e32.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+        t0 = time.perf_counter()
+        e32.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+        wall32 = time.perf_counter() - t0
+        e32.close()
+        with np.errstate(divide="ignore"):
+            same = (o32["iters"] == out["iters"]) & (np.round(np.log10(o32["lamb_out"])) == np.round(np.log10(out["lamb_out"])))
+        ax = tuple(range(1, 3))
+        err = np.maximum(
+            np.abs(o32["xvar"] - out["xvar"]).max(axis=ax) / np.maximum(1, np.abs(out["xvar"]).max(axis=ax)),
+            np.abs(o32["uvar"] - out["uvar"]).max(axis=ax) / np.maximum(1, np.abs(out["uvar"]).max(axis=ax)),
+        )
         rows.append({
             "N": N, "B": B, "wall_ms": wall * 1e3, "pipeline_ms": st["kernel_ms"], "solves_per_s": B / wall,
             "iters_per_solve": st["ilqr_iterations"] / B, "algorithmic_tflops": tf, "frac_of_fp64_peak": tf / peak,
             "finite": bool(np.isfinite(out["xvar"]).all()),
+            "fp32": {"wall_ms": wall32 * 1e3, "same_discrete_path": float(same.mean()),
+                     "within_1e-4_of_fp64_where_path_matches": float((err[same] <= 1e-4).mean()),
+                     "median_rel_err": float(np.median(err[same]))},
         })  # fmt: skip
     return {"config": "BASELINE config 4a: horizon sweep, host-pointer API (copies inside the timed call)", "fp64_peak_tflops": peak, "rows": rows}
 

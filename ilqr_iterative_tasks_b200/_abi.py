@@ -17,7 +17,7 @@ class Params(C.Structure):
         ("max_relax_iter", C.c_int32),
         ("max_sim_steps", C.c_int32),
         ("obstacle_horizon", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("precision", C.c_int32),
         ("matrix_Q", C.c_double * 16),
         ("matrix_R", C.c_double * 4),
         ("matrix_Qterminal", C.c_double * 16),

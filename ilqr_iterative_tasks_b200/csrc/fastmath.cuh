@@ -136,4 +136,17 @@ I2_HD void sincos_fast(double x, double* sn, double* cs) {
   *cs = ((k + 1) & 2) ? -cc : cc;
 }
 
+// ---- single precision (optional FP32 build): the CUDA library routines are already branch-light in float
+I2_HD float rcp_fast(float x) { return 1.0f / x; }
+I2_HD float exp_fast_bounded(float x) { return expf(x); }
+I2_HD float exp_fast_lo(float x) { return expf(x); }
+I2_HD void sincos_fast(float x, float* sn, float* cs) {
+#ifdef __CUDA_ARCH__
+  sincosf(x, sn, cs);
+#else
+  *sn = sinf(x);
+  *cs = cosf(x);
+#endif
+}
+
 }  // namespace i2lqr

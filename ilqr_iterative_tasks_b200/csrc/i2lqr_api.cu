@@ -129,7 +129,7 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   const size_t smem_full = (size_t)kSolveThreads * 18 * kp.N * sizeof(double);
   const size_t smem_cur = (size_t)kSolveThreads * 8 * kp.N * sizeof(double);
   int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur * 2 <= kSmemLimit ? 2 : 1);
-  const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon;
+  const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon && h->params.precision == 0;
   if (tmem_ok && w.n_items >= 8192) scratch = 3;
   if (force >= 0) scratch = force;
   if (scratch == 3 && !tmem_ok) scratch = 0;
@@ -144,17 +144,35 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   w.stats = h->ctl.p;
   long long blocks_needed = (w.n_items + threads - 1) / threads;
   if (blocks_needed < 1) blocks_needed = 1;
-  using KernelT = void (*)(const KParams, const Work);
-  auto pick = [&](auto mode) -> KernelT {
+  const bool fp32 = h->params.precision == 1;
+  if (fp32 && scratch >= 2) scratch = smem_full / 2 <= kSmemLimit ? 0 : 1;  // FP32 build: shared memory or global slab
+  const size_t rsz = fp32 ? sizeof(float) : sizeof(double);
+  using Kernel64 = void (*)(const KParams, const Work);
+  using Kernel32 = void (*)(const KParamsT<float>, const Work);
+  Kernel64 k64 = nullptr;
+  Kernel32 k32 = nullptr;
+  auto pick64 = [&](auto mode) -> Kernel64 {
     constexpr int M = decltype(mode)::value;
     constexpr int T = kSolveThreads;
-    if (kp.has_qr) return scratch == 0 ? solve_kernel<true, 0, M, T> : (scratch == 1 ? solve_kernel<true, 1, M, T> : solve_kernel<true, 2, M, T>);
-    return scratch == 0 ? solve_kernel<false, 0, M, T> : (scratch == 1 ? solve_kernel<false, 1, M, T> : solve_kernel<false, 2, M, T>);
+    if (kp.has_qr) return scratch == 0 ? solve_kernel<double, true, 0, M, T> : (scratch == 1 ? solve_kernel<double, true, 1, M, T> : solve_kernel<double, true, 2, M, T>);
+    return scratch == 0 ? solve_kernel<double, false, 0, M, T> : (scratch == 1 ? solve_kernel<double, false, 1, M, T> : solve_kernel<double, false, 2, M, T>);
   };
-  KernelT kern = w.mode == 0 ? pick(std::integral_constant<int, 0>()) : pick(std::integral_constant<int, 1>());
-  if (scratch == 3) kern = solve_kernel<false, 3, 0, kTmemThreads>;
+  auto pick32 = [&](auto mode) -> Kernel32 {
+    constexpr int M = decltype(mode)::value;
+    constexpr int T = kSolveThreads;
+    if (kp.has_qr) return scratch == 0 ? solve_kernel<float, true, 0, M, T> : solve_kernel<float, true, 1, M, T>;
+    return scratch == 0 ? solve_kernel<float, false, 0, M, T> : solve_kernel<float, false, 1, M, T>;
+  };
+  if (fp32) {
+    k32 = w.mode == 0 ? pick32(std::integral_constant<int, 0>()) : pick32(std::integral_constant<int, 1>());
+  } else {
+    k64 = w.mode == 0 ? pick64(std::integral_constant<int, 0>()) : pick64(std::integral_constant<int, 1>());
+    if (scratch == 3) k64 = solve_kernel<double, false, 3, 0, kTmemThreads>;
+  }
+  const void* kern = fp32 ? (const void*)k32 : (const void*)k64;
   int per_sm = 0;
-  size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : (scratch == 3 ? (size_t)kTmemThreads * 8 * kp.N * sizeof(double) : 0));
+  size_t smem = scratch == 0 ? smem_full * rsz / sizeof(double)
+                             : (scratch == 2 ? smem_cur : (scratch == 3 ? (size_t)kTmemThreads * 8 * kp.N * sizeof(double) : 0));
   // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
   static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
   if (smem > 0 && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
@@ -168,13 +186,18 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
   if (scratch == 1 || scratch == 2) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
-    CU(h->gscratch[pipe].ensure((size_t)grid * threads * per_lane));
+    CU(h->gscratch[pipe].ensure((size_t)grid * threads * per_lane));  // sized in doubles: enough for either precision
     w.gscratch = h->gscratch[pipe].p;
     w.gstride = grid * threads;
   }
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
   if (debug) fprintf(stderr, "[i2lqr] solve launch: scratch %d grid %lld x %d smem %zu per_sm %d items %lld\n", scratch, grid, threads, smem, per_sm, w.n_items);
-  kern<<<(unsigned)grid, threads, smem, st>>>(kp, w);
+  if (fp32) {
+    const KParamsT<float> kpf = to_float(kp);
+    k32<<<(unsigned)grid, threads, smem, st>>>(kpf, w);
+  } else {
+    k64<<<(unsigned)grid, threads, smem, st>>>(kp, w);
+  }
   CU(cudaGetLastError());
   h->last_launches += 1;
   return 0;
@@ -275,6 +298,7 @@ int i2lqr_set_params(i2lqr_handle* h, const i2lqr_params* p) {
 
 int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capacity, i2lqr_handle** out) {
   if (!p || !out) return fail("null argument");
+  if (p->precision != 0 && p->precision != 1) return fail("precision must be 0 (FP64) or 1 (FP32)");
   if (n_episodes < 0 || lap_capacity < 0) return fail("negative size");
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -438,7 +462,7 @@ int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const
   return end_stats(h, st, false);
 }
 
-// Host-pointer form.  The batch is cut into chunks that flow through three streams -- H2D of chunk i+1, the
+// Host-pointer form.  Big batches are cut into up to 8 chunks that flow through three streams -- H2D of chunk i+1, the
 // solve of chunk i and D2H of chunk i-1 overlap (full-duplex PCIe when the caller's buffers are pinned;
 // pageable buffers still work, the copies then serialise).
 int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
@@ -466,8 +490,10 @@ int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double
     CU(cudaEventRecord(h->ev0, main));  // aux streams start after the statistics reset (and the shared obstacle)
     cudaStream_t streams[1 + kAuxStreams] = {main, h->aux[0], h->aux[1]};
     for (int i = 0; i < kAuxStreams; ++i) CU(cudaStreamWaitEvent(h->aux[i], h->ev0, 0));
-    const int64_t min_chunk = 32768;
-    int64_t n_chunks = std::min<int64_t>(12, std::max<int64_t>(1, B / min_chunk));
+    // chunks stay large enough for iteration slicing: a small launch is dominated by its longest candidate
+    // (150 iterations ~ 2-3 ms), so cutting finer only serialises straggler tails
+    const int64_t min_chunk = kSliceMinBatch;
+    int64_t n_chunks = std::min<int64_t>(8, std::max<int64_t>(1, B / min_chunk));
     const int64_t chunk = (B + n_chunks - 1) / n_chunks;
     const auto* d_obs = reinterpret_cast<const i2lqr_obstacle*>(h->b_obs.p);
     for (int64_t c = 0, lo = 0; lo < B; ++c, lo += chunk) {

@@ -29,7 +29,8 @@
 namespace i2lqr {
 
 // Parameter block in kernel-argument (constant-bank) space, derived on the host from i2lqr_params.
-struct KParams {
+template <typename R>
+struct KParamsT {
   int N;               // current horizon
   int N_param;         // ilqr_param.num_horizon (terminal obstacle advance, ilqr_helper.py:134-139)
   int K, L;            // num_ss_points, num_ss_iter
@@ -37,18 +38,20 @@ struct KParams {
   int max_relax;       // max_relax_iter
   int has_qr;          // matrix_Q != 0 or matrix_R != 0
   int pad0;
-  double dt, dt2;      // timestep, timestep**2
-  double a_max, d_lim; // clip bounds
-  double eps, lamb0, lamb_factor, max_lamb;
-  double cg, ch, cq2;  // control barrier: q1*q2, q1*q2^2, q2
-  double ca_lo, cd_lo; // exp(-2*q2*a_max), exp(-2*q2*delta_lim)
-  double og, oh, oq2;  // obstacle barrier: q1*q2, q1*q2^2, q2
-  double one_margin;   // 1 + safety_margin
-  double xtarget[4];
-  double Qf[10], Qf2[10];  // symmetric upper triangles of Qterminal and 2*Qterminal (00 01 02 03 11 12 13 22 23 33)
-  double Q[10], Q2[10];    // matrix_Q and 2*matrix_Q
-  double R[3], R2[3];      // matrix_R and 2*matrix_R (00 01 11)
+  R dt, dt2;      // timestep, timestep**2
+  R a_max, d_lim; // clip bounds
+  R eps, lamb0, lamb_factor, max_lamb;
+  R cg, ch, cq2;  // control barrier: q1*q2, q1*q2^2, q2
+  R ca_lo, cd_lo; // exp(-2*q2*a_max), exp(-2*q2*delta_lim)
+  R og, oh, oq2;  // obstacle barrier: q1*q2, q1*q2^2, q2
+  R one_margin;   // 1 + safety_margin
+  R xtarget[4];
+  R Qf[10], Qf2[10];  // symmetric upper triangles of Qterminal and 2*Qterminal (00 01 02 03 11 12 13 22 23 33)
+  R Q[10], Q2[10];    // matrix_Q and 2*matrix_Q
+  R Rm[3], R2[3];     // matrix_R and 2*matrix_R (00 01 11)
 };
+
+using KParams = KParamsT<double>;
 
 struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
   double x, y, width, height, spd;
@@ -63,68 +66,72 @@ struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
 //   HybridScratch current trajectory in shared memory, gains in the global slab: 384 instead of 864 bytes of
 //                 shared memory per lane at N=6, i.e. 12 instead of 8 resident warps per SM.
 // Scalar-addressed gains region shared by the memory-backed scratch types.
-template <class Derived>
+template <class Derived, typename R>
 struct GainsByElement {
   static constexpr bool kAligned = false;
-  __device__ __forceinline__ void stg10(int k, const double (&v)[10]) const {
+  __device__ __forceinline__ void stg10(int k, const R (&v)[10]) const {
 #pragma unroll
     for (int i = 0; i < 10; ++i) static_cast<const Derived*>(this)->stg(k * 10 + i, v[i]);
   }
-  __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
+  __device__ __forceinline__ void ldg10(int k, R (&v)[10]) const {
 #pragma unroll
     for (int i = 0; i < 10; ++i) v[i] = static_cast<const Derived*>(this)->ldg(k * 10 + i);
   }
-  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const {
+  __device__ __forceinline__ void stg8(int k, const R (&v)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) static_cast<const Derived*>(this)->stg(k * 10 + i, v[i]);
   }
-  __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const {
+  __device__ __forceinline__ void ldg8(int k, R (&v)[8]) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = static_cast<const Derived*>(this)->ldg(k * 10 + i);
   }
   __device__ __forceinline__ void fence_gains() const {}
 };
-template <int kStride>
-struct SmemScratch : GainsByElement<SmemScratch<kStride>> {
-  double* base;
-  double* gbase;
-  __device__ __forceinline__ void bind(double* smem_lane, double*, long long, int N) {
+template <typename R, int kStride>
+struct SmemScratch : GainsByElement<SmemScratch<R, kStride>, R> {
+  using real = R;
+  R* base;
+  R* gbase;
+  __device__ __forceinline__ void bind(R* smem_lane, R*, long long, int N) {
     base = smem_lane;
     gbase = smem_lane + (size_t)8 * N * kStride;
   }
-  __device__ __forceinline__ double ldc(int e) const { return base[e * kStride]; }
-  __device__ __forceinline__ void stc(int e, double v) const { base[e * kStride] = v; }
-  __device__ __forceinline__ double ldg(int e) const { return gbase[e * kStride]; }
-  __device__ __forceinline__ void stg(int e, double v) const { gbase[e * kStride] = v; }
+  __device__ __forceinline__ R ldc(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void stc(int e, R v) const { base[e * kStride] = v; }
+  __device__ __forceinline__ R ldg(int e) const { return gbase[e * kStride]; }
+  __device__ __forceinline__ void stg(int e, R v) const { gbase[e * kStride] = v; }
 };
-struct GlobalScratch : GainsByElement<GlobalScratch> {
-  double* base;
-  double* gbase;
+template <typename R>
+struct GlobalScratch : GainsByElement<GlobalScratch<R>, R> {
+  using real = R;
+  R* base;
+  R* gbase;
   long long stride;
-  __device__ __forceinline__ void bind(double*, double* glob_lane, long long gstride, int N) {
+  __device__ __forceinline__ void bind(R*, R* glob_lane, long long gstride, int N) {
     base = glob_lane;
     stride = gstride;
     gbase = glob_lane + (size_t)8 * N * gstride;
   }
-  __device__ __forceinline__ double ldc(int e) const { return base[(size_t)e * stride]; }
-  __device__ __forceinline__ void stc(int e, double v) const { base[(size_t)e * stride] = v; }
-  __device__ __forceinline__ double ldg(int e) const { return gbase[(size_t)e * stride]; }
-  __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
+  __device__ __forceinline__ R ldc(int e) const { return base[(size_t)e * stride]; }
+  __device__ __forceinline__ void stc(int e, R v) const { base[(size_t)e * stride] = v; }
+  __device__ __forceinline__ R ldg(int e) const { return gbase[(size_t)e * stride]; }
+  __device__ __forceinline__ void stg(int e, R v) const { gbase[(size_t)e * stride] = v; }
 };
-template <int kStride>
-struct HybridScratch : GainsByElement<HybridScratch<kStride>> {
-  double* base;
-  double* gbase;
+template <typename R, int kStride>
+struct HybridScratch : GainsByElement<HybridScratch<R, kStride>, R> {
+  using real = R;
+  R* base;
+  R* gbase;
   long long stride;
-  __device__ __forceinline__ void bind(double* smem_lane, double* glob_lane, long long gstride, int) {
+  __device__ __forceinline__ void bind(R* smem_lane, R* glob_lane, long long gstride, int) {
     base = smem_lane;
     gbase = glob_lane;
     stride = gstride;
   }
-  __device__ __forceinline__ double ldc(int e) const { return base[e * kStride]; }
-  __device__ __forceinline__ void stc(int e, double v) const { base[e * kStride] = v; }
-  __device__ __forceinline__ double ldg(int e) const { return gbase[(size_t)e * stride]; }
-  __device__ __forceinline__ void stg(int e, double v) const { gbase[(size_t)e * stride] = v; }
+  __device__ __forceinline__ R ldc(int e) const { return base[e * kStride]; }
+  __device__ __forceinline__ void stc(int e, R v) const { base[e * kStride] = v; }
+  __device__ __forceinline__ R ldg(int e) const { return gbase[(size_t)e * stride]; }
+  __device__ __forceinline__ void stg(int e, R v) const { gbase[(size_t)e * stride] = v; }
 };
 #ifdef __CUDACC__
 // TmemScratch: current trajectory in shared memory, gains / trial trajectory in Blackwell tensor memory
@@ -134,6 +141,7 @@ struct HybridScratch : GainsByElement<HybridScratch<kStride>> {
 // why ilqr_iteration is executed convergently by all 32 lanes.
 template <int kStride>
 struct TmemScratch {
+  using real = double;
   static constexpr bool kAligned = true;
   double* base;
   uint32_t taddr;  // (lane quarter << 16) | first column of this CTA's allocation
@@ -205,42 +213,48 @@ __host__ __device__ __forceinline__ int scratch_doubles(int N) { return 18 * N; 
 #define I2_NEW(N, k) ((N)*8 + (k)*10)
 
 // Registers that persist over a candidate's iterations.
-struct Cand {
-  double x0[4], c0, s0;  // initial state, cos / sin of its heading
-  double xt[4];          // terminal target (safe-set point)
-  double lamb, J;        // LM regularisation, cost of the current trajectory
+template <typename R>
+struct CandT {
+  R x0[4], c0, s0;  // initial state, cos / sin of its heading
+  R xt[4];          // terminal target (safe-set point)
+  R lamb, J;        // LM regularisation, cost of the current trajectory
   // obstacle: centre, 1/width^2, 1/height^2, per-stage drift of the centre (left / up), barrier scales.
   // `obstacle is None` is encoded as zero scales and zero P so that the same straight-line code runs.
-  double ox, oy, oP0, oP1, osx, osy, og, oh;
+  R ox, oy, oP0, oP1, osx, osy, og, oh;
   int iters;
 };
+using Cand = CandT<double>;
 
-__device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+template <typename R>
+__device__ __forceinline__ R clipd(R v, R lo, R hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // v^T M v for symmetric M stored as upper triangle
-__device__ __forceinline__ double quad4(const double* M, double a, double b, double c, double d) {
-  double r0 = M[0] * a + M[1] * b + M[2] * c + M[3] * d;
-  double r1 = M[1] * a + M[4] * b + M[5] * c + M[6] * d;
-  double r2 = M[2] * a + M[5] * b + M[7] * c + M[8] * d;
-  double r3 = M[3] * a + M[6] * b + M[8] * c + M[9] * d;
+template <typename R>
+__device__ __forceinline__ R quad4(const R* M, R a, R b, R c, R d) {
+  R r0 = M[0] * a + M[1] * b + M[2] * c + M[3] * d;
+  R r1 = M[1] * a + M[4] * b + M[5] * c + M[6] * d;
+  R r2 = M[2] * a + M[5] * b + M[7] * c + M[8] * d;
+  R r3 = M[3] * a + M[6] * b + M[8] * c + M[9] * d;
   return r0 * a + r1 * b + r2 * c + r3 * d;
 }
-__device__ __forceinline__ double quad2(const double* M, double a, double b) {
+template <typename R>
+__device__ __forceinline__ R quad2(const R* M, R a, R b) {
   return (M[0] * a + M[1] * b) * a + (M[1] * a + M[2] * b) * b;
 }
 
 // Obstacle ellipse barrier at position (px,py), `step` stages ahead: gradient (2) and Gauss-Newton Hessian
 // (00,01,11) of q1*exp(q2*h), h = 1 + margin - d^T P d   (ilqr_helper.py:32-51,118-149, :59-64).
 // The centre is (x_o - step*spd, y_o) when moving left, (x_o, y_o + step*spd) when moving up.
-__device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c, double px, double py, int step,
-                                                 double& g0, double& g1, double& h00, double& h01, double& h11) {
-  const double st = (double)step;
-  const double cx = c.ox - st * c.osx, cy = c.oy + st * c.osy;
-  const double d0 = px - cx, d1 = py - cy;
-  const double h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
-  const double hd0 = (-2.0 * c.oP0) * d0, hd1 = (-2.0 * c.oP1) * d1;
-  const double e = exp_fast_lo(p.oq2 * h);  // h <= 1 + margin: only underflow needs guarding
-  const double c1 = c.og * e, c2 = c.oh * e;
+template <typename R>
+__device__ __forceinline__ void obstacle_barrier(const KParamsT<R>& p, const CandT<R>& c, R px, R py, int step,
+                                                 R& g0, R& g1, R& h00, R& h01, R& h11) {
+  const R st = R(step);
+  const R cx = c.ox - st * c.osx, cy = c.oy + st * c.osy;
+  const R d0 = px - cx, d1 = py - cy;
+  const R h = p.one_margin - ((d0 * c.oP0) * d0 + (d1 * c.oP1) * d1);
+  const R hd0 = (-R(2.0) * c.oP0) * d0, hd1 = (-R(2.0) * c.oP1) * d1;
+  const R e = exp_fast_lo(p.oq2 * h);  // h <= 1 + margin: only underflow needs guarding
+  const R c1 = c.og * e, c2 = c.oh * e;
   g0 = c1 * hd0;
   g1 = c1 * hd1;
   h00 = c2 * (hd0 * hd0);
@@ -253,59 +267,61 @@ __device__ __forceinline__ void obstacle_barrier(const KParams& p, const Cand& c
 // reference's own runs: SURVEY.md 8a, a5) the clamp is the identity and the result is exactly
 // (Quu + lamb I)^-1, evaluated here in closed form with one reciprocal.  Otherwise the symmetric
 // eigen-decomposition is done by one Jacobi rotation (stable when |b| << |a-d|).
-__device__ __forceinline__ void quu_inverse(double a, double b, double d, double lamb, double& i00, double& i01,
-                                            double& i11) {
-  if (a * d - b * b >= 0.0 && a + d >= 0.0) {
-    const double al = a + lamb, dl = d + lamb;
-    const double r = rcp_fast(al * dl - b * b);
+template <typename R>
+__device__ __forceinline__ void quu_inverse(R a, R b, R d, R lamb, R& i00, R& i01,
+                                            R& i11) {
+  if (a * d - b * b >= R(0.0) && a + d >= R(0.0)) {
+    const R al = a + lamb, dl = d + lamb;
+    const R r = rcp_fast(al * dl - b * b);
     i00 = dl * r;
     i01 = -b * r;
     i11 = al * r;
     return;
   }
-  double c = 1.0, s = 0.0, e1 = a, e2 = d;
-  if (b != 0.0) {
-    double tau = (d - a) / (2.0 * b);
-    double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-    c = 1.0 / sqrt(1.0 + t * t);
+  R c = R(1.0), s = R(0.0), e1 = a, e2 = d;
+  if (b != R(0.0)) {
+    R tau = (d - a) / (R(2.0) * b);
+    R t = (tau >= R(0.0) ? R(1.0) : -R(1.0)) / (fabs(tau) + sqrt(R(1.0) + tau * tau));
+    c = R(1.0) / sqrt(R(1.0) + t * t);
     s = t * c;
     e1 = a - t * b;
     e2 = d + t * b;
   }
-  e1 = (e1 < 0.0 ? 0.0 : e1) + lamb;
-  e2 = (e2 < 0.0 ? 0.0 : e2) + lamb;
-  double r1 = 1.0 / e1, r2 = 1.0 / e2;
+  e1 = (e1 < R(0.0) ? R(0.0) : e1) + lamb;
+  e2 = (e2 < R(0.0) ? R(0.0) : e2) + lamb;
+  R r1 = R(1.0) / e1, r2 = R(1.0) / e2;
   i00 = c * r1 * c + s * r2 * s;
   i01 = s * r2 * c - c * r1 * s;
   i11 = s * r1 * s + c * r2 * c;
 }
 
 // Terminal cost (x_N - x_t)^T Qf (x_N - x_t)
-__device__ __forceinline__ double terminal_cost(const KParams& p, const Cand& c, const double* xN) {
+template <typename R>
+__device__ __forceinline__ R terminal_cost(const KParamsT<R>& p, const CandT<R>& c, const R* xN) {
   return quad4(p.Qf, xN[0] - c.xt[0], xN[1] - c.xt[1], xN[2] - c.xt[2], xN[3] - c.xt[3]);
 }
 
 // Candidate start (utils/base.py:405-410 + the first rollout of iterative_ilqr.py:32-48).  With u0 == null the
 // inputs are zero (what calc_input passes): heading and speed stay put and every stage reuses
 // cos/sin(theta_0).  u0 (2,N) is the warm start of a direct `ilqr()` call.
-template <bool kQR, int kN, class Scratch>
-__device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const Scratch& s, const double* u0) {
+template <bool kQR, int kN, class Scratch, typename R = typename Scratch::real>
+__device__ __forceinline__ void init_candidate(const KParamsT<R>& p, CandT<R>& c, const Scratch& s, const double* u0) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
-  double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
-  double cs = c.c0, sn = c.s0;
-  double J = 0.0;
+  R x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
+  R cs = c.c0, sn = c.s0;
+  R J = R(0.0);
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
-    double ua = 0.0, ud = 0.0;
+    R ua = R(0.0), ud = R(0.0);
     if (u0 != nullptr) {
-      ua = clipd(u0[k], -p.a_max, p.a_max);
-      ud = clipd(u0[N + k], -p.d_lim, p.d_lim);
+      ua = clipd(R(u0[k]), -p.a_max, p.a_max);
+      ud = clipd(R(u0[N + k]), -p.d_lim, p.d_lim);
     }
     if (kQR) {
-      const double l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
-      J = J + l_state + quad2(p.R, ua, ud);
+      const R l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
+      J = J + l_state + quad2(p.Rm, ua, ud);
     }
-    const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
+    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
     x[0] = x[0] + cs * sd;
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;
@@ -325,26 +341,26 @@ __device__ __forceinline__ void init_candidate(const KParams& p, Cand& c, const 
 }
 
 // Backward Riccati pass over the current trajectory; leaves the gains in the new-slots.
-template <bool kQR, int kN, class Scratch>
-__device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, const Scratch& s) {
+template <bool kQR, int kN, class Scratch, typename R = typename Scratch::real>
+__device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<R>& c, const Scratch& s) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
-  const double dt = p.dt;
+  const R dt = p.dt;
   // ---- value function at the horizon end: get_cost_final (ilqr_helper.py:106-150)
-  double xN[4];
+  R xN[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
-  double Vx0, Vx1, Vx2, Vx3;
+  R Vx0, Vx1, Vx2, Vx3;
   {
-    double e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
+    R e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
     Vx0 = p.Qf2[0] * e0 + p.Qf2[1] * e1 + p.Qf2[2] * e2 + p.Qf2[3] * e3;
     Vx1 = p.Qf2[1] * e0 + p.Qf2[4] * e1 + p.Qf2[5] * e2 + p.Qf2[6] * e3;
     Vx2 = p.Qf2[2] * e0 + p.Qf2[5] * e1 + p.Qf2[7] * e2 + p.Qf2[8] * e3;
     Vx3 = p.Qf2[3] * e0 + p.Qf2[6] * e1 + p.Qf2[8] * e2 + p.Qf2[9] * e3;
   }
-  double V00 = p.Qf2[0], V01 = p.Qf2[1], V02 = p.Qf2[2], V03 = p.Qf2[3], V11 = p.Qf2[4], V12 = p.Qf2[5],
+  R V00 = p.Qf2[0], V01 = p.Qf2[1], V02 = p.Qf2[2], V03 = p.Qf2[3], V11 = p.Qf2[4], V12 = p.Qf2[5],
          V13 = p.Qf2[6], V22 = p.Qf2[7], V23 = p.Qf2[8], V33 = p.Qf2[9];
   {
-    double g0, g1, h00, h01, h11;
+    R g0, g1, h00, h01, h11;
     obstacle_barrier(p, c, xN[0], xN[1], p.N_param, g0, g1, h00, h01, h11);
     Vx0 += g0;
     Vx1 += g1;
@@ -355,10 +371,10 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = N - 1; k >= 0; --k) {
     // ---- trajectory at stage k
-    const double ua = s.ldc(I2_CUR(k) + 0), ud = s.ldc(I2_CUR(k) + 1);
-    const double v1 = s.ldc(I2_CUR(k) + 4);                               // v_{k+1}
-    const double cs = s.ldc(I2_CUR(k) + 6), sn = s.ldc(I2_CUR(k) + 7);     // cos / sin theta_{k+1}
-    double xk[4];
+    const R ua = s.ldc(I2_CUR(k) + 0), ud = s.ldc(I2_CUR(k) + 1);
+    const R v1 = s.ldc(I2_CUR(k) + 4);                               // v_{k+1}
+    const R cs = s.ldc(I2_CUR(k) + 6), sn = s.ldc(I2_CUR(k) + 7);     // cos / sin theta_{k+1}
+    R xk[4];
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xk[i] = c.x0[i];
@@ -371,43 +387,43 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
       }
     }
     // ---- linearisation at (v_{k+1}, theta_{k+1}, a_k): iterative_ilqr.py:92-99, kinetic_bicycle.py:30-52
-    const double sp = v1 * dt + (ua * p.dt2) / 2.0;
-    const double al = cs * dt, be = -sp * sn, ga = sn * dt, de = sp * cs;
-    const double b0 = p.dt2 * cs / 2.0, b1 = p.dt2 * sn / 2.0;
+    const R sp = v1 * dt + (ua * p.dt2) / R(2.0);
+    const R al = cs * dt, be = -sp * sn, ga = sn * dt, de = sp * cs;
+    const R b0 = p.dt2 * cs / R(2.0), b1 = p.dt2 * sn / R(2.0);
     // ---- stage cost derivatives: ilqr_helper.py:25-55, input barriers :83-103
-    double lu0, lu1, luu00, luu11;
+    R lu0, lu1, luu00, luu11;
     {
       // the lower-bound barriers are the reciprocals of the upper-bound ones up to a constant:
       // exp(q2(-ubar - u)) = exp(-2 q2 ubar) / exp(q2(u - ubar)) -- two exp + two reciprocals instead of four exp;
       // u is clipped, so the exponents lie in [-2 q2 ubar, 0] and need no range guard
-      const double e1 = exp_fast_bounded(p.cq2 * (ua - p.a_max)), e3 = exp_fast_bounded(p.cq2 * (ud - p.d_lim));
-      const double e2 = p.ca_lo * rcp_fast(e1), e4 = p.cd_lo * rcp_fast(e3);
+      const R e1 = exp_fast_bounded(p.cq2 * (ua - p.a_max)), e3 = exp_fast_bounded(p.cq2 * (ud - p.d_lim));
+      const R e2 = p.ca_lo * rcp_fast(e1), e4 = p.cd_lo * rcp_fast(e3);
       lu0 = p.cg * e1 - p.cg * e2;
       lu1 = p.cg * e3 - p.cg * e4;
       luu00 = p.ch * e1 + p.ch * e2;
       luu11 = p.ch * e3 + p.ch * e4;
     }
-    double g0, g1, l00, l01, l11;  // obstacle barrier: gradient and Hessian of the position block
+    R g0, g1, l00, l01, l11;  // obstacle barrier: gradient and Hessian of the position block
     obstacle_barrier(p, c, xk[0], xk[1], k, g0, g1, l00, l01, l11);
     // ---- Q-function (iterative_ilqr.py:112-116), products written as nested fma chains
-    const double G0 = fma(dt, V02, fma(b1, V01, b0 * V00)), G1 = fma(dt, V12, fma(b1, V11, b0 * V01));
-    const double G2 = fma(dt, V22, fma(b1, V12, b0 * V02)), G3 = fma(dt, V23, fma(b1, V13, b0 * V03));
-    const double H0 = dt * V03, H1 = dt * V13, H2 = dt * V23, H3 = dt * V33;
-    const double X02 = fma(al, G0, fma(ga, G1, G2)), X03 = fma(be, G0, fma(de, G1, G3));  // Qux row 0 = [G0 G1 X02 X03]
-    const double X12 = fma(al, H0, fma(ga, H1, H2)), X13 = fma(be, H0, fma(de, H1, H3));  // Qux row 1 = [H0 H1 X12 X13]
-    const double W02 = fma(al, V00, fma(ga, V01, V02)), W12 = fma(al, V01, fma(ga, V11, V12));
-    const double W22 = fma(al, V02, fma(ga, V12, V22)), W03 = fma(be, V00, fma(de, V01, V03));
-    const double W13 = fma(be, V01, fma(de, V11, V13)), W23 = fma(be, V02, fma(de, V12, V23));
-    const double W33 = fma(be, V03, fma(de, V13, V33));
-    double Qx0, Qx1, Qx2, Qx3, Qu0, Qu1, Quu00, Quu01, Quu10, Quu11;
-    double M00, M01, M02, M03, M11, M12, M13, M22, M23, M33;
+    const R G0 = fma(dt, V02, fma(b1, V01, b0 * V00)), G1 = fma(dt, V12, fma(b1, V11, b0 * V01));
+    const R G2 = fma(dt, V22, fma(b1, V12, b0 * V02)), G3 = fma(dt, V23, fma(b1, V13, b0 * V03));
+    const R H0 = dt * V03, H1 = dt * V13, H2 = dt * V23, H3 = dt * V33;
+    const R X02 = fma(al, G0, fma(ga, G1, G2)), X03 = fma(be, G0, fma(de, G1, G3));  // Qux row 0 = [G0 G1 X02 X03]
+    const R X12 = fma(al, H0, fma(ga, H1, H2)), X13 = fma(be, H0, fma(de, H1, H3));  // Qux row 1 = [H0 H1 X12 X13]
+    const R W02 = fma(al, V00, fma(ga, V01, V02)), W12 = fma(al, V01, fma(ga, V11, V12));
+    const R W22 = fma(al, V02, fma(ga, V12, V22)), W03 = fma(be, V00, fma(de, V01, V03));
+    const R W13 = fma(be, V01, fma(de, V11, V13)), W23 = fma(be, V02, fma(de, V12, V23));
+    const R W33 = fma(be, V03, fma(de, V13, V33));
+    R Qx0, Qx1, Qx2, Qx3, Qu0, Qu1, Quu00, Quu01, Quu10, Quu11;
+    R M00, M01, M02, M03, M11, M12, M13, M22, M23, M33;
     if (kQR) {
-      const double d0 = xk[0] - p.xtarget[0], d1 = xk[1] - p.xtarget[1], d2 = xk[2] - p.xtarget[2],
+      const R d0 = xk[0] - p.xtarget[0], d1 = xk[1] - p.xtarget[1], d2 = xk[2] - p.xtarget[2],
                    d3 = xk[3] - p.xtarget[3];
-      const double lx0 = (p.Q2[0] * d0 + p.Q2[1] * d1 + p.Q2[2] * d2 + p.Q2[3] * d3) + g0;
-      const double lx1 = (p.Q2[1] * d0 + p.Q2[4] * d1 + p.Q2[5] * d2 + p.Q2[6] * d3) + g1;
-      const double lx2 = p.Q2[2] * d0 + p.Q2[5] * d1 + p.Q2[7] * d2 + p.Q2[8] * d3;
-      const double lx3 = p.Q2[3] * d0 + p.Q2[6] * d1 + p.Q2[8] * d2 + p.Q2[9] * d3;
+      const R lx0 = (p.Q2[0] * d0 + p.Q2[1] * d1 + p.Q2[2] * d2 + p.Q2[3] * d3) + g0;
+      const R lx1 = (p.Q2[1] * d0 + p.Q2[4] * d1 + p.Q2[5] * d2 + p.Q2[6] * d3) + g1;
+      const R lx2 = p.Q2[2] * d0 + p.Q2[5] * d1 + p.Q2[7] * d2 + p.Q2[8] * d3;
+      const R lx3 = p.Q2[3] * d0 + p.Q2[6] * d1 + p.Q2[8] * d2 + p.Q2[9] * d3;
       lu0 = (p.R2[0] * ua + p.R2[1] * ud) + lu0;
       lu1 = (p.R2[1] * ua + p.R2[2] * ud) + lu1;
       luu00 += p.R2[0];
@@ -451,22 +467,22 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
     Quu00 = fma(G2, dt, fma(G1, b1, fma(G0, b0, luu00)));
     Quu11 = fma(H3, dt, luu11);
     // ---- regularised inverse and gains: iterative_ilqr.py:118-126
-    double i00, i01, i11;
-    quu_inverse(Quu00, (Quu01 + Quu10) / 2.0, Quu11, c.lamb, i00, i01, i11);
-    const double k0 = -fma(i01, Qu1, i00 * Qu0), k1 = -fma(i11, Qu1, i01 * Qu0);
-    const double K00 = -fma(i01, H0, i00 * G0), K01 = -fma(i01, H1, i00 * G1);
-    const double K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
-    const double K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
-    const double K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
+    R i00, i01, i11;
+    quu_inverse(Quu00, (Quu01 + Quu10) / R(2.0), Quu11, c.lamb, i00, i01, i11);
+    const R k0 = -fma(i01, Qu1, i00 * Qu0), k1 = -fma(i11, Qu1, i01 * Qu0);
+    const R K00 = -fma(i01, H0, i00 * G0), K01 = -fma(i01, H1, i00 * G1);
+    const R K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
+    const R K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
+    const R K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
     {
-      const double gv[10] = {k0, k1, K00, K01, K02, K03, K10, K11, K12, K13};
+      const R gv[10] = {k0, k1, K00, K01, K02, K03, K10, K11, K12, K13};
       s.stg10(k, gv);
     }
     // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
-    const double P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
-    const double P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
-    const double P20 = fma(K12, Quu10, K02 * Quu00), P21 = fma(K12, Quu11, K02 * Quu01);
-    const double P30 = fma(K13, Quu10, K03 * Quu00), P31 = fma(K13, Quu11, K03 * Quu01);
+    const R P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
+    const R P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
+    const R P20 = fma(K12, Quu10, K02 * Quu00), P21 = fma(K12, Quu11, K02 * Quu01);
+    const R P30 = fma(K13, Quu10, K03 * Quu00), P31 = fma(K13, Quu11, K03 * Quu01);
     Vx0 = fma(-P01, k1, fma(-P00, k0, Qx0));
     Vx1 = fma(-P11, k1, fma(-P10, k0, Qx1));
     Vx2 = fma(-P21, k1, fma(-P20, k0, Qx2));
@@ -487,20 +503,20 @@ __device__ __forceinline__ void backward_pass(const KParams& p, const Cand& c, c
 // Full-step forward pass (iterative_ilqr.py:133-160).  Consumes the gains, leaves the trial trajectory in
 // the new-slots, returns cost_new; Jtarget is the cost the reference would recompute for the trial
 // trajectory at the top of its next iteration (stage cost about xtarget, iterative_ilqr.py:43-48).
-template <bool kQR, int kN, class Scratch>
-__device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, const Scratch& s, double& Jtarget) {
+template <bool kQR, int kN, class Scratch, typename R = typename Scratch::real>
+__device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& c, const Scratch& s, R& Jtarget) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
-  double x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
-  double cs = c.c0, sn = c.s0;
-  double Jn = 0.0, Jt = 0.0;
-  double g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
+  R x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
+  R cs = c.c0, sn = c.s0;
+  R Jn = R(0.0), Jt = R(0.0);
+  R g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
   s.ldg10(0, g);
 #pragma unroll
   for (int i = 0; i < 10; ++i) gn[i] = g[i];
 #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
-    if (k + 1 < N) s.ldg10(k + 1, gn);
-    double xo[4];
+    s.ldg10(k + 1 < N ? k + 1 : k, gn);  // clamped, not conditional: the prefetch must never leave the lane's strip
+    R xo[4];
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = c.x0[i];
@@ -508,31 +524,31 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = s.ldc(I2_CUR(k - 1) + 2 + i);
     }
-    const double uo0 = s.ldc(I2_CUR(k) + 0), uo1 = s.ldc(I2_CUR(k) + 1);
-    const double d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
-    double ua = (uo0 + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
-    double ud = (uo1 + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
+    const R uo0 = s.ldc(I2_CUR(k) + 0), uo1 = s.ldc(I2_CUR(k) + 1);
+    const R d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
+    R ua = (uo0 + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
+    R ud = (uo1 + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
     ua = clipd(ua, -p.a_max, p.a_max);
     ud = clipd(ud, -p.d_lim, p.d_lim);
     if (kQR) {
-      const double l_ctrl = quad2(p.R, ua, ud);
+      const R l_ctrl = quad2(p.Rm, ua, ud);
       Jn = Jn + quad4(p.Q, x[0] - c.xt[0], x[1] - c.xt[1], x[2] - c.xt[2], x[3] - c.xt[3]) + l_ctrl;
       Jt = Jt + quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]) + l_ctrl;
     }
-    const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
+    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
     x[0] = x[0] + cs * sd;
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;
     x[3] = x[3] + ud * p.dt;
     sincos_fast(x[3], &sn, &cs);
     {
-      const double tv[8] = {ua, ud, x[0], x[1], x[2], x[3], cs, sn};
+      const R tv[8] = {ua, ud, x[0], x[1], x[2], x[3], cs, sn};
       s.stg8(k, tv);
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) g[i] = gn[i];
   }
-  const double T = terminal_cost(p, c, x);
+  const R T = terminal_cost(p, c, x);
   Jtarget = Jt + T;
   return Jn + T;
 }
@@ -541,23 +557,23 @@ __device__ __forceinline__ double forward_pass(const KParams& p, const Cand& c, 
 // Returns true when the candidate's loop ends.  Written so that every lane of a warp can execute it
 // convergently (lanes without a live candidate pass live = false and only burn their own scratch): the
 // tensor-memory scratch needs warp-aligned accesses.
-template <bool kQR, int kN, class Scratch>
-__device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const Scratch& s, bool live = true) {
+template <bool kQR, int kN, class Scratch, typename R = typename Scratch::real>
+__device__ __forceinline__ bool ilqr_iteration(const KParamsT<R>& p, CandT<R>& c, const Scratch& s, bool live = true) {
   backward_pass<kQR, kN>(p, c, s);
   s.fence_gains();
-  double Jt;
-  const double Jn = forward_pass<kQR, kN>(p, c, s, Jt);
+  R Jt;
+  const R Jn = forward_pass<kQR, kN>(p, c, s, Jt);
   s.fence_gains();
   const int N = kN > 0 ? kN : p.N;
   const bool accept = live && Jn < c.J;
   if (Scratch::kAligned || accept) {
     // trial -> current; the trial of stage k+1 is loaded while stage k is stored
-    double t[8], tn[8];
+    R t[8], tn[8];
     s.ldg8(0, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) tn[i] = t[i];
     for (int k = 0; k < N; ++k) {
-      if (k + 1 < N) s.ldg8(k + 1, tn);
+      s.ldg8(k + 1 < N ? k + 1 : k, tn);  // clamped prefetch (see forward_pass)
       if (accept) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, t[i]);
@@ -581,9 +597,10 @@ __device__ __forceinline__ bool ilqr_iteration(const KParams& p, Cand& c, const 
 }
 
 // Relax-cost ladder (utils/base.py:427-437); `scale` = 10**it of the outer iteration.
-__device__ __forceinline__ double relax_cost(const KParams& p, const double* xN, const double* xt, double qfun,
-                                             double scale) {
-  const double e0 = xN[0] - xt[0], e1 = xN[1] - xt[1], e2 = xN[2] - xt[2], e3 = xN[3] - xt[3];
+template <typename R>
+__device__ __forceinline__ double relax_cost(const KParamsT<R>& p, const R* xN, const R* xt, double qfun, double scale) {
+  const double e0 = (double)xN[0] - (double)xt[0], e1 = (double)xN[1] - (double)xt[1], e2 = (double)xN[2] - (double)xt[2],
+               e3 = (double)xN[3] - (double)xt[3];
   const double r = sqrt(e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3);
   for (int i = 1; i <= p.max_relax; ++i) {
     if (r <= 80.0 * i / scale) return qfun + p.N + 100 * i;
@@ -593,8 +610,8 @@ __device__ __forceinline__ double relax_cost(const KParams& p, const double* xN,
 }
 
 // Result in the reference's array layout: xvar (4, N+1), uvar (2, N), time on the last axis.
-template <int kN, class Scratch>
-__device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c, const Scratch& s, double* xvar,
+template <int kN, class Scratch, typename R = typename Scratch::real>
+__device__ __forceinline__ void store_candidate(const KParamsT<R>& p, const CandT<R>& c, const Scratch& s, double* xvar,
                                                 double* uvar) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   if (xvar) {
@@ -615,18 +632,19 @@ __device__ __forceinline__ void store_candidate(const KParams& p, const Cand& c,
   }
 }
 
-__device__ __forceinline__ void load_obstacle(const KParams& p, Cand& c, const DevObstacle* o) {
+template <typename R>
+__device__ __forceinline__ void load_obstacle(const KParamsT<R>& p, CandT<R>& c, const DevObstacle* o) {
   if (o != nullptr && o->present) {
-    c.ox = o->x;
-    c.oy = o->y;
-    c.oP0 = 1.0 / (o->width * o->width);
-    c.oP1 = 1.0 / (o->height * o->height);
-    c.osx = o->moving_option == 2 ? o->spd : 0.0;
-    c.osy = o->moving_option == 1 ? o->spd : 0.0;
+    c.ox = R(o->x);
+    c.oy = R(o->y);
+    c.oP0 = R(1.0 / (o->width * o->width));
+    c.oP1 = R(1.0 / (o->height * o->height));
+    c.osx = R(o->moving_option == 2 ? o->spd : 0.0);
+    c.osy = R(o->moving_option == 1 ? o->spd : 0.0);
     c.og = p.og;
     c.oh = p.oh;
   } else {
-    c.ox = c.oy = c.oP0 = c.oP1 = c.osx = c.osy = c.og = c.oh = 0.0;
+    c.ox = c.oy = c.oP0 = c.oP1 = c.osx = c.osy = c.og = c.oh = R(0.0);
   }
 }
 

@@ -88,18 +88,21 @@ constexpr int kTmemMaxHorizon = 6;
 
 // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab),
 //           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8)
-template <int kScratch, int kThreads>
+template <typename R, int kScratch, int kThreads>
 struct ScratchSelect {
-  using type = typename std::conditional<kScratch == 0, SmemScratch<kThreads>,
-               typename std::conditional<kScratch == 1, GlobalScratch,
-               typename std::conditional<kScratch == 2, HybridScratch<kThreads>, TmemScratch<kThreads>>::type>::type>::type;
+  using type = typename std::conditional<kScratch == 0, SmemScratch<R, kThreads>,
+               typename std::conditional<kScratch == 1, GlobalScratch<R>,
+               typename std::conditional<kScratch == 2, HybridScratch<R, kThreads>, TmemScratch<kThreads>>::type>::type>::type;
 };
 
-template <bool kQR, int kScratch, int kMode, int kThreads>
+// R = double is the product path (results within 1e-9 of the reference); R = float is the optional FP32
+// build of BASELINE config 4 (inputs / outputs stay double, everything in between is single precision).
+template <typename R, bool kQR, int kScratch, int kMode, int kThreads>
 __global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : 1)
-solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) {
-  extern __shared__ double smem[];
-  using ScratchT = typename ScratchSelect<kScratch, kThreads>::type;
+solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
+  extern __shared__ double smem_raw[];
+  R* smem = reinterpret_cast<R*>(smem_raw);
+  using ScratchT = typename ScratchSelect<R, kScratch, kThreads>::type;
   ScratchT s;
   __shared__ uint32_t tmem_base;
   if constexpr (kScratch == 3) {
@@ -114,14 +117,14 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     s.bind_tmem(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
-    for (int e = 0; e < 8 * p.N; ++e) s.stc(e, 0.0);  // lanes without a live candidate iterate on zeros
+    for (int e = 0; e < 8 * p.N; ++e) s.stc(e, R(0.0));  // lanes without a live candidate iterate on zeros
   } else {
-    s.bind(smem + threadIdx.x, w.gscratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
+    s.bind(smem + threadIdx.x, reinterpret_cast<R*>(w.gscratch) + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
   }
   constexpr int kN = 0;  // stage loops stay rolled: the fully unrolled N=6 body measured 1.4x slower (I-cache, spills)
   const unsigned lane = threadIdx.x & 31u;
   const int N = p.N;
-  Cand c = {};
+  CandT<R> c = {};
   int state = ST_NEED;
   long long item = 0;
   unsigned long long my_iters = 0, my_solves = 0;
@@ -137,7 +140,7 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
     }
     const int park_words = 8 * N + 4;
     long long n_idx = 0, idx = 0;  // position in the pass's work list (== candidate id in pass 0)
-    double n_x0[4], n_xt[4], n_lamb = p.lamb0;
+    double n_x0[4], n_xt[4], n_lamb = (double)p.lamb0;
     DevObstacle n_obs;
     n_obs.present = 0;
     for (;;) {
@@ -172,19 +175,19 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
           idx = n_idx;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            c.x0[i] = n_x0[i];
-            c.xt[i] = n_xt[i];
+            c.x0[i] = R(n_x0[i]);
+            c.xt[i] = R(n_xt[i]);
           }
-          c.lamb = n_lamb;
+          c.lamb = R(n_lamb);
           load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
           sincos_fast(c.x0[3], &c.s0, &c.c0);
           if (w.pass == 0) {
             init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
           } else {  // resume a candidate parked by the previous pass
             const double* ps = w.resume_state + (size_t)idx * park_words;
-            for (int e = 0; e < 8 * N; ++e) s.stc(e, ps[e]);
-            c.lamb = ps[8 * N];
-            c.J = ps[8 * N + 1];
+            for (int e = 0; e < 8 * N; ++e) s.stc(e, R(ps[e]));
+            c.lamb = R(ps[8 * N]);
+            c.J = R(ps[8 * N + 1]);
             c.iters = (int)ps[8 * N + 2];
           }
           have_next = false;
@@ -210,7 +213,7 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
         if (finished) {
           my_solves += 1;
           store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
-          if (w.lamb_out) w.lamb_out[item] = c.lamb;
+          if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
           if (w.iters) w.iters[item] = c.iters;
           state = ST_NEED;
         } else if (w.iter_cap > 0 && c.iters >= w.iter_cap) {
@@ -231,9 +234,9 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
         const long long pslot = (long long)pbase + __popc(parkers & ((1u << lane) - 1u));
         if (park && pslot < w.park_capacity) {
           double* ps = w.park_state + (size_t)pslot * park_words;
-          for (int e = 0; e < 8 * N; ++e) ps[e] = s.ldc(e);
-          ps[8 * N] = c.lamb;
-          ps[8 * N + 1] = c.J;
+          for (int e = 0; e < 8 * N; ++e) ps[e] = (double)s.ldc(e);
+          ps[8 * N] = (double)c.lamb;
+          ps[8 * N + 1] = (double)c.J;
           ps[8 * N + 2] = (double)c.iters;
           w.park_list[pslot] = (int)item;
           state = ST_NEED;
@@ -270,7 +273,7 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
               c.lamb = p.lamb0;  // utils/base.py:393
               load_obstacle(p, c, w.ep_obs + ep);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) c.x0[i] = w.x[(size_t)ep * 4 + i];
+              for (int i = 0; i < 4; ++i) c.x0[i] = R(w.x[(size_t)ep * 4 + i]);
               sincos_fast(c.x0[3], &c.s0, &c.c0);
               state = ST_INIT;
             }
@@ -281,7 +284,7 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
       if (state == ST_INIT) {
         jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c.xt[i] = lap[(size_t)i * w.set.Tcap + jsel];
+        for (int i = 0; i < 4; ++i) c.xt[i] = R(lap[(size_t)i * w.set.Tcap + jsel]);
         init_candidate<kQR, kN>(p, c, s, nullptr);
         state = ST_RUN;
       }
@@ -292,12 +295,12 @@ solve_kernel(const __grid_constant__ KParams p, const __grid_constant__ Work w) 
           my_solves += 1;
           const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
           store_candidate<kN>(p, c, s, w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
-          double xN[4];
+          R xN[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
           const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
           w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
-          w.cand_lamb[tslot] = c.lamb;
+          w.cand_lamb[tslot] = (double)c.lamb;
           w.cand_iters[tslot] = c.iters;
           ++rank;
           state = rank < cnt ? ST_INIT : ST_NEED;  // lambda is carried to the lap's next candidate

@@ -57,15 +57,30 @@ inline const char* fill_kparams(const i2lqr_params& p, KParams* k) {
   upper4(p.matrix_Qterminal, 2.0, k->Qf2);
   upper4(p.matrix_Q, 1.0, k->Q);
   upper4(p.matrix_Q, 2.0, k->Q2);
-  k->R[0] = p.matrix_R[0];
-  k->R[1] = p.matrix_R[1];
-  k->R[2] = p.matrix_R[3];
-  for (int i = 0; i < 3; ++i) k->R2[i] = 2.0 * k->R[i];
+  k->Rm[0] = p.matrix_R[0];
+  k->Rm[1] = p.matrix_R[1];
+  k->Rm[2] = p.matrix_R[3];
+  for (int i = 0; i < 3; ++i) k->R2[i] = 2.0 * k->Rm[i];
   bool qr = false;
   for (int i = 0; i < 16; ++i) qr = qr || p.matrix_Q[i] != 0.0;
   for (int i = 0; i < 4; ++i) qr = qr || p.matrix_R[i] != 0.0;
   k->has_qr = qr;
   return nullptr;
+}
+
+// Single-precision copy of the parameter block for the optional FP32 build.
+inline KParamsT<float> to_float(const KParams& k) {
+  KParamsT<float> f;
+  f.N = k.N; f.N_param = k.N_param; f.K = k.K; f.L = k.L; f.max_iter = k.max_iter; f.max_relax = k.max_relax;
+  f.has_qr = k.has_qr; f.pad0 = 0;
+  f.dt = (float)k.dt; f.dt2 = (float)k.dt2; f.a_max = (float)k.a_max; f.d_lim = (float)k.d_lim;
+  f.eps = (float)k.eps; f.lamb0 = (float)k.lamb0; f.lamb_factor = (float)k.lamb_factor; f.max_lamb = (float)k.max_lamb;
+  f.cg = (float)k.cg; f.ch = (float)k.ch; f.cq2 = (float)k.cq2; f.ca_lo = (float)k.ca_lo; f.cd_lo = (float)k.cd_lo;
+  f.og = (float)k.og; f.oh = (float)k.oh; f.oq2 = (float)k.oq2; f.one_margin = (float)k.one_margin;
+  for (int i = 0; i < 4; ++i) f.xtarget[i] = (float)k.xtarget[i];
+  for (int i = 0; i < 10; ++i) { f.Qf[i] = (float)k.Qf[i]; f.Qf2[i] = (float)k.Qf2[i]; f.Q[i] = (float)k.Q[i]; f.Q2[i] = (float)k.Q2[i]; }
+  for (int i = 0; i < 3; ++i) { f.Rm[i] = (float)k.Rm[i]; f.R2[i] = (float)k.R2[i]; }
+  return f;
 }
 
 }  // namespace i2lqr

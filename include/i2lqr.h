@@ -41,7 +41,8 @@ typedef struct i2lqr_params {
   int32_t obstacle_horizon; /* steps the obstacle is advanced for the terminal barrier: the reference uses
                                ilqr_param.num_horizon there (control/ilqr_helper.py:134-139) even when ilqr() is
                                called with another num_horizon; 0 = same as num_horizon */
-  int32_t reserved1;
+  int32_t precision;      /* 0 = FP64 (the product path, parity <= 1e-9); 1 = optional FP32 build (BASELINE config 4:
+                             <= 1e-4 against FP64 on single solves whose discrete path matches); I/O stays double */
   double matrix_Q[16];         /* default 0 */
   double matrix_R[4];          /* default 0 */
   double matrix_Qterminal[16]; /* default 2*diag(1,1,20,0.02) */

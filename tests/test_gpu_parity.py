@@ -231,6 +231,49 @@ def test_full_size_properties(eng_mod):
     e.close()
 
 
+@pytest.mark.parametrize("N", [6, 10, 25, 50])
+def test_fp32_build_tolerance(eng_mod, N):
+    """BASELINE config 4 gate for the optional FP32 build (params.precision = 1): on single solves from
+    identical inputs, FP32 agrees with FP64 within 1e-4 relative wherever the discrete path (iteration count
+    and lambda exponent) is the same; the fraction whose path diverged is reported, not hidden."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+
+    B = 4096
+    d = synth.flat_candidates(B, N, seed=5 + N)
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e64 = eng_mod.Engine(_abi.default_params(num_horizon=N))
+    e32 = eng_mod.Engine(_abi.default_params(num_horizon=N, precision=1))
+    a = e64.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    b = e32.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    same = (a["iters"] == b["iters"]) & (np.round(np.log10(a["lamb_out"])) == np.round(np.log10(b["lamb_out"])))
+    err = np.maximum(H.rel_err(b["xvar"], a["xvar"]), H.rel_err(b["uvar"], a["uvar"]))
+    within = (err[same] <= 1e-4).mean()
+    print("FP32 N=%d: same discrete path %.1f%%, of those within 1e-4: %.2f%% (median %.1e)" % (N, 100 * same.mean(), 100 * within, np.median(err[same])))
+    assert same.mean() >= 0.85
+    assert within >= 0.99
+    assert np.median(err[same]) <= 1e-5
+    assert np.isfinite(b["xvar"]).all()
+    e64.close()
+    e32.close()
+
+
+def test_fp32_controller_step_runs(eng_mod):
+    """The FP32 build also drives the controller step (lambda chains); decisions may differ from FP64 on
+    closed loops, so only sanity is checked here: same winner on an easy step, finite prediction."""
+    g = H.load("steps_stock.npz")
+    from ilqr_iterative_tasks_b200 import _abi
+
+    p = _abi.default_params(num_ss_points=int(g["K"]), num_ss_iter=int(g["L"]), precision=1)
+    e = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+    e.add_lap(0, g["lap0"])
+    s = int(g["solve_ids"][5])
+    e.set_obstacle(0, H.step_obstacle(g, s))
+    out = e.solve_step(g["step/x"][s].reshape(1, 4))
+    assert np.isfinite(out["x_pred"]).all() and out["winner_idx"][0] >= 0
+    assert np.abs(out["x_pred"][0] - g["solve/x_pred"][5]).max() <= 1e-2 * max(1.0, np.abs(g["solve/x_pred"][5]).max())
+    e.close()
+
+
 def test_error_paths(eng_mod):
     from ilqr_iterative_tasks_b200 import _abi
 

@@ -66,3 +66,26 @@ u, x, lo, it = solve(p, d["x0"], d["x_term"], d["lamb_in"], obs)
 uo, xo, loo, ito = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
 ok = (it == ito) & (lo == loo)
 print("oracle sample %d: discrete mismatches %d (%.4f%%), rel err x %.2e u %.2e, mean iters %.3f" % (n, (~ok).sum(), 100 * (~ok).mean(), H.rel_err(x[ok], xo[ok]).max(), H.rel_err(u[ok], uo[ok]).max(), it.mean()))
+
+# ---- FP32 build vs FP64 (BASELINE config 4 gate: <= 1e-4 where the discrete path matches)
+def solve32(p, x0, xt, lamb, obs):
+    kp = C.create_string_buffer(lib.host_kparams_size())
+    lib.host_fill_kparams(C.byref(p), kp)
+    B, N = x0.shape[0], p.num_horizon
+    u = np.zeros((B, 2, N)); x = np.zeros((B, 4, N + 1)); lo = np.zeros(B); it = np.zeros(B, dtype=np.int32)
+    x0 = np.ascontiguousarray(x0); xt = np.ascontiguousarray(xt); lamb = np.ascontiguousarray(lamb)
+    lib.host_solve_f32(kp, C.c_int64(B), x0.ctypes.data_as(dp), xt.ctypes.data_as(dp), lamb.ctypes.data_as(dp),
+                       obs.ctypes.data_as(C.c_void_p), C.c_int64(B), u.ctypes.data_as(dp), x.ctypes.data_as(dp),
+                       lo.ctypes.data_as(dp), it.ctypes.data_as(C.POINTER(C.c_int32)))
+    return u, x, lo, it
+
+
+for N in (6, 10, 25, 50):
+    d = synth.flat_candidates(4096, N, seed=5 + N)
+    p = _abi.default_params(num_horizon=N); obs = _abi.obstacle_array(d["obs"], d["mode"])
+    u64, x64, l64, i64 = solve(p, d["x0"], d["x_term"], d["lamb_in"], obs)
+    u32, x32, l32, i32 = solve32(p, d["x0"], d["x_term"], d["lamb_in"], obs)
+    same = i64 == i32
+    ex = H.rel_err(x32[same], x64[same]); eu = H.rel_err(u32[same], u64[same])
+    print("FP32 N=%d: same iteration count %.1f%%; of those rel err x p50 %.1e p99 %.1e max %.1e | u max %.1e; within 1e-4: %.1f%%"
+          % (N, 100 * same.mean(), np.median(ex), np.percentile(ex, 99), ex.max(), eu.max(), 100 * (np.maximum(ex, eu) <= 1e-4).mean()))

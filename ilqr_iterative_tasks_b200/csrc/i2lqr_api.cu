@@ -100,6 +100,8 @@ struct i2lqr_handle {
   DevBuf<double> q_x0;
   // batched episodes (K4)
   bool ep_ready = false;
+  unsigned long long ep_noise_seed = 0;  // 0 = noise off (every reference script calls set_zero_noise)
+  int ep_lap_index = 0;
   DevBuf<double> ep_upred, ep_goal, ep_lapx, ep_lapu;
   DevBuf<int> ep_step, ep_done, ep_horizon, ep_pb, ep_active, ep_status, ep_nrun, ep_laplen;
   DevBuf<DevObstacle> d_obs0;
@@ -329,16 +331,18 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
     CU(cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming));
   }
   CU(h->ctl.ensure(kCtlWords));
-  CU(cudaMemset(h->ctl.p, 0, kCtlWords * sizeof(unsigned long long)));
+  // initialisation goes through the handle's own (non-blocking) stream: a legacy-stream cudaMemset is not
+  // ordered against it and could land after the first add_lap / launch
+  CU(cudaMemsetAsync(h->ctl.p, 0, kCtlWords * sizeof(unsigned long long), h->stream));
   if (n_episodes > 0) {
     if (lap_capacity <= p->num_horizon) return fail("lap_capacity must exceed num_horizon");
     const size_t ss_n = (size_t)h->E * h->L * 4 * h->Tcap;
     CU(cudaMalloc(&h->set.ss, ss_n * sizeof(double)));
-    CU(cudaMemset(h->set.ss, 0, ss_n * sizeof(double)));
+    CU(cudaMemsetAsync(h->set.ss, 0, ss_n * sizeof(double), h->stream));
     CU(cudaMalloc(&h->set.lap_len, sizeof(int) * h->E * h->L));
     CU(cudaMalloc(&h->set.lap_count, sizeof(int) * h->E));
-    CU(cudaMemset(h->set.lap_len, 0, sizeof(int) * h->E * h->L));
-    CU(cudaMemset(h->set.lap_count, 0, sizeof(int) * h->E));
+    CU(cudaMemsetAsync(h->set.lap_len, 0, sizeof(int) * h->E * h->L, h->stream));
+    CU(cudaMemsetAsync(h->set.lap_count, 0, sizeof(int) * h->E, h->stream));
     h->set.L = h->L;
     h->set.Tcap = h->Tcap;
     h->h_lap_len.assign((size_t)h->E * h->L, 0);
@@ -346,6 +350,7 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
     DevObstacle none{};
     h->h_obs.assign(h->E, none);
   }
+  CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return 0;
 }
@@ -796,6 +801,13 @@ int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* go
   CU(cudaMemcpyAsync(h->ep_horizon.p, hor.data(), E * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
   h->ep_ready = true;
+  h->ep_lap_index = 0;
+  return 0;
+}
+
+int i2lqr_episodes_set_noise(i2lqr_handle* h, uint64_t seed) {
+  if (!h) return fail("null handle");
+  h->ep_noise_seed = seed;
   return 0;
 }
 
@@ -822,7 +834,8 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
     episode_pre_kernel<<<gb, tb, 0, st>>>(es, E, N);
     CU(cudaGetLastError());
     if (run_step(h, E, h->ep_active.p, st)) return 1;
-    episode_post_kernel<<<gb, tb, 0, st>>>(es, h->kp, h->s_u.p, h->s_upred.p, h->s_shrink.p, E, i, h->params.goal_tol);
+    episode_post_kernel<<<gb, tb, 0, st>>>(es, h->kp, h->s_u.p, h->s_upred.p, h->s_shrink.p, E, i, h->params.goal_tol,
+                                           h->ep_noise_seed, h->ep_lap_index);
     CU(cudaGetLastError());
     h->last_launches += 2;
     CU(cudaMemcpyAsync(h->h_nrun, h->ep_nrun.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -833,6 +846,7 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
   CU(cudaGetLastError());
   h->last_launches += 1;
   if (end_stats(h, st, true)) return 1;
+  h->ep_lap_index += 1;
   // host mirrors of the safe-set bookkeeping
   CU(cudaMemcpy(h->h_lap_len.data(), h->set.lap_len, sizeof(int) * (size_t)E * h->L, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(h->h_lap_count.data(), h->set.lap_count, sizeof(int) * (size_t)E, cudaMemcpyDeviceToHost));

@@ -519,8 +519,30 @@ __global__ void episode_pre_kernel(EpisodeState s, int E, int N_param) {
   s.active[e] = (!s.done[e] && s.horizon[e] == N_param) ? 1 : 0;
 }
 
+// Philox4x32-10 counter-based generator (Salmon et al. 2011): one 128-bit block per (episode, lap, step).
+__device__ __forceinline__ void philox4x32(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ key0, n2 = hi0 ^ c3 ^ key1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    key0 += 0x9E3779B9u;
+    key1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
 __global__ void episode_post_kernel(EpisodeState s, const __grid_constant__ KParams p, const double* u_solve,
-                                    const double* upred_solve, const int* shrink, int E, int sim_i, double goal_tol) {
+                                    const double* upred_solve, const int* shrink, int E, int sim_i, double goal_tol,
+                                    unsigned long long noise_seed, int lap_index) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E || s.done[e]) return;
   const int N = p.N;
@@ -549,7 +571,22 @@ __global__ void episode_post_kernel(EpisodeState s, const __grid_constant__ KPar
   double sn, cs;
   sincos_fast(x[3], &sn, &cs);
   const double sd = x[2] * p.dt + (ua * p.dt2) / 2.0;
-  const double x0 = x[0] + cs * sd, x1 = x[1] + sn * sd, x2 = x[2] + ua * p.dt, x3 = x[3] + ud * p.dt;
+  const double x0 = x[0] + cs * sd, x1 = x[1] + sn * sd;
+  double x2 = x[2] + ua * p.dt, x3 = x[3] + ud * p.dt;
+  if (noise_seed != 0) {
+    // plant noise of KineticBicycle.forward_dynamics (utils/base.py:207-211): clipped Gaussians on speed and
+    // heading; two normals per step by Box-Muller from one Philox block keyed by (seed, episode, lap, step)
+    uint32_t r[4];
+    philox4x32((uint32_t)noise_seed, (uint32_t)(noise_seed >> 32), (uint32_t)e, (uint32_t)lap_index, (uint32_t)s.step[e], 0x1234567u, r);
+    const double u1 = ((double)r[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)r[1] * (1.0 / 4294967296.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn2, cs2;
+    sincos(6.283185307179586 * u2, &sn2, &cs2);
+    const double noise_v = fmax(-0.05, fmin(rad * cs2 * 0.01, 0.05));
+    const double noise_theta = fmax(-0.05, fmin(rad * sn2 * 0.005, 0.05));
+    x2 += 0.5 * noise_v;
+    x3 += 0.5 * noise_theta;
+  }
   x[0] = x0;
   x[1] = x1;
   x[2] = x2;

@@ -25,7 +25,7 @@ EXPORTS = [
     "i2lqr_abi_version", "i2lqr_last_error", "i2lqr_default_params", "i2lqr_create", "i2lqr_destroy",
     "i2lqr_set_params", "i2lqr_solve_batch", "i2lqr_solve_batch_device", "i2lqr_add_lap", "i2lqr_num_laps",
     "i2lqr_set_obstacle", "i2lqr_select_knn", "i2lqr_solve_step", "i2lqr_get_step_trace",
-    "i2lqr_episodes_begin", "i2lqr_episodes_run_lap", "i2lqr_episodes_status", "i2lqr_last_stats", "i2lqr_sync_stats",
+    "i2lqr_episodes_begin", "i2lqr_episodes_run_lap", "i2lqr_episodes_status", "i2lqr_episodes_set_noise", "i2lqr_last_stats", "i2lqr_sync_stats",
     "i2lqr_measure_fp64_peak",
 ]  # fmt: skip
 
@@ -209,6 +209,9 @@ class Engine:
         lu = np.empty((E, S, 2)) if want_traj else None
         _check(lib().i2lqr_episodes_run_lap(self._h, lap_len.ctypes.data_as(_i32p), _d(lx), _d(lu)))
         return (lap_len, lx, lu) if want_traj else lap_len
+
+    def episodes_set_noise(self, seed):
+        _check(lib().i2lqr_episodes_set_noise(self._h, C.c_uint64(seed)))
 
     def episodes_status(self):
         st = np.empty(self.n_episodes, dtype=np.int32)

@@ -11,7 +11,7 @@ from . import _abi, engine, synth
 
 
 class EpisodeBatch:
-    def __init__(self, params, x0, obstacles=None, initial_lap=None, device=0, lap_capacity=None):
+    def __init__(self, params, x0, obstacles=None, initial_lap=None, device=0, lap_capacity=None, noise_seed=0):
         """x0 (E,4) first-lap start states; obstacles: None or structured array (E) of i2lqr_obstacle;
         initial_lap (T,4): the feasible first lap every episode starts from (default: the reference's
         scripted lap, KineticBicycle.get_traj)."""
@@ -30,6 +30,8 @@ class EpisodeBatch:
                 o = _abi.Obstacle.from_buffer_copy(obstacles[e].tobytes())
                 self.engine.set_obstacle(e, o)
         self.engine.episodes_begin(x0, self.initial_lap[-1])
+        if noise_seed:  # plant noise of utils/base.py:207-211 (off in every reference script)
+            self.engine.episodes_set_noise(noise_seed)
         self.laps_run = 0
 
     def set_obstacles(self, obstacles):

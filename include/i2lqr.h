@@ -140,6 +140,11 @@ int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* go
  * episode's safe set.  lap_x : optional (E, max_sim_steps+1, 4); lap_u : optional (E, max_sim_steps, 2). */
 int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, double* lap_u);
 
+/* Plant noise of KineticBicycle.forward_dynamics (iterative_ilqr/utils/base.py:207-211): clipped Gaussians on
+ * speed and heading, drawn on the device from a counter-based generator keyed by (seed, episode, lap, step).
+ * seed = 0 (default) switches the noise off, as `set_zero_noise()` does in every reference script. */
+int i2lqr_episodes_set_noise(i2lqr_handle* h, uint64_t seed);
+
 /* Per-episode status of the last lap: 0 reached the goal, 1 stopped at max_sim_steps ("not finished",
  * :722-726), 2 playback ran out of inputs (IndexError in the reference), 3 lap too short/long to store. */
 int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status);

@@ -131,3 +131,31 @@ def test_episode_batch_random_scenarios_vs_oracle():
             assert lens[e] == len(ref[lap + 1]) - 1, (e, lap, lens[e], len(ref[lap + 1]) - 1)
             err = np.abs(lx[e, : lens[e] + 1] - ref[lap + 1]).max()
             assert err < 1e-6, (e, lap, err)
+
+
+def test_episode_noise_is_bounded_and_reproducible():
+    """Plant noise (utils/base.py:207-211) from the device-side counter RNG: same seed -> identical laps,
+    another seed -> different laps, and every step's deviation from the noise-free model stays within the
+    reference's clip (0.5 * 0.05 on speed and heading)."""
+    from ilqr_iterative_tasks_b200 import _abi, episodes, synth
+
+    p = _abi.default_params(num_ss_points=8, num_ss_iter=1)
+    lap0, _ = synth.initial_lap()
+    runs = []
+    for seed in (7, 7, 8):
+        eb = episodes.EpisodeBatch(p, np.zeros((4, 4)), initial_lap=lap0, noise_seed=seed)
+        lens, lx, lu = eb.run_lap(want_traj=True)
+        runs.append((lens.copy(), lx.copy(), lu.copy()))
+        eb.close()
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][0], runs[1][0])
+    assert not np.array_equal(runs[0][1], runs[2][1])
+    lens, lx, lu = runs[0]
+    assert not np.array_equal(lx[0], lx[1])  # episodes draw different noise
+    for e in range(4):
+        for k in range(int(lens[e]) - 1):  # the last row is snapped to the goal
+            x, u = lx[e, k], lu[e, k]
+            travel = x[2] + u[0] / 2
+            clean = np.array([x[0] + np.cos(x[3]) * travel, x[1] + np.sin(x[3]) * travel, x[2] + u[0], x[3] + u[1]])
+            dev = lx[e, k + 1] - clean
+            assert np.abs(dev[:2]).max() < 1e-9 and np.abs(dev[2:]).max() <= 0.025 + 1e-12
+    assert np.abs(lx[0, 1:int(lens[0])] - lx[1, 1:int(lens[0])]).max() > 1e-6

@@ -188,6 +188,28 @@ def test_multi_episode_step_equals_single(eng_mod):
     big.close()
 
 
+def test_handle_recreation_is_race_free(eng_mod):
+    """Regression: handle initialisation used legacy-stream cudaMemset calls that were not ordered against the
+    handle's non-blocking stream, so the first add_lap could be wiped (episode 0 lost its lap ~3 % of the
+    time when handles were created back to back).  Identical episodes must give identical answers."""
+    g = H.load("steps_stock.npz")
+    p = H.step_params(g)
+    x = np.tile(g["step/x"][int(g["solve_ids"][2])], (3, 1))
+    ref = None
+    for _ in range(60):
+        e = eng_mod.Engine(p, n_episodes=3, lap_capacity=128)
+        for k in range(3):
+            e.add_lap(k, g["lap0"])
+            e.set_obstacle(k, H.step_obstacle(g, int(g["solve_ids"][2])))
+        out = e.solve_step(x)
+        e.close()
+        assert np.array_equal(out["u"][0], out["u"][1]) and np.array_equal(out["u"][0], out["u"][2])
+        assert out["winner_idx"][0] == out["winner_idx"][2]
+        if ref is None:
+            ref = out["u"].copy()
+        assert np.array_equal(out["u"], ref)
+
+
 def test_full_size_properties(eng_mod):
     """BASELINE config 5 at full size (2^20 candidates): size-independent properties.
     determinism (bit-identical reruns), permutation equivariance (results do not depend on which lane or in

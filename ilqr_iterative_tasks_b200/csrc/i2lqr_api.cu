@@ -205,6 +205,59 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   return 0;
 }
 
+// Controller-step form: chain_kernel with kRungs speculative lambda rungs per chain.  The rung count follows the
+// load: rungs trade idle lanes for fewer sequential trips, so they are used while every warp still has an SM
+// sub-partition of its own and dropped once the chains alone fill the GPU.
+template <typename R, int kRungs>
+const void* pick_chain(bool has_qr, int scratch) {
+  if (has_qr) return scratch == 0 ? (const void*)chain_kernel<R, true, 0, kRungs> : (scratch == 1 ? (const void*)chain_kernel<R, true, 1, kRungs> : (const void*)chain_kernel<R, true, 2, kRungs>);
+  return scratch == 0 ? (const void*)chain_kernel<R, false, 0, kRungs> : (scratch == 1 ? (const void*)chain_kernel<R, false, 1, kRungs> : (const void*)chain_kernel<R, false, 2, kRungs>);
+}
+
+int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
+  const KParams& kp = h->kp;
+  const bool fp32 = h->params.precision == 1;
+  const size_t rsz = fp32 ? sizeof(float) : sizeof(double);
+  const size_t smem_full = (size_t)kSolveThreads * 18 * kp.N * rsz;
+  const size_t smem_cur = (size_t)kSolveThreads * 8 * kp.N * rsz;
+  static const int force = getenv("I2LQR_SCRATCH") ? atoi(getenv("I2LQR_SCRATCH")) : -1;  // tuning switch
+  int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur * 2 <= kSmemLimit ? 2 : 1);
+  if (force >= 0 && force <= 2) scratch = force;
+  if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
+  if (scratch == 2 && smem_cur > kSmemLimit) scratch = 1;
+  if (fp32 && scratch == 2) scratch = 1;
+  static const int force_rungs = getenv("I2LQR_RUNGS") ? atoi(getenv("I2LQR_RUNGS")) : 0;  // tuning switch
+  const long long slots = 4LL * h->n_sms;  // one warp per SM sub-partition
+  int rungs = w.n_items * 4 <= slots * 32 ? 4 : (w.n_items * 2 <= slots * 32 ? 2 : 1);
+  if (force_rungs == 1 || force_rungs == 2 || force_rungs == 4) rungs = force_rungs;
+  const void* kern;
+  if (fp32)
+    kern = rungs == 4 ? pick_chain<float, 4>(kp.has_qr, scratch) : (rungs == 2 ? pick_chain<float, 2>(kp.has_qr, scratch) : pick_chain<float, 1>(kp.has_qr, scratch));
+  else
+    kern = rungs == 4 ? pick_chain<double, 4>(kp.has_qr, scratch) : (rungs == 2 ? pick_chain<double, 2>(kp.has_qr, scratch) : pick_chain<double, 1>(kp.has_qr, scratch));
+  const size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
+  if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const long long lanes = w.n_items * rungs;
+  const long long grid = std::max<long long>(1, (lanes + kSolveThreads - 1) / kSolveThreads);
+  if (scratch != 0) {
+    const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
+    CU(h->gscratch[0].ensure((size_t)grid * kSolveThreads * per_lane));
+    w.gscratch = h->gscratch[0].p;
+    w.gstride = grid * kSolveThreads;
+  }
+  CU(h->ctl.ensure(kCtlWords));
+  w.counter = nullptr;
+  w.stats = h->ctl.p;
+  static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[i2lqr] chain launch: rungs %d scratch %d grid %lld smem %zu chains %lld\n", rungs, scratch, grid, smem, w.n_items);
+  const KParamsT<float> kpf = fp32 ? to_float(kp) : KParamsT<float>{};
+  void* args[2] = {fp32 ? (void*)&kpf : (void*)&kp, (void*)&w};
+  CU(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kSolveThreads), args, smem, st));
+  h->last_launches += 1;
+  return 0;
+}
+
 int begin_stats(i2lqr_handle* h, cudaStream_t st) {
   h->last_launches = 0;
   CU(h->ctl.ensure(kCtlWords));
@@ -677,7 +730,7 @@ int run_step(i2lqr_handle* h, int n_episodes, const int* d_active, cudaStream_t 
     w.cand_cost = h->s_cand_cost.p;
     w.cand_lamb = h->s_cand_lamb.p;
     w.cand_iters = h->s_cand_iters.p;
-    if (launch_solve(h, w, st)) return 1;
+    if (launch_chain(h, w, st)) return 1;
 
     WinnerArgs wa{};
     wa.n_episodes = n_episodes;

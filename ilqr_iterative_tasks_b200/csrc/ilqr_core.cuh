@@ -100,6 +100,8 @@ struct SmemScratch : GainsByElement<SmemScratch<R, kStride>, R> {
   __device__ __forceinline__ void stc(int e, R v) const { base[e * kStride] = v; }
   __device__ __forceinline__ R ldg(int e) const { return gbase[e * kStride]; }
   __device__ __forceinline__ void stg(int e, R v) const { gbase[e * kStride] = v; }
+  // gains / trial region of the lane `delta` positions away in the same warp (speculative lambda rungs)
+  __device__ __forceinline__ R ldg_lane(int delta, int e) const { return gbase[e * kStride + delta]; }
 };
 template <typename R>
 struct GlobalScratch : GainsByElement<GlobalScratch<R>, R> {
@@ -116,6 +118,7 @@ struct GlobalScratch : GainsByElement<GlobalScratch<R>, R> {
   __device__ __forceinline__ void stc(int e, R v) const { base[(size_t)e * stride] = v; }
   __device__ __forceinline__ R ldg(int e) const { return gbase[(size_t)e * stride]; }
   __device__ __forceinline__ void stg(int e, R v) const { gbase[(size_t)e * stride] = v; }
+  __device__ __forceinline__ R ldg_lane(int delta, int e) const { return gbase[(size_t)e * stride + delta]; }
 };
 template <typename R, int kStride>
 struct HybridScratch : GainsByElement<HybridScratch<R, kStride>, R> {
@@ -132,6 +135,7 @@ struct HybridScratch : GainsByElement<HybridScratch<R, kStride>, R> {
   __device__ __forceinline__ void stc(int e, R v) const { base[e * kStride] = v; }
   __device__ __forceinline__ R ldg(int e) const { return gbase[(size_t)e * stride]; }
   __device__ __forceinline__ void stg(int e, R v) const { gbase[(size_t)e * stride] = v; }
+  __device__ __forceinline__ R ldg_lane(int delta, int e) const { return gbase[(size_t)e * stride + delta]; }
 };
 #ifdef __CUDACC__
 // TmemScratch: current trajectory in shared memory, gains / trial trajectory in Blackwell tensor memory

@@ -325,6 +325,149 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
   }
 }
 
+// ------------------------------------------------------------------------------- K2, controller-step form
+// Lambda chains with speculative Levenberg-Marquardt rungs.  The K candidates of one (episode, lap) are a
+// sequential chain (lambda is carried, utils/base.py:393,414-426), and inside a candidate every rejected
+// iteration repeats the backward and forward pass from the SAME trajectory with lambda * 10
+// (iterative_ilqr.py:74-84; no line search) -- half of all iterations of a closed-loop run are
+// rejects.  kRungs adjacent lanes therefore own one chain: all hold the same current trajectory, lane r
+// evaluates the iteration with lambda * 10^r (the exact value the reference would reach after r rejects), and
+// the group then accepts in the reference's order -- the first rung whose trial cost is below the current cost
+// wins, the rungs before it count as the rejected iterations they are, the rungs after it are discarded.  One
+// trip of the warp loop thus consumes 1..kRungs reference iterations; results are bit-identical to the
+// one-lane chain (same code, same operands).  A chain is a static work item: lane group g of the grid owns
+// chain g.
+template <typename R, bool kQR, int kScratch, int kRungs>
+__global__ void __launch_bounds__(kSolveThreads, 1)
+chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
+  extern __shared__ double smem_raw[];
+  R* smem = reinterpret_cast<R*>(smem_raw);
+  using ScratchT = typename ScratchSelect<R, kScratch, kSolveThreads>::type;
+  static_assert(kScratch != 3, "the controller-step kernel keeps its scratch in memory");
+  ScratchT s;
+  s.bind(smem + threadIdx.x, reinterpret_cast<R*>(w.gscratch) + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
+  constexpr int kN = 0;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int rung = lane % kRungs;
+  const int gbase_lane = lane - rung;  // first lane of this chain's group
+  const int N = p.N;
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kRungs;
+  CandT<R> c = {};
+  int state = ST_DONE;
+  int rank = 0, cnt = 0, ep = 0, lrel = 0, T = 0;
+  const double* lap = nullptr;
+  long long jsel = 0;
+  unsigned long long my_iters = 0, my_solves = 0;
+  if (item < w.n_items) {
+    ep = (int)(item / w.set.L);
+    lrel = (int)(item % w.set.L);
+    cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
+    if (cnt > 0) {
+      const int count = w.set.lap_count[ep];
+      const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
+      const int slot = (min_iter + lrel) % w.set.L;
+      T = w.set.lap_len[(size_t)ep * w.set.L + slot];
+      lap = w.set.lap(ep, slot);
+      c.lamb = p.lamb0;  // utils/base.py:393
+      load_obstacle(p, c, w.ep_obs + ep);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c.x0[i] = R(w.x[(size_t)ep * 4 + i]);
+      sincos_fast(c.x0[3], &c.s0, &c.c0);
+      state = ST_INIT;
+    }
+  }
+  for (;;) {
+    if (__all_sync(kFull, state == ST_DONE)) break;
+    if (state == ST_INIT) {
+      jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c.xt[i] = R(lap[(size_t)i * w.set.Tcap + jsel]);
+      init_candidate<kQR, kN>(p, c, s, nullptr);  // every rung keeps its own copy of the current trajectory
+      state = ST_RUN;
+    }
+    __syncwarp();
+    const bool run = state == ST_RUN;
+    R Jn = R(0.0), Jt = R(0.0);
+    if (run) {
+      const R lamb_chain = c.lamb;
+      for (int r = 0; r < rung; ++r) c.lamb *= p.lamb_factor;  // the value r rejects lead to, same operations
+      backward_pass<kQR, kN>(p, c, s);
+      Jn = forward_pass<kQR, kN>(p, c, s, Jt);
+      c.lamb = lamb_chain;
+    }
+    __syncwarp();  // trial trajectories are read across lanes below
+    const unsigned acc_all = __ballot_sync(kFull, run && Jn < c.J);
+    const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
+    // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
+    int winner = -1;
+    bool fin = false;
+    int consumed = 0;
+    R lamb = c.lamb;
+    if (run) {
+#pragma unroll
+      for (int r = 0; r < kRungs; ++r) {
+        if (winner >= 0 || fin) break;
+        if (c.iters + consumed >= p.max_iter) {
+          fin = true;
+          break;
+        }
+        ++consumed;
+        if ((acc >> r) & 1u) {
+          winner = r;
+          lamb /= p.lamb_factor;
+        } else {
+          lamb *= p.lamb_factor;
+          if (lamb > p.max_lamb) fin = true;
+        }
+      }
+    }
+    const int src = winner >= 0 ? gbase_lane + winner : lane;
+    const R Jn_w = __shfl_sync(kFull, Jn, src), Jt_w = __shfl_sync(kFull, Jt, src);
+    if (run) {
+      if (winner >= 0) {
+        const int delta = winner - rung;
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, s.ldg_lane(delta, k * 10 + i));
+        }
+        if (fabs((Jn_w - c.J) / c.J) < p.eps) fin = true;
+        c.J = kQR ? Jt_w : Jn_w;
+      }
+      c.lamb = lamb;
+      c.iters += consumed;
+      if (c.iters >= p.max_iter) fin = true;
+    }
+    __syncwarp();  // the winner's trial slots are overwritten by the next trip only after everyone copied them
+    if (run && fin) {
+      const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
+      const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
+      if (rung == 0) {
+        my_iters += (unsigned long long)c.iters;
+        my_solves += 1;
+        store_candidate<kN>(p, c, s, w.cand_x + cslot * 4 * (N + 1), nullptr);
+        R xN[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
+        w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
+        w.cand_lamb[tslot] = (double)c.lamb;
+        w.cand_iters[tslot] = c.iters;
+      }
+      if (rung == kRungs - 1) store_candidate<kN>(p, c, s, nullptr, w.cand_u + cslot * 2 * N);
+      ++rank;
+      state = rank < cnt ? ST_INIT : ST_DONE;  // lambda is carried to the lap's next candidate
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_iters += __shfl_xor_sync(kFull, my_iters, o);
+    my_solves += __shfl_xor_sync(kFull, my_solves, o);
+  }
+  if (lane == 0 && w.stats != nullptr && my_solves) {
+    atomicAdd(w.stats + 0, my_iters);
+    atomicAdd(w.stats + 1, my_solves);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // One warp per (episode, active lap).  The lap's SoA rows are read coalesced, the 1-norm distances
 // ((|dx|+|dy|)+|dv|)+|dtheta| (same association as scipy's norm, bit-exact) are staged in

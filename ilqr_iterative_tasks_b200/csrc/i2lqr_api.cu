@@ -214,6 +214,11 @@ const void* pick_chain(bool has_qr, int scratch) {
   return scratch == 0 ? (const void*)chain_kernel<R, false, 0, kRungs> : (scratch == 1 ? (const void*)chain_kernel<R, false, 1, kRungs> : (const void*)chain_kernel<R, false, 2, kRungs>);
 }
 
+template <typename R, int kRungs>
+const void* pick_chain_lat(bool has_qr) {
+  return has_qr ? (const void*)chain_lat_kernel<R, true, kRungs> : (const void*)chain_lat_kernel<R, false, kRungs>;
+}
+
 int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   const KParams& kp = h->kp;
   const bool fp32 = h->params.precision == 1;
@@ -235,7 +240,18 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
     kern = rungs == 4 ? pick_chain<float, 4>(kp.has_qr, scratch) : (rungs == 2 ? pick_chain<float, 2>(kp.has_qr, scratch) : pick_chain<float, 1>(kp.has_qr, scratch));
   else
     kern = rungs == 4 ? pick_chain<double, 4>(kp.has_qr, scratch) : (rungs == 2 ? pick_chain<double, 2>(kp.has_qr, scratch) : pick_chain<double, 1>(kp.has_qr, scratch));
-  const size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
+  size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
+  // latency-oriented form (chain_core.cuh) whenever a warp's working set fits shared memory
+  static const bool no_lat = getenv("I2LQR_CHAIN_LAT") && atoi(getenv("I2LQR_CHAIN_LAT")) == 0;  // tuning switch
+  const size_t smem_lat = (size_t)kSolveThreads * chain_lane_elems(kp.N, rungs) * rsz;
+  if (!no_lat && smem_lat <= kSmemLimit) {
+    scratch = 0;
+    smem = smem_lat;
+    if (fp32)
+      kern = rungs == 4 ? pick_chain_lat<float, 4>(kp.has_qr) : (rungs == 2 ? pick_chain_lat<float, 2>(kp.has_qr) : pick_chain_lat<float, 1>(kp.has_qr));
+    else
+      kern = rungs == 4 ? pick_chain_lat<double, 4>(kp.has_qr) : (rungs == 2 ? pick_chain_lat<double, 2>(kp.has_qr) : pick_chain_lat<double, 1>(kp.has_qr));
+  }
   if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long long lanes = w.n_items * rungs;

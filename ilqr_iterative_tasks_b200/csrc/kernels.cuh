@@ -10,6 +10,7 @@
 
 #include <type_traits>
 
+#include "chain_core.cuh"
 #include "ilqr_core.cuh"
 
 namespace i2lqr {
@@ -346,11 +347,11 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
   static_assert(kScratch != 3, "the controller-step kernel keeps its scratch in memory");
   ScratchT s;
   s.bind(smem + threadIdx.x, reinterpret_cast<R*>(w.gscratch) + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
-  constexpr int kN = 0;
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int rung = lane % kRungs;
   const int gbase_lane = lane - rung;  // first lane of this chain's group
+  constexpr int kN = 0;
   const int N = p.N;
   const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kRungs;
   CandT<R> c = {};
@@ -457,6 +458,160 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
       ++rank;
       state = rank < cnt ? ST_INIT : ST_DONE;  // lambda is carried to the lap's next candidate
     }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    my_iters += __shfl_xor_sync(kFull, my_iters, o);
+    my_solves += __shfl_xor_sync(kFull, my_solves, o);
+  }
+  if (lane == 0 && w.stats != nullptr && my_solves) {
+    atomicAdd(w.stats + 0, my_iters);
+    atomicAdd(w.stats + 1, my_solves);
+  }
+}
+
+// Latency-oriented form of chain_kernel for horizons whose working set fits one warp's shared memory
+// (chain_core.cuh): the group of kRungs lanes shares one current trajectory (pointer switch instead of a copy on
+// accept) and the lambda-independent part of the backward pass (one task per stage, dealt to the group's lanes),
+// every rung then runs the Riccati recursion and the skewed forward pass with its own lambda.  Same arithmetic
+// and same accept order as chain_kernel.
+template <typename R, bool kQR, int kRungs>
+__global__ void __launch_bounds__(kSolveThreads, 1)
+chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
+  extern __shared__ double smem_raw[];
+  R* smem = reinterpret_cast<R*>(smem_raw);
+  constexpr int S = kSolveThreads;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int rung = lane % kRungs;
+  const int gbase_lane = lane - rung;
+  const int N = p.N;
+  ChainLane<R, S> v;
+  v.col = smem + lane;
+  v.grp = smem + gbase_lane;
+  v.N = N;
+  v.rungs = kRungs;
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kRungs;
+  CandT<R> c = {};
+  int state = ST_DONE;
+  int rank = 0, cnt = 0, ep = 0, lrel = 0, T = 0;
+  const double* lap = nullptr;
+  long long jsel = 0;
+  unsigned long long my_iters = 0, my_solves = 0;
+  int wb = 0;               // trial buffer this lane writes next
+  const R* cur = v.trial_of(0, 0);  // current trajectory of the group: some lane's trial buffer
+  bool dirty = true;        // the shared terms do not belong to `cur` yet
+  if (item < w.n_items) {
+    ep = (int)(item / w.set.L);
+    lrel = (int)(item % w.set.L);
+    cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
+    if (cnt > 0) {
+      const int count = w.set.lap_count[ep];
+      const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
+      const int slot = (min_iter + lrel) % w.set.L;
+      T = w.set.lap_len[(size_t)ep * w.set.L + slot];
+      lap = w.set.lap(ep, slot);
+      c.lamb = p.lamb0;  // utils/base.py:393
+      load_obstacle(p, c, w.ep_obs + ep);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c.x0[i] = R(w.x[(size_t)ep * 4 + i]);
+      sincos_fast(c.x0[3], &c.s0, &c.c0);
+      state = ST_INIT;
+    }
+  }
+  for (;;) {
+    if (__all_sync(kFull, state == ST_DONE)) break;
+    if (state == ST_INIT) {
+      jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c.xt[i] = R(lap[(size_t)i * w.set.Tcap + jsel]);
+      c.J = chain_init<kQR, S>(p, c, rung == 0 ? v.trial(0) : nullptr);
+      c.iters = 0;
+      cur = v.trial_of(0, 0);
+      wb = rung == 0 ? 1 : 0;
+      dirty = true;
+      state = ST_RUN;
+    }
+    __syncwarp();
+    const bool run = state == ST_RUN;
+    if (run && dirty) chain_terms<kQR, S>(p, c, v, cur, rung);
+    __syncwarp();
+    R Jn = R(0.0), Jt = R(0.0);
+    if (run) {
+      R lamb_r = c.lamb;
+      for (int r = 0; r < rung; ++r) lamb_r *= p.lamb_factor;  // the value r rejects lead to, same operations
+      chain_riccati<kQR, S>(p, v, lamb_r);
+      Jn = chain_forward<kQR, S>(p, c, cur, v.gains(), v.trial(wb), Jt);
+    }
+    __syncwarp();
+    const unsigned acc_all = __ballot_sync(kFull, run && Jn < c.J);
+    const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
+    // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
+    int winner = -1;
+    bool fin = false;
+    int consumed = 0;
+    R lamb = c.lamb;
+    if (run) {
+#pragma unroll
+      for (int r = 0; r < kRungs; ++r) {
+        if (winner >= 0 || fin) break;
+        if (c.iters + consumed >= p.max_iter) {
+          fin = true;
+          break;
+        }
+        ++consumed;
+        if ((acc >> r) & 1u) {
+          winner = r;
+          lamb /= p.lamb_factor;
+        } else {
+          lamb *= p.lamb_factor;
+          if (lamb > p.max_lamb) fin = true;
+        }
+      }
+    }
+    const int src = winner >= 0 ? gbase_lane + winner : lane;
+    const R Jn_w = __shfl_sync(kFull, Jn, src), Jt_w = __shfl_sync(kFull, Jt, src);
+    const int wb_w = __shfl_sync(kFull, wb, src);
+    if (run) {
+      dirty = winner >= 0;
+      if (winner >= 0) {
+        cur = v.trial_of(winner, wb_w);  // the winner's trial is the current trajectory from here on
+        if (rung == winner) wb ^= 1;
+        if (fabs((Jn_w - c.J) / c.J) < p.eps) fin = true;
+        c.J = kQR ? Jt_w : Jn_w;
+      }
+      c.lamb = lamb;
+      c.iters += consumed;
+      if (c.iters >= p.max_iter) fin = true;
+    }
+    if (run && fin) {
+      const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
+      const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
+      double* xv = w.cand_x + cslot * 4 * (N + 1);
+      double* uv = w.cand_u + cslot * 2 * N;
+      for (int k = rung; k < N; k += kRungs) {  // result in the reference's layout: xvar (4, N+1), uvar (2, N)
+        const R* s = cur + (size_t)(8 * k) * S;
+        uv[k] = (double)s[0];
+        uv[N + k] = (double)s[S];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i * (N + 1) + k + 1] = (double)s[(2 + i) * S];
+      }
+      if (rung == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i * (N + 1)] = (double)c.x0[i];
+        my_iters += (unsigned long long)c.iters;
+        my_solves += 1;
+        R xN[4];
+        const R* s = cur + (size_t)(8 * (N - 1)) * S;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xN[i] = s[(2 + i) * S];
+        w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
+        w.cand_lamb[tslot] = (double)c.lamb;
+        w.cand_iters[tslot] = c.iters;
+      }
+      ++rank;
+      state = rank < cnt ? ST_INIT : ST_DONE;  // lambda is carried to the lap's next candidate
+    }
+    __syncwarp();
   }
   for (int o = 16; o > 0; o >>= 1) {
     my_iters += __shfl_xor_sync(kFull, my_iters, o);

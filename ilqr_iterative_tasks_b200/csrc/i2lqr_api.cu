@@ -214,9 +214,14 @@ const void* pick_chain(bool has_qr, int scratch) {
   return scratch == 0 ? (const void*)chain_kernel<R, false, 0, kRungs> : (scratch == 1 ? (const void*)chain_kernel<R, false, 1, kRungs> : (const void*)chain_kernel<R, false, 2, kRungs>);
 }
 
-template <typename R, int kRungs>
+template <typename R, int kRungs, int kGroup>
 const void* pick_chain_lat(bool has_qr) {
-  return has_qr ? (const void*)chain_lat_kernel<R, true, kRungs> : (const void*)chain_lat_kernel<R, false, kRungs>;
+  return has_qr ? (const void*)chain_lat_kernel<R, true, kRungs, kGroup> : (const void*)chain_lat_kernel<R, false, kRungs, kGroup>;
+}
+template <typename R>
+const void* pick_chain_lat(bool has_qr, int rungs, int group) {
+  if (rungs == 4) return group == 32 ? pick_chain_lat<R, 4, 32>(has_qr) : (group == 8 ? pick_chain_lat<R, 4, 8>(has_qr) : pick_chain_lat<R, 4, 4>(has_qr));
+  return rungs == 2 ? pick_chain_lat<R, 2, 2>(has_qr) : pick_chain_lat<R, 1, 1>(has_qr);
 }
 
 int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
@@ -243,18 +248,23 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   size_t smem = scratch == 0 ? smem_full : (scratch == 2 ? smem_cur : 0);
   // latency-oriented form (chain_core.cuh) whenever a warp's working set fits shared memory
   static const bool no_lat = getenv("I2LQR_CHAIN_LAT") && atoi(getenv("I2LQR_CHAIN_LAT")) == 0;  // tuning switch
-  const size_t smem_lat = (size_t)kSolveThreads * chain_lane_elems(kp.N, rungs) * rsz;
+  // lanes per chain: as many as keep the launch within one warp per SM sub-partition (the rungs first, then
+  // extra lanes that only share the stage tasks)
+  int group = rungs;
+  if (rungs == 4) group = w.n_items <= slots ? 32 : (w.n_items * 8 <= slots * 32 ? 8 : 4);
+  static const int force_group = getenv("I2LQR_GROUP") ? atoi(getenv("I2LQR_GROUP")) : 0;  // tuning switch
+  if (rungs == 4 && (force_group == 4 || force_group == 8 || force_group == 32)) group = force_group;
+  const size_t smem_lat = (size_t)kSolveThreads * chain_lane_elems(kp.N, group) * rsz;
+  int lanes_per_chain = rungs;
   if (!no_lat && smem_lat <= kSmemLimit) {
     scratch = 0;
     smem = smem_lat;
-    if (fp32)
-      kern = rungs == 4 ? pick_chain_lat<float, 4>(kp.has_qr) : (rungs == 2 ? pick_chain_lat<float, 2>(kp.has_qr) : pick_chain_lat<float, 1>(kp.has_qr));
-    else
-      kern = rungs == 4 ? pick_chain_lat<double, 4>(kp.has_qr) : (rungs == 2 ? pick_chain_lat<double, 2>(kp.has_qr) : pick_chain_lat<double, 1>(kp.has_qr));
+    lanes_per_chain = group;
+    kern = fp32 ? pick_chain_lat<float>(kp.has_qr, rungs, group) : pick_chain_lat<double>(kp.has_qr, rungs, group);
   }
   if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const long long lanes = w.n_items * rungs;
+  const long long lanes = w.n_items * lanes_per_chain;
   const long long grid = std::max<long long>(1, (lanes + kSolveThreads - 1) / kSolveThreads);
   if (scratch != 0) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
@@ -266,7 +276,7 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   w.counter = nullptr;
   w.stats = h->ctl.p;
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
-  if (debug) fprintf(stderr, "[i2lqr] chain launch: rungs %d scratch %d grid %lld smem %zu chains %lld\n", rungs, scratch, grid, smem, w.n_items);
+  if (debug) fprintf(stderr, "[i2lqr] chain launch: rungs %d lanes/chain %d scratch %d grid %lld smem %zu chains %lld\n", rungs, lanes_per_chain, scratch, grid, smem, w.n_items);
   const KParamsT<float> kpf = fp32 ? to_float(kp) : KParamsT<float>{};
   void* args[2] = {fp32 ? (void*)&kpf : (void*)&kp, (void*)&w};
   CU(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kSolveThreads), args, smem, st));

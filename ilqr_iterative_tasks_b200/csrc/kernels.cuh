@@ -473,8 +473,11 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
 // (chain_core.cuh): the group of kRungs lanes shares one current trajectory (pointer switch instead of a copy on
 // accept) and the lambda-independent part of the backward pass (one task per stage, dealt to the group's lanes),
 // every rung then runs the Riccati recursion and the skewed forward pass with its own lambda.  Same arithmetic
-// and same accept order as chain_kernel.
-template <typename R, bool kQR, int kRungs>
+// and same accept order as chain_kernel.  A chain owns kGroup >= kRungs adjacent lanes: the first kRungs are the
+// rungs, all kGroup share the stage tasks.  With few chains (one controller, config 2) kGroup = 32 gives every
+// chain a warp, hence an SM sub-partition, of its own and one task per lane; with many chains (batched
+// episodes) kGroup shrinks so that the chains still fit one warp per sub-partition.
+template <typename R, bool kQR, int kRungs, int kGroup>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
   extern __shared__ double smem_raw[];
@@ -482,15 +485,16 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
   constexpr int S = kSolveThreads;
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int rung = lane % kRungs;
+  const int rung = lane % kGroup;  // position in the group; a rung when < kRungs
+  const bool is_rung = rung < kRungs;
   const int gbase_lane = lane - rung;
   const int N = p.N;
   ChainLane<R, S> v;
   v.col = smem + lane;
   v.grp = smem + gbase_lane;
   v.N = N;
-  v.rungs = kRungs;
-  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kRungs;
+  v.rungs = kGroup;
+  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
   CandT<R> c = {};
   int state = ST_DONE;
   int rank = 0, cnt = 0, ep = 0, lrel = 0, T = 0;
@@ -536,14 +540,14 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
     if (run && dirty) chain_terms<kQR, S>(p, c, v, cur, rung);
     __syncwarp();
     R Jn = R(0.0), Jt = R(0.0);
-    if (run) {
+    if (run && is_rung) {
       R lamb_r = c.lamb;
       for (int r = 0; r < rung; ++r) lamb_r *= p.lamb_factor;  // the value r rejects lead to, same operations
       chain_riccati<kQR, S>(p, v, lamb_r);
       Jn = chain_forward<kQR, S>(p, c, cur, v.gains(), v.trial(wb), Jt);
     }
     __syncwarp();
-    const unsigned acc_all = __ballot_sync(kFull, run && Jn < c.J);
+    const unsigned acc_all = __ballot_sync(kFull, run && is_rung && Jn < c.J);
     const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
     // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
     int winner = -1;
@@ -588,7 +592,7 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
       const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
       double* xv = w.cand_x + cslot * 4 * (N + 1);
       double* uv = w.cand_u + cslot * 2 * N;
-      for (int k = rung; k < N; k += kRungs) {  // result in the reference's layout: xvar (4, N+1), uvar (2, N)
+      for (int k = rung; k < N; k += kGroup) {  // result in the reference's layout: xvar (4, N+1), uvar (2, N)
         const R* s = cur + (size_t)(8 * k) * S;
         uv[k] = (double)s[0];
         uv[N + k] = (double)s[S];

@@ -213,20 +213,24 @@ __device__ __forceinline__ void chain_terms(const KParamsT<R>& p, const CandT<R>
   for (int k0 = rung; k0 < n_tasks; k0 += 2 * v.rungs) {
     const int k1 = k0 + v.rungs;
     const bool two = k1 < n_tasks;
-    TaskIn<R> a, b;
+    TaskIn<R> a;
     chain_task_load<S>(p, c, cur, k0, a);
-    chain_task_load<S>(p, c, cur, two ? k1 : k0, b);
-    R oa[kTermWidth], ob[kTermWidth];
-    chain_task_eval<kQR>(p, c, a, oa);
-    chain_task_eval<kQR>(p, c, b, ob);
-    R* da = v.terms_w(k0);
-#pragma unroll
-    for (int i = 0; i < kTermWidth - 1; ++i) da[i * S] = oa[i];
-    if (two) {
+    R oa[kTermWidth];
+    if (two) {  // two tasks side by side
+      TaskIn<R> b;
+      chain_task_load<S>(p, c, cur, k1, b);
+      R ob[kTermWidth];
+      chain_task_eval<kQR>(p, c, a, oa);
+      chain_task_eval<kQR>(p, c, b, ob);
       R* db = v.terms_w(k1);
 #pragma unroll
       for (int i = 0; i < kTermWidth - 1; ++i) db[i * S] = ob[i];
+    } else {
+      chain_task_eval<kQR>(p, c, a, oa);
     }
+    R* da = v.terms_w(k0);
+#pragma unroll
+    for (int i = 0; i < kTermWidth - 1; ++i) da[i * S] = oa[i];
   }
 }
 
@@ -328,11 +332,13 @@ __device__ __forceinline__ void chain_riccati(const KParamsT<R>& p, const ChainL
       i11 = aq * r;
       if (!(a * d - b * b >= R(0.0) && a + d >= R(0.0))) quu_inverse(a, b, d, lamb, i00, i01, i11);
     }
-    const R k0 = -fma(i01, Qu1, i00 * Qu0), k1 = -fma(i11, Qu1, i01 * Qu0);
-    const R K00 = -fma(i01, H0, i00 * G0), K01 = -fma(i01, H1, i00 * G1);
-    const R K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
-    const R K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
-    const R K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
+    // The gains are kept with the opposite sign (kp = -k, Kp = -K: no negation instructions); the value-function
+    // update below is invariant under that sign flip and the forward pass subtracts -- bit-identical results.
+    const R k0 = fma(i01, Qu1, i00 * Qu0), k1 = fma(i11, Qu1, i01 * Qu0);
+    const R K00 = fma(i01, H0, i00 * G0), K01 = fma(i01, H1, i00 * G1);
+    const R K02 = fma(i01, X12, i00 * X02), K03 = fma(i01, X13, i00 * X03);
+    const R K10 = fma(i11, H0, i01 * G0), K11 = fma(i11, H1, i01 * G1);
+    const R K12 = fma(i11, X12, i01 * X02), K13 = fma(i11, X13, i01 * X03);
     {
       R* g = gains + (size_t)(10 * k) * S;
       g[0] = k0;
@@ -403,8 +409,9 @@ __device__ __forceinline__ R chain_forward(const KParamsT<R>& p, const CandT<R>&
     R sn, cs;
     sincos_inline(x[3], &sn, &cs);
     const R d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
-    R ua = (uo[0] + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
-    R ud = (uo[1] + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
+    // u + k + K (x - xo) with the sign-flipped gains of chain_riccati
+    R ua = (uo[0] - g[0]) - fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
+    R ud = (uo[1] - g[1]) - fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
     ua = clipd(ua, -p.a_max, p.a_max);
     ud = clipd(ud, -p.d_lim, p.d_lim);
     if (kQR) {

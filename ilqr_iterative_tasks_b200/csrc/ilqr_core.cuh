@@ -473,11 +473,14 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
     // ---- regularised inverse and gains: iterative_ilqr.py:118-126
     R i00, i01, i11;
     quu_inverse(Quu00, (Quu01 + Quu10) / R(2.0), Quu11, c.lamb, i00, i01, i11);
-    const R k0 = -fma(i01, Qu1, i00 * Qu0), k1 = -fma(i11, Qu1, i01 * Qu0);
-    const R K00 = -fma(i01, H0, i00 * G0), K01 = -fma(i01, H1, i00 * G1);
-    const R K02 = -fma(i01, X12, i00 * X02), K03 = -fma(i01, X13, i00 * X03);
-    const R K10 = -fma(i11, H0, i01 * G0), K11 = -fma(i11, H1, i01 * G1);
-    const R K12 = -fma(i11, X12, i01 * X02), K13 = -fma(i11, X13, i01 * X03);
+    // The gains are kept with the opposite sign (k0 = -k[0], K00 = -K[0][0], ...): ten negation instructions per
+    // stage less; the value-function update below is invariant under the flip and the forward pass subtracts,
+    // so every result is bit-identical to the reference's sign convention.
+    const R k0 = fma(i01, Qu1, i00 * Qu0), k1 = fma(i11, Qu1, i01 * Qu0);
+    const R K00 = fma(i01, H0, i00 * G0), K01 = fma(i01, H1, i00 * G1);
+    const R K02 = fma(i01, X12, i00 * X02), K03 = fma(i01, X13, i00 * X03);
+    const R K10 = fma(i11, H0, i01 * G0), K11 = fma(i11, H1, i01 * G1);
+    const R K12 = fma(i11, X12, i01 * X02), K13 = fma(i11, X13, i01 * X03);
     {
       const R gv[10] = {k0, k1, K00, K01, K02, K03, K10, K11, K12, K13};
       s.stg10(k, gv);
@@ -530,8 +533,9 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
     }
     const R uo0 = s.ldc(I2_CUR(k) + 0), uo1 = s.ldc(I2_CUR(k) + 1);
     const R d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
-    R ua = (uo0 + g[0]) + fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
-    R ud = (uo1 + g[1]) + fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
+    // u + k + K (x - xo) with the sign-flipped gains of backward_pass
+    R ua = (uo0 - g[0]) - fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
+    R ud = (uo1 - g[1]) - fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
     ua = clipd(ua, -p.a_max, p.a_max);
     ud = clipd(ud, -p.d_lim, p.d_lim);
     if (kQR) {

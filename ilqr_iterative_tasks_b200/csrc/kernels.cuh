@@ -314,7 +314,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     my_iters += __shfl_xor_sync(0xffffffffu, my_iters, o);
     my_solves += __shfl_xor_sync(0xffffffffu, my_solves, o);
   }
-  if (lane == 0 && w.stats != nullptr && my_solves) {
+  if (lane == 0 && w.stats != nullptr && (my_solves | my_iters)) {
     atomicAdd(w.stats + 0, my_iters);
     atomicAdd(w.stats + 1, my_solves);
   }
@@ -463,7 +463,7 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     my_iters += __shfl_xor_sync(kFull, my_iters, o);
     my_solves += __shfl_xor_sync(kFull, my_solves, o);
   }
-  if (lane == 0 && w.stats != nullptr && my_solves) {
+  if (lane == 0 && w.stats != nullptr && (my_solves | my_iters)) {
     atomicAdd(w.stats + 0, my_iters);
     atomicAdd(w.stats + 1, my_solves);
   }
@@ -621,7 +621,7 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
     my_iters += __shfl_xor_sync(kFull, my_iters, o);
     my_solves += __shfl_xor_sync(kFull, my_solves, o);
   }
-  if (lane == 0 && w.stats != nullptr && my_solves) {
+  if (lane == 0 && w.stats != nullptr && (my_solves | my_iters)) {
     atomicAdd(w.stats + 0, my_iters);
     atomicAdd(w.stats + 1, my_solves);
   }

@@ -520,7 +520,7 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
   s.ldg10(0, g);
 #pragma unroll
   for (int i = 0; i < 10; ++i) gn[i] = g[i];
-#pragma unroll(kN > 0 ? kN : 1)
+#pragma unroll(kN > 0 ? kN : 2)  // two stages per trip: the one-stage-ahead operand registers need no rotation moves
   for (int k = 0; k < N; ++k) {
     s.ldg10(k + 1 < N ? k + 1 : k, gn);  // clamped, not conditional: the prefetch must never leave the lane's strip
     R xo[4];
@@ -580,6 +580,7 @@ __device__ __forceinline__ bool ilqr_iteration(const KParamsT<R>& p, CandT<R>& c
     s.ldg8(0, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) tn[i] = t[i];
+#pragma unroll 2
     for (int k = 0; k < N; ++k) {
       s.ldg8(k + 1 < N ? k + 1 : k, tn);  // clamped prefetch (see forward_pass)
       if (accept) {

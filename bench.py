@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram bytes of the dominant launch (pass 0 over 2^20 candidates) from profiles/r01_solve_kernel_v6_summary.txt
+NCU_TRAFFIC_BYTES = 129622528 + 300095232
 METRIC = "candidate iLQR solves/sec"
 UNIT = "solves/s"
 
@@ -62,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )  # fmt: skip
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -384,7 +386,10 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "kernel": "solve_kernel<false,true,0>", "kernel_ms": avg_ms,
+                "traffic": NCU_TRAFFIC_BYTES if (B == 1 << 20 and N == 6) else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the pass-0 launch (2^20 candidates), one ncu --set full "
+                                "capture: profiles/r01_solve_kernel_v6_summary.txt; algorithmic bytes per launch = %d" % (B * bytes_per_solve(N)),
+                "kernel": "solve_kernel<double, kQR=false, kScratch=3 (tensor-memory gains), kMode=0, 128 threads>", "kernel_ms": avg_ms,
                 "isolated": {"launch_ms": kernel_ms, "achieved": flops / (kernel_ms * 1e-3) / 1e12,
                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
                              "note": "one launch at a time on one stream (what ncu sees); the timed region pipelines "

@@ -372,7 +372,7 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
     V01 += h01;
     V11 += h11;
   }
-#pragma unroll(kN > 0 ? kN : 1)
+#pragma unroll(kN > 0 ? kN : 1)  // (two stages per trip measured 11 % slower here: 720-instruction body)
   for (int k = N - 1; k >= 0; --k) {
     // ---- trajectory at stage k
     const R ua = s.ldc(I2_CUR(k) + 0), ud = s.ldc(I2_CUR(k) + 1);

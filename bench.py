@@ -332,11 +332,12 @@ def run_ours(args):
     import threading
 
     x0_np, xt_np, lamb_np = h_x0.numpy(), h_xt.numpy(), h_lamb.numpy()
+    obs_np = h_obs.numpy().view(_abi.OBSTACLE_DTYPE).reshape(B)  # the pinned copy: a pageable upload would serialise the pipeline
     outs_np = [{k: v.numpy() for k, v in ho.items()} for ho in h_outs]
 
     def host_steps(i, n):
         for _ in range(n):
-            engs[i].solve_batch(x0_np, xt_np, lamb_np, obs, out=outs_np[i])
+            engs[i].solve_batch(x0_np, xt_np, lamb_np, obs_np, out=outs_np[i])
 
     for i in range(n_pipe):
         host_steps(i, 1)

@@ -40,6 +40,22 @@ int fail(const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// Zeroing a few control words goes through a one-warp kernel, not cudaMemsetAsync: a memset may be queued on a
+// copy engine and then waits behind another handle's bulk download, which stalls the solve launch behind it.
+__global__ void zero_words_kernel(unsigned long long* p, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0ull;
+}
+// Same reason for the statistics readback: a 16-byte cudaMemcpy would queue behind another handle's bulk download,
+// so a one-thread kernel writes the two counters straight into mapped pinned host memory.
+__global__ void publish_words_kernel(const unsigned long long* src, volatile unsigned long long* dst_host, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst_host[i] = src[i];
+  __threadfence_system();
+}
+inline cudaError_t zero_words(unsigned long long* p, int n, cudaStream_t st) {
+  zero_words_kernel<<<1, 32, 0, st>>>(p, n);
+  return cudaGetLastError();
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -76,13 +92,22 @@ struct i2lqr_handle {
   // statistics words + work-fetch counters
   DevBuf<unsigned long long> ctl;
   int ctl_next = 0;
-  cudaStream_t aux[2] = {nullptr, nullptr};  // extra streams of the chunked host pipeline
-  cudaEvent_t aux_done[2] = {nullptr, nullptr};
-  DevBuf<double> gscratch[3];
+  static constexpr int kPipes = 8;      // streams of the chunked host pipeline (the handle's own + 7)
+  cudaStream_t aux[kPipes - 1] = {};
+  cudaEvent_t aux_done[kPipes - 1] = {};
+  cudaEvent_t d2h_done = nullptr;        // all downloads of the last host-pointer batch have landed
+  unsigned long long* h_stats = nullptr;  // mapped pinned host memory: statistics published by a kernel
+  // uploads and downloads each get a stream of their own that never carries the other direction: the driver
+  // binds a stream's copies to one copy engine, so a stream that uploads AND downloads queues both directions
+  // on the same engine and the link never runs full duplex (measured: profiles/r01_host_pipeline_timeline.txt)
+  cudaStream_t up = nullptr, down = nullptr;
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t ev_up[kMaxChunks] = {}, ev_solved[kMaxChunks] = {};
+  DevBuf<double> gscratch[kPipes];
   // iteration-sliced passes: parked candidates (ping-pong), per pipeline stream
-  DevBuf<double> park_state[3][2];
-  DevBuf<int> park_list[3][2];
-  DevBuf<unsigned long long> park_count[3];  // one slab per pipeline stream (launches on different streams overlap)
+  DevBuf<double> park_state[kPipes][2];
+  DevBuf<int> park_list[kPipes][2];
+  DevBuf<unsigned long long> park_count[kPipes];  // one slab per pipeline stream (launches on different streams overlap)
   // flat batch staging
   DevBuf<double> b_x0, b_xt, b_lamb, b_uvar, b_xvar, b_lamb_out, b_uinit;
   DevBuf<DevObstacle> b_obs;
@@ -116,9 +141,10 @@ int make_kparams(const i2lqr_params& p, KParams* k) {
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
+
 constexpr int kCtlSlots = 16;   // fetch counters: one per launch that may be in flight concurrently
 constexpr int kCtlWords = 2 + kCtlSlots;  // ctl[0] executed iterations, ctl[1] finished solves, then the counters
-constexpr int kAuxStreams = 2;
+constexpr int kAuxStreams = i2lqr_handle::kPipes - 1;
 constexpr long long kSliceMinBatch = 131072;  // smaller flat batches run as a single pass
 
 // Launches the persistent solve kernel for `w` (counter / stats pointers are filled in here).
@@ -141,7 +167,7 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   CU(h->ctl.ensure(kCtlWords));
   const int slot = h->ctl_next;
   h->ctl_next = (slot + 1) % kCtlSlots;
-  CU(cudaMemsetAsync(h->ctl.p + 2 + slot, 0, sizeof(unsigned long long), st));
+  CU(zero_words(h->ctl.p + 2 + slot, 1, st));
   w.counter = h->ctl.p + 2 + slot;
   w.stats = h->ctl.p;
   long long blocks_needed = (w.n_items + threads - 1) / threads;
@@ -287,16 +313,18 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
 int begin_stats(i2lqr_handle* h, cudaStream_t st) {
   h->last_launches = 0;
   CU(h->ctl.ensure(kCtlWords));
-  CU(cudaMemsetAsync(h->ctl.p, 0, 2 * sizeof(unsigned long long), st));
+  CU(zero_words(h->ctl.p, 2, st));
   CU(cudaEventRecord(h->ev0, st));
   return 0;
 }
 
 // Waits for `st` and reads back the device-side counters and the ev0..ev1 kernel time.
 int finish_stats(i2lqr_handle* h, cudaStream_t st) {
-  unsigned long long s[2];
-  CU(cudaMemcpyAsync(s, h->ctl.p, sizeof s, cudaMemcpyDeviceToHost, st));
+  if (!h->h_stats) CU(cudaHostAlloc((void**)&h->h_stats, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+  publish_words_kernel<<<1, 32, 0, st>>>(h->ctl.p, h->h_stats, 2);
+  CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));
+  const unsigned long long s[2] = {h->h_stats[0], h->h_stats[1]};
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;
@@ -402,11 +430,24 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
   h->K = p->num_ss_points;
   h->Tcap = lap_capacity;
   CU(cudaSetDevice(device));
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  // pipeline stream i carries chunk i of a host-pointer batch: earlier chunks get the higher priority so that their
+  // last passes are scheduled ahead of later chunks' first passes and their download starts early
+  int prio_least = 0, prio_greatest = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  static const bool no_prio = getenv("I2LQR_NO_PRIO") != nullptr;  // tuning switch
+  auto pipe_priority = [&](int i) { return no_prio ? prio_least : std::min(prio_least, prio_greatest + i); };
+  CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, pipe_priority(0)));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreateWithFlags(&h->d2h_done, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking));
+  for (int i = 0; i < i2lqr_handle::kMaxChunks; ++i) {
+    CU(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_solved[i], cudaEventDisableTiming));
+  }
   for (int i = 0; i < kAuxStreams; ++i) {
-    CU(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&h->aux[i], cudaStreamNonBlocking, pipe_priority(1 + i)));
     CU(cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming));
   }
   CU(h->ctl.ensure(kCtlWords));
@@ -438,7 +479,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->gscratch[0], &h->gscratch[1], &h->gscratch[2], &h->s_x, &h->s_u,
+  for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->s_x, &h->s_u,
                   &h->s_xpred, &h->s_upred, &h->s_cand_x, &h->s_cand_u, &h->s_cand_cost, &h->s_cand_lamb, &h->s_wcost,
                   &h->q_x0})
     b->release();
@@ -448,6 +489,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen}) b->release();
   h->d_obs0.release();
   if (h->h_nrun) cudaFreeHost(h->h_nrun);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
   h->ctl.release();
   h->b_obs.release();
   h->d_obs.release();
@@ -456,7 +498,15 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (h->set.lap_count) cudaFree(h->set.lap_count);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
-  for (int i = 0; i < 3; ++i) {
+  if (h->d2h_done) cudaEventDestroy(h->d2h_done);
+  for (int i = 0; i < i2lqr_handle::kMaxChunks; ++i) {
+    if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
+    if (h->ev_solved[i]) cudaEventDestroy(h->ev_solved[i]);
+  }
+  if (h->up) cudaStreamDestroy(h->up);
+  if (h->down) cudaStreamDestroy(h->down);
+  for (int i = 0; i < i2lqr_handle::kPipes; ++i) {
+    h->gscratch[i].release();
     h->park_count[i].release();
     for (int b = 0; b < 2; ++b) {
       h->park_state[i][b].release();
@@ -513,7 +563,7 @@ int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const 
     CU(h->park_list[pipe][b].ensure((size_t)capacity));
   }
   CU(h->park_count[pipe].ensure(4));
-  CU(cudaMemsetAsync(h->park_count[pipe].p, 0, 4 * sizeof(unsigned long long), st));
+  CU(zero_words(h->park_count[pipe].p, 4, st));
   const int n_pass = 4;
   for (int ps = 0; ps < n_pass; ++ps) {
     Work wp = w;
@@ -546,9 +596,13 @@ int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const
   return end_stats(h, st, false);
 }
 
-// Host-pointer form.  Big batches are cut into up to 8 chunks that flow through three streams -- H2D of chunk i+1, the
-// solve of chunk i and D2H of chunk i-1 overlap (full-duplex PCIe when the caller's buffers are pinned;
-// pageable buffers still work, the copies then serialise).
+// Host-pointer form.  Uploads (one stream that only ever uploads), solves (a stream per chunk) and downloads (one
+// stream that only ever downloads) of up to four chunks overlap; with two or more caller threads, each on its
+// own handle, one caller's upload + solve runs under the other's download and the call rate is bound by the
+// D2H direction of PCIe (measured 51 GB/s of 57).  Nothing on this path uses a pageable copy: even the 16-byte
+// statistics readback goes through mapped memory, because a pageable copy queues behind whatever bulk transfer
+// another handle has in flight (that alone cost 30 % of the end-to-end rate, profiles/r01_host_pipeline.txt).
+// The caller's buffers should be pinned; pageable buffers still work, the copies then serialise.
 int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term, const double* lamb_in,
                       const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
                       double* lamb_out, int32_t* iters) {
@@ -568,45 +622,100 @@ int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double
     if (iters) CU(h->b_iters.ensure(nb));
   }
   cudaStream_t main = h->stream;
+  static const bool tl = getenv("I2LQR_TIMELINE") != nullptr;  // developer switch: per-chunk event timeline on stderr
+  static cudaEvent_t tl_base = nullptr;
+  std::vector<cudaEvent_t> tev;
+  auto mark = [&](cudaStream_t st) { if (tl) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+  std::vector<int64_t> sizes;      // chunk sizes
+  {
+  if (tl && !tl_base) {
+    cudaEventCreate(&tl_base);
+    cudaEventRecord(tl_base, main);
+  }
   if (begin_stats(h, main)) return 1;
   if (B > 0) {
     if (n_obs == 1) CU(cudaMemcpyAsync(h->b_obs.p, obs, sizeof(DevObstacle), cudaMemcpyHostToDevice, main));
     CU(cudaEventRecord(h->ev0, main));  // aux streams start after the statistics reset (and the shared obstacle)
-    cudaStream_t streams[1 + kAuxStreams] = {main, h->aux[0], h->aux[1]};
+    cudaStream_t streams[1 + kAuxStreams];
+    streams[0] = main;
+    for (int i = 0; i < kAuxStreams; ++i) streams[1 + i] = h->aux[i];
     for (int i = 0; i < kAuxStreams; ++i) CU(cudaStreamWaitEvent(h->aux[i], h->ev0, 0));
-    // chunks stay large enough for iteration slicing: a small launch is dominated by its longest candidate
-    // (150 iterations ~ 2-3 ms), so cutting finer only serialises straggler tails
-    const int64_t min_chunk = kSliceMinBatch;
-    int64_t n_chunks = std::min<int64_t>(8, std::max<int64_t>(1, B / min_chunk));
+    // Few, large chunks: a launch needs several candidates per lane to average out the 1..150 iterations a candidate
+    // takes (2^17 candidates per launch run at 0.43 of the 2^20 rate), and iteration slicing needs >= 2^17.  Four
+    // chunks let the first download start a quarter of the way in; finer cuts only cost GPU time.
+    static const int max_chunks = getenv("I2LQR_CHUNKS") ? atoi(getenv("I2LQR_CHUNKS")) : 4;  // tuning switch
+    const int64_t n_chunks = std::min<int64_t>(std::min(max_chunks, i2lqr_handle::kMaxChunks), std::max<int64_t>(1, B / (2 * kSliceMinBatch)));
     const int64_t chunk = (B + n_chunks - 1) / n_chunks;
+    for (int64_t left = B; left > 0; left -= std::min(chunk, left)) sizes.push_back(std::min(chunk, left));
     const auto* d_obs = reinterpret_cast<const i2lqr_obstacle*>(h->b_obs.p);
-    for (int64_t c = 0, lo = 0; lo < B; ++c, lo += chunk) {
-      const int64_t n = std::min<int64_t>(chunk, B - lo);
-      const size_t un = (size_t)n, ulo = (size_t)lo;
-      cudaStream_t st = streams[c % (1 + kAuxStreams)];
+    if ((int64_t)sizes.size() > i2lqr_handle::kMaxChunks) return fail("internal: too many chunks");
+    CU(cudaStreamWaitEvent(h->up, h->ev0, 0));
+    CU(cudaStreamWaitEvent(h->down, h->ev0, 0));
+    // uploads of all chunks, in order, on the upload stream
+    for (int64_t c = 0, lo = 0; c < (int64_t)sizes.size(); lo += sizes[c], ++c) {
+      const size_t un = (size_t)sizes[c], ulo = (size_t)lo;
+      cudaStream_t st = h->up;
       CU(cudaMemcpyAsync(h->b_x0.p + ulo * 4, x0 + ulo * 4, un * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
       CU(cudaMemcpyAsync(h->b_xt.p + ulo * 4, x_term + ulo * 4, un * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
       if (lamb_in) CU(cudaMemcpyAsync(h->b_lamb.p + ulo, lamb_in + ulo, un * sizeof(double), cudaMemcpyHostToDevice, st));
       if (n_obs > 1) CU(cudaMemcpyAsync(h->b_obs.p + ulo, obs + ulo, un * sizeof(DevObstacle), cudaMemcpyHostToDevice, st));
       if (uvar_init)
         CU(cudaMemcpyAsync(h->b_uinit.p + ulo * 2 * N, uvar_init + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyHostToDevice, st));
-      if (launch_flat(h, lo, n, h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr, d_obs, n_obs,
+      CU(cudaEventRecord(h->ev_up[c], st));
+      mark(st);
+    }
+    // every chunk's solve on a compute stream of its own
+    for (int64_t c = 0, lo = 0; c < (int64_t)sizes.size(); lo += sizes[c], ++c) {
+      cudaStream_t st = streams[c % (1 + kAuxStreams)];
+      CU(cudaStreamWaitEvent(st, h->ev_up[c], 0));
+      if (launch_flat(h, lo, sizes[c], h->b_x0.p, h->b_xt.p, lamb_in ? h->b_lamb.p : nullptr, d_obs, n_obs,
                       uvar_init ? h->b_uinit.p : nullptr, uvar ? h->b_uvar.p : nullptr, xvar ? h->b_xvar.p : nullptr,
                       lamb_out ? h->b_lamb_out.p : nullptr, iters ? h->b_iters.p : nullptr, st, (int)(c % (1 + kAuxStreams))))
         return 1;
+      CU(cudaEventRecord(h->ev_solved[c], st));
+      mark(st);
+    }
+  }
+  }
+  if (B > 0) {
+    // Downloads are only handed to the driver once they can run: a copy that still waits for its solve would sit
+    // at the head of the copy engine's hardware queue and hold up every transfer queued behind it, including
+    // other handles' (other caller threads') transfers.
+    int64_t lo = 0;
+    for (int64_t c = 0; c < (int64_t)sizes.size(); lo += sizes[c], ++c) {
+      const size_t un = (size_t)sizes[c], ulo = (size_t)lo;
+      cudaStream_t st = h->down;
+      CU(cudaEventSynchronize(h->ev_solved[c]));
       if (uvar) CU(cudaMemcpyAsync(uvar + ulo * 2 * N, h->b_uvar.p + ulo * 2 * N, un * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (xvar)
         CU(cudaMemcpyAsync(xvar + ulo * 4 * (N + 1), h->b_xvar.p + ulo * 4 * (N + 1), un * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (lamb_out) CU(cudaMemcpyAsync(lamb_out + ulo, h->b_lamb_out.p + ulo, un * sizeof(double), cudaMemcpyDeviceToHost, st));
       if (iters) CU(cudaMemcpyAsync(iters + ulo, h->b_iters.p + ulo, un * sizeof(int), cudaMemcpyDeviceToHost, st));
+      mark(st);
     }
+    CU(cudaEventRecord(h->d2h_done, h->down));
     for (int i = 0; i < kAuxStreams; ++i) {
       CU(cudaEventRecord(h->aux_done[i], h->aux[i]));
       CU(cudaStreamWaitEvent(main, h->aux_done[i], 0));
     }
+    CU(cudaStreamWaitEvent(main, h->d2h_done, 0));
   }
   CU(cudaEventRecord(h->ev1, main));  // here: whole pipeline (copies included), see i2lqr_last_stats
-  return finish_stats(h, main);
+  const int rc = finish_stats(h, main);
+  if (tl && rc == 0) {
+    float t0 = 0;
+    cudaEventElapsedTime(&t0, tl_base, h->ev0);
+    const size_t nc = tev.size() / 3;
+    for (size_t i = 0; i < nc; ++i) {
+      float a, b, c2;
+      cudaEventElapsedTime(&a, tl_base, tev[i]);
+      cudaEventElapsedTime(&b, tl_base, tev[nc + i]);
+      cudaEventElapsedTime(&c2, tl_base, tev[2 * nc + i]);
+      fprintf(stderr, "[timeline %p] call@%.2f chunk %zu: uploaded %.2f  solved %.2f  downloaded %.2f ms\n", (void*)h, t0, i, a, b, c2);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+  }
+  return rc;
 }
 
 // -------------------------------------------------------------------------------------------- safe set

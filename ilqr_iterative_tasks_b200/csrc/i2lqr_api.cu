@@ -97,6 +97,8 @@ struct i2lqr_handle {
   cudaEvent_t aux_done[kPipes - 1] = {};
   cudaEvent_t d2h_done = nullptr;        // all downloads of the last host-pointer batch have landed
   unsigned long long* h_stats = nullptr;  // mapped pinned host memory: statistics published by a kernel
+  unsigned char* stage = nullptr;         // pinned staging block of the controller-step call
+  size_t stage_bytes = 0;
   // uploads and downloads each get a stream of their own that never carries the other direction: the driver
   // binds a stream's copies to one copy engine, so a stream that uploads AND downloads queues both directions
   // on the same engine and the link never runs full duplex (measured: profiles/r01_host_pipeline_timeline.txt)
@@ -490,6 +492,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   h->d_obs0.release();
   if (h->h_nrun) cudaFreeHost(h->h_nrun);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->stage) cudaFreeHost(h->stage);
   h->ctl.release();
   h->b_obs.release();
   h->d_obs.release();
@@ -911,19 +914,36 @@ int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u
   cudaStream_t st = h->stream;
   if (ensure_step_workspace(h)) return 1;
   const size_t E = n_episodes, N = h->kp.N;
-  CU(cudaMemcpyAsync(h->s_x.p, x, E * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  // The caller's arrays are ordinary (pageable) memory: the state goes up and the results come down through one
+  // pinned staging block, so the call issues asynchronous copies only and blocks once.
+  const size_t n_in = E * 4 * sizeof(double);
+  const size_t sz[8] = {E * 2 * sizeof(double), E * 4 * (N + 1) * sizeof(double), E * 2 * N * sizeof(double), E * sizeof(int),
+                        E * sizeof(int),        E * sizeof(long long),            E * sizeof(double),         E * sizeof(int)};
+  const void* src[8] = {h->s_u.p, h->s_xpred.p, h->s_upred.p, h->s_wlap.p, h->s_wrank.p, h->s_widx.p, h->s_wcost.p, h->s_shrink.p};
+  void* dst[8] = {u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink};
+  size_t off[8], total = (n_in + 15) / 16 * 16;
+  for (int i = 0; i < 8; ++i) {
+    off[i] = total;
+    total += (sz[i] + 15) / 16 * 16;
+  }
+  if (total > h->stage_bytes) {
+    if (h->stage) cudaFreeHost(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    CU(cudaMallocHost((void**)&h->stage, total));
+    h->stage_bytes = total;
+  }
+  memcpy(h->stage, x, n_in);
+  CU(cudaMemcpyAsync(h->s_x.p, h->stage, n_in, cudaMemcpyHostToDevice, st));
   if (begin_stats(h, st)) return 1;
   if (run_step(h, n_episodes, nullptr, st)) return 1;
   CU(cudaEventRecord(h->ev1, st));
-  if (u) CU(cudaMemcpyAsync(u, h->s_u.p, E * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (x_pred) CU(cudaMemcpyAsync(x_pred, h->s_xpred.p, E * 4 * (N + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (u_pred) CU(cudaMemcpyAsync(u_pred, h->s_upred.p, E * 2 * N * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (winner_lap) CU(cudaMemcpyAsync(winner_lap, h->s_wlap.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (winner_rank) CU(cudaMemcpyAsync(winner_rank, h->s_wrank.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (winner_idx) CU(cudaMemcpyAsync(winner_idx, h->s_widx.p, E * sizeof(long long), cudaMemcpyDeviceToHost, st));
-  if (winner_cost) CU(cudaMemcpyAsync(winner_cost, h->s_wcost.p, E * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (shrink) CU(cudaMemcpyAsync(shrink, h->s_shrink.p, E * sizeof(int), cudaMemcpyDeviceToHost, st));
-  return finish_stats(h, st);
+  for (int i = 0; i < 8; ++i)
+    if (dst[i]) CU(cudaMemcpyAsync(h->stage + off[i], src[i], sz[i], cudaMemcpyDeviceToHost, st));
+  if (finish_stats(h, st)) return 1;
+  for (int i = 0; i < 8; ++i)
+    if (dst[i]) memcpy(dst[i], h->stage + off[i], sz[i]);
+  return 0;
 }
 
 int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, double* cand_cost, double* cand_lamb,

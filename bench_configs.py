@@ -1,5 +1,6 @@
 """Measurements of the BASELINE.json configs that are not the bench.py headline (config 5):
 
+    python bench_configs.py stock       # config 1: the reference's own 10-lap run through the drop-in classes
     python bench_configs.py latency     # config 2: one closed-loop lap, K=64, L=8: per-step latency on 1 GPU
     python bench_configs.py episodes    # config 3: independent closed-loop episodes (512 per GPU), K=8, L=2
     python bench_configs.py horizon     # config 4a: horizon sweep N=10..200, flat batch with obstacle barrier
@@ -21,6 +22,50 @@ from ilqr_iterative_tasks_b200 import _abi, engine, episodes, synth  # noqa: E40
 
 def flops_per_iteration(N):
     return 927 * N + 177
+
+
+def stock(device=0, laps=10, K=8, L=2):
+    """BASELINE config 1: the reference's own run -- `ilqr_test.py --lap-number 10 --num-ss-iters 2
+    --num-ss-points 8` -- driven through the drop-in classes exactly as that script drives the reference
+    (one `calc_input` = one controller step on the GPU; plant and lap bookkeeping in the host loop)."""
+    import ilqr_iterative_tasks_b200 as pkg
+
+    pkg.install_dropin()
+    from utils import base  # the drop-in
+
+    dt, N = 1, 6
+    ego = base.KineticBicycle(False, system_param=base.KineticBicycleParam())
+    ego.set_state([0, 0, 0, 0])
+    ego.set_timestep(dt)
+    ego.get_traj()
+    ego.set_zero_noise()
+    ctrl = base.iLqr(base.iLqrParam(num_ss_points=K, num_ss_iter=L, timestep=dt, num_horizon=N), obstacle=base.Obstacle(31, -3, 8, 6),
+                     system_param=base.KineticBicycleParam())
+    ctrl.add_trajectory(ego.xcl, ego.ucl)
+    ctrl.set_timestep(dt)
+    ego.set_ctrl_policy(ctrl)
+    sim = base.Simulator()
+    sim.set_robotic(ego)
+    sim.set_timestep(dt)
+    sim.set_traj()
+    import contextlib
+    import io
+
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):  # Simulator.sim prints "iteration: k finished" like the reference
+        for lap in range(laps):
+            sim.sim(lap, sim_time=50)
+            ego.data["state"][-1][-1, :] = ego.xcl[-1, :]
+            ctrl.add_trajectory(ego.data["state"][-1], ego.data["input"][-1])
+    wall = time.perf_counter() - t0
+    solver = np.concatenate([np.asarray(d).ravel() for d in ego.diagnostics["solver_time"]])
+    return {
+        "config": "BASELINE config 1: ilqr_test.py --lap-number %d --num-ss-iters %d --num-ss-points %d through the drop-in" % (laps, L, K),
+        "wall_s": wall, "lap_steps": [int(len(s)) - 1 for s in ego.data["state"]],
+        "controller_step_ms_p50": float(np.median(solver) * 1e3), "controller_steps": int(solver.size),
+        "reference": {"wall_s": 302.0, "lap_steps": [54, 29, 23, 23, 22, 22, 22, 22, 22, 22],
+                      "note": "unmodified Python reference in the build container, one core (SURVEY.md 8c)"},
+    }  # fmt: skip
 
 
 def latency(device=0):
@@ -115,5 +160,5 @@ def horizon_sweep(device=0):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "latency"
     dev = int(os.environ.get("LOCAL_RANK", "0"))
-    fn = {"latency": latency, "episodes": episodes_cfg, "horizon": horizon_sweep}[what]
+    fn = {"stock": stock, "latency": latency, "episodes": episodes_cfg, "horizon": horizon_sweep}[what]
     print(json.dumps(fn(dev)))

@@ -1,5 +1,7 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle and the
 golden vectors minted from the Python reference.  Discrete results exact; floats within 1e-9 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -162,6 +164,64 @@ def test_controller_step_synthetic_horizons(eng_mod):
         assert np.abs(out["x_pred"][0] - g[k + "x_pred"]).max() <= H.RTOL * max(1.0, np.abs(g[k + "x_pred"]).max())
         assert np.abs(out["u_pred"][0] - g[k + "u_pred"]).max() <= H.RTOL * 2
         e.close()
+
+
+_VARIANT_SCRIPT = r"""
+import sys, json, hashlib, numpy as np
+sys.path.insert(0, {root!r})
+from tests import helpers as H
+from ilqr_iterative_tasks_b200 import engine
+g = H.load("steps_k64.npz")
+p = H.step_params(g)
+e = engine.Engine(p, n_episodes=1, lap_capacity=128)
+added, h, ok = 0, hashlib.sha256(), True
+for si, s in list(enumerate(g["solve_ids"]))[::3]:
+    n_laps = int(g["step/n_laps"][s])
+    while added < n_laps:
+        e.add_lap(0, g["lap%d" % added]); added += 1
+    e.set_obstacle(0, H.step_obstacle(g, s))
+    out = e.solve_step(g["step/x"][s].reshape(1, 4))
+    tr = e.step_trace(1)
+    ok = ok and np.array_equal(tr["sel_idx"][0], g["solve/sel_idx"][si]) and np.array_equal(tr["cand_iters"][0], g["solve/c_iters"][si])
+    ok = ok and np.array_equal(np.nan_to_num(tr["cand_lamb"][0], nan=-1.0), np.nan_to_num(g["solve/c_lamb"][si], nan=-1.0))
+    xr = g["solve/x_pred"][si]
+    ok = ok and float(np.abs(out["x_pred"][0] - xr).max()) <= H.RTOL * max(1.0, float(np.abs(xr).max()))
+    for k in ("u", "x_pred", "u_pred", "winner_idx"):
+        h.update(np.ascontiguousarray(out[k]).tobytes())
+    h.update(np.nan_to_num(tr["cand_cost"][0], nan=-1.0, posinf=-2.0).tobytes())
+e.close()
+print("RESULT" + json.dumps({{"ok": bool(ok), "digest": h.hexdigest()}}))
+"""
+
+
+def test_controller_step_kernel_variants_agree():
+    """The controller-step kernel exists in several shapes chosen by load (rungs 1 / 2 / 4 per chain, 4 / 8 / 32
+    lanes per chain, latency-oriented core or the generic one).  Each is forced through its tuning switch in a
+    process of its own (the switches are read once), replays the K=64 golden steps, and must reproduce the
+    reference's discrete trace; the latency-oriented shapes must agree with each other bit for bit, and so must
+    the generic ones (the two cores differ by rounding only: same arithmetic, different FMA contraction)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    variants = [
+        {"I2LQR_GROUP": "32"}, {"I2LQR_GROUP": "8"}, {"I2LQR_GROUP": "4"}, {"I2LQR_RUNGS": "2"}, {"I2LQR_RUNGS": "1"},
+        {"I2LQR_CHAIN_LAT": "0"}, {"I2LQR_CHAIN_LAT": "0", "I2LQR_RUNGS": "1"}, {"I2LQR_CHAIN_LAT": "0", "I2LQR_SCRATCH": "1"},
+    ]  # fmt: skip
+    for env in variants:
+        full = dict(os.environ)
+        full.update(env)
+        out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=root)], capture_output=True, text=True, timeout=600, env=full)
+        assert out.returncode == 0, (env, out.stderr[-1500:])
+        res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT")][0][6:])
+        assert res["ok"], env
+        digests[tuple(sorted(env.items()))] = res["digest"]
+    lat = {d for k, d in digests.items() if ("I2LQR_CHAIN_LAT", "0") not in k}
+    gen = {d for k, d in digests.items() if ("I2LQR_CHAIN_LAT", "0") in k}
+    assert len(lat) == 1, digests
+    assert len(gen) == 1, digests
 
 
 def test_multi_episode_step_equals_single(eng_mod):

@@ -123,6 +123,8 @@ struct i2lqr_handle {
   // controller-step workspace
   DevBuf<double> s_x, s_u, s_xpred, s_upred, s_cand_x, s_cand_u, s_cand_cost, s_cand_lamb, s_wcost;
   DevBuf<long long> s_sel_idx, s_widx, q_idx;
+  bool split_open = false;  // between i2lqr_split_begin and i2lqr_split_end
+  DevBuf<int> s_sel_cnt_own;
   DevBuf<int> s_sel_cnt, s_cand_iters, s_wlap, s_wrank, s_shrink, q_cnt;
   DevBuf<double> q_x0;
   // batched episodes (K4)
@@ -486,7 +488,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
                   &h->q_x0})
     b->release();
   for (auto* b : {&h->s_sel_idx, &h->s_widx, &h->q_idx}) b->release();
-  for (auto* b : {&h->b_iters, &h->s_sel_cnt, &h->s_cand_iters, &h->s_wlap, &h->s_wrank, &h->s_shrink, &h->q_cnt}) b->release();
+  for (auto* b : {&h->b_iters, &h->s_sel_cnt, &h->s_sel_cnt_own, &h->s_cand_iters, &h->s_wlap, &h->s_wrank, &h->s_shrink, &h->q_cnt}) b->release();
   for (auto* b : {&h->ep_upred, &h->ep_goal, &h->ep_lapx, &h->ep_lapu}) b->release();
   for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen}) b->release();
   h->d_obs0.release();
@@ -822,82 +824,139 @@ int ensure_step_workspace(i2lqr_handle* h) {
   return 0;
 }
 
-// The three outer iterations of calc_input on device-resident state x (E,4); results stay on the device.
-int run_step(i2lqr_handle* h, int n_episodes, const int* d_active, cudaStream_t st) {
+// One outer iteration of calc_input (utils/base.py:384-478) as three launches; the split form of the step
+// (i2lqr_split_*) calls them one by one with an exchange between K2 and K3.
+int launch_knn_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, cudaStream_t st) {
   int warps;
   size_t smem;
   if (knn_smem_config(h, &warps, &smem)) return 1;
+  KnnArgs ka{};
+  ka.set = h->set;
+  ka.K = h->K;
+  ka.it = it;
+  ka.n_episodes = n_episodes;
+  ka.x = h->s_x.p;
+  ka.x_pred = h->s_xpred.p;
+  ka.N = h->kp.N;
+  ka.active = d_active;
+  ka.sel_idx = h->s_sel_idx.p;
+  ka.sel_cnt = h->s_sel_cnt.p;
+  const long long n_warps = (long long)n_episodes * h->L;
+  knn_kernel<<<(unsigned)((n_warps + warps - 1) / warps), 32 * warps, smem, st>>>(ka);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  return 0;
+}
+
+// `sel_cnt` = candidates per (episode, lap) the chains walk: the K-nearest counts, or a masked copy of them
+// when this handle only owns some of the laps.
+int launch_chain_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, const int* sel_cnt, cudaStream_t st) {
+  Work w{};
+  w.mode = 1;
+  w.n_items = (long long)n_episodes * h->L;
+  w.it = it;
+  w.scale = it == 0 ? 1.0 : (it == 1 ? 10.0 : 100.0);  // 10**it, utils/base.py:428-435
+  w.set = h->set;
+  w.x = h->s_x.p;
+  w.ep_obs = h->d_obs.p;
+  w.active = d_active;
+  w.sel_idx = h->s_sel_idx.p;
+  w.sel_cnt = sel_cnt;
+  w.cand_x = h->s_cand_x.p;
+  w.cand_u = h->s_cand_u.p;
+  w.cand_cost = h->s_cand_cost.p;
+  w.cand_lamb = h->s_cand_lamb.p;
+  w.cand_iters = h->s_cand_iters.p;
+  return launch_chain(h, w, st);
+}
+
+int launch_winner_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, cudaStream_t st) {
+  WinnerArgs wa{};
+  wa.n_episodes = n_episodes;
+  wa.it = it;
+  wa.L = h->L;
+  wa.K = h->K;
+  wa.N = h->kp.N;
+  wa.lap_count = h->set.lap_count;
+  wa.lap_len = h->set.lap_len;
+  wa.active = d_active;
+  wa.sel_cnt = h->s_sel_cnt.p;
+  wa.sel_idx = h->s_sel_idx.p;
+  wa.cand_cost = h->s_cand_cost.p;
+  wa.cand_x = h->s_cand_x.p;
+  wa.cand_u = h->s_cand_u.p;
+  wa.u = h->s_u.p;
+  wa.x_pred = h->s_xpred.p;
+  wa.u_pred = h->s_upred.p;
+  wa.winner_lap = h->s_wlap.p;
+  wa.winner_rank = h->s_wrank.p;
+  wa.winner_idx = h->s_widx.p;
+  wa.winner_cost = h->s_wcost.p;
+  wa.shrink = h->s_shrink.p;
+  const int wthreads = 128;
+  winner_kernel<<<(unsigned)(((long long)n_episodes * 32 + wthreads - 1) / wthreads), wthreads, 0, st>>>(wa);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  return 0;
+}
+
+// unused trace slots read as "no candidate"
+int clear_step_trace(i2lqr_handle* h, cudaStream_t st) {
+  const size_t n = (size_t)h->E * kOuter * h->L * h->K;
+  CU(cudaMemsetAsync(h->s_sel_idx.p, 0xff, sizeof(long long) * n, st));
+  CU(cudaMemsetAsync(h->s_cand_cost.p, 0xff, sizeof(double) * n, st));
+  CU(cudaMemsetAsync(h->s_cand_lamb.p, 0xff, sizeof(double) * n, st));
+  CU(cudaMemsetAsync(h->s_cand_iters.p, 0xff, sizeof(int) * n, st));
+  return 0;
+}
+
+// The three outer iterations of calc_input on device-resident state x (E,4); results stay on the device.
+int run_step(i2lqr_handle* h, int n_episodes, const int* d_active, cudaStream_t st) {
   if (sync_obstacles(h)) return 1;
-  const size_t E = h->E, L = h->L, K = h->K;
-  // unused trace slots read as "no candidate"
-  CU(cudaMemsetAsync(h->s_sel_idx.p, 0xff, sizeof(long long) * E * kOuter * L * K, st));
-  CU(cudaMemsetAsync(h->s_cand_cost.p, 0xff, sizeof(double) * E * kOuter * L * K, st));
-  CU(cudaMemsetAsync(h->s_cand_lamb.p, 0xff, sizeof(double) * E * kOuter * L * K, st));
-  CU(cudaMemsetAsync(h->s_cand_iters.p, 0xff, sizeof(int) * E * kOuter * L * K, st));
-  double scale = 1.0;
+  if (clear_step_trace(h, st)) return 1;
   for (int it = 0; it < kOuter; ++it) {
-    KnnArgs ka{};
-    ka.set = h->set;
-    ka.K = h->K;
-    ka.it = it;
-    ka.n_episodes = n_episodes;
-    ka.x = h->s_x.p;
-    ka.x_pred = h->s_xpred.p;
-    ka.N = h->kp.N;
-    ka.active = d_active;
-    ka.sel_idx = h->s_sel_idx.p;
-    ka.sel_cnt = h->s_sel_cnt.p;
-    const long long n_warps = (long long)n_episodes * h->L;
-    knn_kernel<<<(unsigned)((n_warps + warps - 1) / warps), 32 * warps, smem, st>>>(ka);
-    CU(cudaGetLastError());
-    h->last_launches += 1;
-
-    Work w{};
-    w.mode = 1;
-    w.n_items = n_warps;
-    w.it = it;
-    w.scale = scale;
-    w.set = h->set;
-    w.x = h->s_x.p;
-    w.ep_obs = h->d_obs.p;
-    w.active = d_active;
-    w.sel_idx = h->s_sel_idx.p;
-    w.sel_cnt = h->s_sel_cnt.p;
-    w.cand_x = h->s_cand_x.p;
-    w.cand_u = h->s_cand_u.p;
-    w.cand_cost = h->s_cand_cost.p;
-    w.cand_lamb = h->s_cand_lamb.p;
-    w.cand_iters = h->s_cand_iters.p;
-    if (launch_chain(h, w, st)) return 1;
-
-    WinnerArgs wa{};
-    wa.n_episodes = n_episodes;
-    wa.it = it;
-    wa.L = h->L;
-    wa.K = h->K;
-    wa.N = h->kp.N;
-    wa.lap_count = h->set.lap_count;
-    wa.lap_len = h->set.lap_len;
-    wa.active = d_active;
-    wa.sel_cnt = h->s_sel_cnt.p;
-    wa.sel_idx = h->s_sel_idx.p;
-    wa.cand_cost = h->s_cand_cost.p;
-    wa.cand_x = h->s_cand_x.p;
-    wa.cand_u = h->s_cand_u.p;
-    wa.u = h->s_u.p;
-    wa.x_pred = h->s_xpred.p;
-    wa.u_pred = h->s_upred.p;
-    wa.winner_lap = h->s_wlap.p;
-    wa.winner_rank = h->s_wrank.p;
-    wa.winner_idx = h->s_widx.p;
-    wa.winner_cost = h->s_wcost.p;
-    wa.shrink = h->s_shrink.p;
-    const int wthreads = 128;
-    winner_kernel<<<(unsigned)(((long long)n_episodes * 32 + wthreads - 1) / wthreads), wthreads, 0, st>>>(wa);
-    CU(cudaGetLastError());
-    h->last_launches += 1;
-    scale *= 10.0;
+    if (launch_knn_step(h, it, n_episodes, d_active, st)) return 1;
+    if (launch_chain_step(h, it, n_episodes, d_active, h->s_sel_cnt.p, st)) return 1;
+    if (launch_winner_step(h, it, n_episodes, d_active, st)) return 1;
   }
+  return 0;
+}
+
+// The caller's arrays are ordinary (pageable) memory: the state goes up and the results come down through one
+// pinned staging block, so a controller-step call issues asynchronous copies only and blocks once.
+int stage_reserve(i2lqr_handle* h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return 0;
+  if (h->stage) cudaFreeHost(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  CU(cudaMallocHost((void**)&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+size_t step_result_bytes(i2lqr_handle* h, int n_episodes) {
+  const size_t E = n_episodes, N = h->kp.N;
+  return 16 * 9 + E * (2 + 4 * (N + 1) + 2 * N + 1) * sizeof(double) + E * 3 * sizeof(int) + E * sizeof(long long);
+}
+// Results of the step that was just queued on `st`: device -> staging block (from byte `base`) -> caller.
+int download_step_results(i2lqr_handle* h, int n_episodes, double* u, double* x_pred, double* u_pred, int32_t* winner_lap,
+                          int32_t* winner_rank, int64_t* winner_idx, double* winner_cost, int32_t* shrink, size_t base,
+                          cudaStream_t st) {
+  const size_t E = n_episodes, N = h->kp.N;
+  const size_t sz[8] = {E * 2 * sizeof(double), E * 4 * (N + 1) * sizeof(double), E * 2 * N * sizeof(double), E * sizeof(int),
+                        E * sizeof(int),        E * sizeof(long long),            E * sizeof(double),         E * sizeof(int)};
+  const void* src[8] = {h->s_u.p, h->s_xpred.p, h->s_upred.p, h->s_wlap.p, h->s_wrank.p, h->s_widx.p, h->s_wcost.p, h->s_shrink.p};
+  void* dst[8] = {u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink};
+  size_t off[8], total = base;
+  for (int i = 0; i < 8; ++i) {
+    off[i] = total;
+    total += (sz[i] + 15) / 16 * 16;
+  }
+  if (total > h->stage_bytes) return fail("staging block too small (%zu > %zu)", total, h->stage_bytes);
+  for (int i = 0; i < 8; ++i)
+    if (dst[i]) CU(cudaMemcpyAsync(h->stage + off[i], src[i], sz[i], cudaMemcpyDeviceToHost, st));
+  if (finish_stats(h, st)) return 1;
+  for (int i = 0; i < 8; ++i)
+    if (dst[i]) memcpy(dst[i], h->stage + off[i], sz[i]);
   return 0;
 }
 }  // namespace
@@ -913,37 +972,15 @@ int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u
   CU(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   if (ensure_step_workspace(h)) return 1;
-  const size_t E = n_episodes, N = h->kp.N;
-  // The caller's arrays are ordinary (pageable) memory: the state goes up and the results come down through one
-  // pinned staging block, so the call issues asynchronous copies only and blocks once.
-  const size_t n_in = E * 4 * sizeof(double);
-  const size_t sz[8] = {E * 2 * sizeof(double), E * 4 * (N + 1) * sizeof(double), E * 2 * N * sizeof(double), E * sizeof(int),
-                        E * sizeof(int),        E * sizeof(long long),            E * sizeof(double),         E * sizeof(int)};
-  const void* src[8] = {h->s_u.p, h->s_xpred.p, h->s_upred.p, h->s_wlap.p, h->s_wrank.p, h->s_widx.p, h->s_wcost.p, h->s_shrink.p};
-  void* dst[8] = {u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink};
-  size_t off[8], total = (n_in + 15) / 16 * 16;
-  for (int i = 0; i < 8; ++i) {
-    off[i] = total;
-    total += (sz[i] + 15) / 16 * 16;
-  }
-  if (total > h->stage_bytes) {
-    if (h->stage) cudaFreeHost(h->stage);
-    h->stage = nullptr;
-    h->stage_bytes = 0;
-    CU(cudaMallocHost((void**)&h->stage, total));
-    h->stage_bytes = total;
-  }
+  const size_t n_in = (size_t)n_episodes * 4 * sizeof(double);
+  if (stage_reserve(h, n_in + step_result_bytes(h, n_episodes))) return 1;
   memcpy(h->stage, x, n_in);
   CU(cudaMemcpyAsync(h->s_x.p, h->stage, n_in, cudaMemcpyHostToDevice, st));
   if (begin_stats(h, st)) return 1;
   if (run_step(h, n_episodes, nullptr, st)) return 1;
   CU(cudaEventRecord(h->ev1, st));
-  for (int i = 0; i < 8; ++i)
-    if (dst[i]) CU(cudaMemcpyAsync(h->stage + off[i], src[i], sz[i], cudaMemcpyDeviceToHost, st));
-  if (finish_stats(h, st)) return 1;
-  for (int i = 0; i < 8; ++i)
-    if (dst[i]) memcpy(dst[i], h->stage + off[i], sz[i]);
-  return 0;
+  return download_step_results(h, n_episodes, u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink,
+                               (n_in + 15) / 16 * 16, st);
 }
 
 int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, double* cand_cost, double* cand_lamb,
@@ -957,6 +994,112 @@ int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, doub
   if (cand_cost) CU(cudaMemcpy(cand_cost, h->s_cand_cost.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (cand_lamb) CU(cudaMemcpy(cand_lamb, h->s_cand_lamb.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (cand_iters) CU(cudaMemcpy(cand_iters, h->s_cand_iters.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// --------------------------------------------------------------------- controller step split over handles
+namespace {
+int split_check(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts) {
+  if (!h) return fail("null handle");
+  if (n_episodes < 1 || n_episodes > h->E) return fail("n_episodes %d out of range [1,%d]", n_episodes, h->E);
+  if (it < 0 || it >= kOuter) return fail("outer iteration %d out of range [0,%d)", it, kOuter);
+  if (n_parts < 1 || part < 0 || part >= n_parts) return fail("part %d of %d is not a valid split", part, n_parts);
+  if (!h->split_open) return fail("no split step is open (call i2lqr_split_begin first)");
+  return 0;
+}
+SplitArgs split_args(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts, double* rows) {
+  SplitArgs a{};
+  a.n_episodes = n_episodes;
+  a.it = it;
+  a.L = h->L;
+  a.K = h->K;
+  a.N = h->kp.N;
+  a.part = part;
+  a.n_parts = n_parts;
+  a.lap_count = h->set.lap_count;
+  a.sel_cnt = h->s_sel_cnt.p;
+  a.sel_cnt_own = h->s_sel_cnt_own.p;
+  a.cand_cost = h->s_cand_cost.p;
+  a.cand_lamb = h->s_cand_lamb.p;
+  a.cand_iters = h->s_cand_iters.p;
+  a.cand_x = h->s_cand_x.p;
+  a.cand_u = h->s_cand_u.p;
+  a.rows = rows;
+  return a;
+}
+}  // namespace
+
+int i2lqr_split_row_doubles(i2lqr_handle* h, int64_t* row_doubles) {
+  if (!h || !row_doubles) return fail("null argument");
+  *row_doubles = split_row_doubles(h->K, h->kp.N);
+  return 0;
+}
+
+int i2lqr_split_begin(i2lqr_handle* h, int n_episodes, const double* x, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  if (n_episodes < 1 || n_episodes > h->E) return fail("n_episodes %d out of range [1,%d]", n_episodes, h->E);
+  if (!x) return fail("null state");
+  for (int e = 0; e < n_episodes; ++e)
+    if (h->h_lap_count[e] == 0) return fail("episode %d has no stored lap (call add_trajectory first)", e);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  if (ensure_step_workspace(h)) return 1;
+  CU(h->s_sel_cnt_own.ensure((size_t)h->E * h->L));
+  if (sync_obstacles(h)) return 1;
+  if (st != h->stream) CU(cudaStreamSynchronize(h->stream));  // the obstacle upload rides the handle's stream
+  const size_t n_in = (size_t)n_episodes * 4 * sizeof(double);
+  if (stage_reserve(h, n_in + step_result_bytes(h, n_episodes))) return 1;
+  memcpy(h->stage, x, n_in);
+  CU(cudaMemcpyAsync(h->s_x.p, h->stage, n_in, cudaMemcpyHostToDevice, st));
+  if (begin_stats(h, st)) return 1;
+  if (clear_step_trace(h, st)) return 1;
+  h->split_open = true;
+  return 0;
+}
+
+int i2lqr_split_solve(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts, double* rows_device,
+                      void* cuda_stream) {
+  if (split_check(h, n_episodes, it, part, n_parts)) return 1;
+  if (!rows_device) return fail("null exchange buffer");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  if (launch_knn_step(h, it, n_episodes, nullptr, st)) return 1;
+  const SplitArgs a = split_args(h, n_episodes, it, part, n_parts, rows_device);
+  const int n_laps = n_episodes * h->L;
+  split_mask_kernel<<<(n_laps + 127) / 128, 128, 0, st>>>(a);
+  CU(cudaGetLastError());
+  if (launch_chain_step(h, it, n_episodes, nullptr, h->s_sel_cnt_own.p, st)) return 1;
+  split_pack_kernel<<<(n_laps * 32 + 127) / 128, 128, 0, st>>>(a);
+  CU(cudaGetLastError());
+  h->last_launches += 2;
+  return 0;
+}
+
+int i2lqr_split_merge(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts, const double* all_rows_device,
+                      void* cuda_stream) {
+  if (split_check(h, n_episodes, it, part, n_parts)) return 1;
+  if (!all_rows_device) return fail("null exchange buffer");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  const SplitArgs a = split_args(h, n_episodes, it, part, n_parts, const_cast<double*>(all_rows_device));
+  const int n_laps = n_episodes * h->L;
+  split_unpack_kernel<<<(n_laps * 32 + 127) / 128, 128, 0, st>>>(a);
+  CU(cudaGetLastError());
+  h->last_launches += 1;
+  return launch_winner_step(h, it, n_episodes, nullptr, st);
+}
+
+int i2lqr_split_end(i2lqr_handle* h, int n_episodes, double* u, double* x_pred, double* u_pred, int32_t* winner_lap,
+                    int32_t* winner_rank, int64_t* winner_idx, double* winner_cost, int32_t* shrink, void* cuda_stream) {
+  if (!h) return fail("null handle");
+  if (n_episodes < 1 || n_episodes > h->E) return fail("n_episodes %d out of range [1,%d]", n_episodes, h->E);
+  if (!h->split_open) return fail("no split step is open (call i2lqr_split_begin first)");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  h->split_open = false;
+  CU(cudaEventRecord(h->ev1, st));
+  if (download_step_results(h, n_episodes, u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink, 0, st))
+    return 1;
   return 0;
 }
 

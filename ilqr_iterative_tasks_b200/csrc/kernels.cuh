@@ -792,6 +792,87 @@ __global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
   if (lane < 2) a.u[(size_t)e * 2 + lane] = a.cand_u[cslot * nu + (size_t)lane * a.N];
 }
 
+// ------------------------------------------------------------------------------- split controller step
+// One controller step whose laps are solved by several handles (GPUs): SURVEY.md 8e "Collective".  Handle
+// `part` of `n_parts` owns the active laps with (relative lap number) % n_parts == part and runs their lambda
+// chains; what the other handles need of a lap travels as one packed row per (episode, lap):
+//   [0] rank of the lap's first arg-min candidate   [1..K] relaxed costs   [K+1..2K] lambda after each candidate
+//   [2K+1..3K] executed iterations   then that candidate's xvar (4,N+1) and uvar (2,N)
+// -- only a lap's first arg-min can win the step (utils/base.py:462-465), so its trajectory is the only one that
+// has to cross.  After the all-gather every handle holds every row, unpacks them into its own step workspace
+// and runs the same winner_kernel: all handles end the outer iteration with bit-identical x_pred / u_pred.
+struct SplitArgs {
+  int n_episodes, it, L, K, N;
+  int part, n_parts;
+  const int* lap_count;    // (E)
+  const int* sel_cnt;      // (E,L)  true K-nearest counts
+  int* sel_cnt_own;        // (E,L)  counts with the laps of other handles zeroed (what the chains walk)
+  double* cand_cost;       // (E,3,L,K)
+  double* cand_lamb;
+  int* cand_iters;
+  double* cand_x;          // (E,L,K,4,N+1)
+  double* cand_u;          // (E,L,K,2,N)
+  double* rows;            // pack: (E,L,row) of this handle; unpack: (n_parts,E,L,row) gathered
+};
+__host__ __device__ __forceinline__ int split_row_doubles(int K, int N) { return 1 + 3 * K + 4 * (N + 1) + 2 * N; }
+
+__global__ void split_mask_kernel(const __grid_constant__ SplitArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_episodes * a.L) return;
+  a.sel_cnt_own[i] = (i % a.L) % a.n_parts == a.part ? a.sel_cnt[i] : 0;
+}
+
+// one warp per (episode, lap)
+__global__ void split_pack_kernel(const __grid_constant__ SplitArgs a) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)a.n_episodes * a.L) return;
+  const int e = (int)(wid / a.L), l = (int)(wid % a.L);
+  const int row = split_row_doubles(a.K, a.N);
+  double* out = a.rows + (size_t)wid * row;
+  const int cnt = l % a.n_parts == a.part ? a.sel_cnt[wid] : 0;
+  if (cnt == 0) {
+    for (int i = lane; i < row; i += 32) out[i] = 0.0;
+    return;
+  }
+  const size_t tslot = (((size_t)e * kOuter + a.it) * a.L + l) * a.K;
+  int br = 0;
+  for (int r = 1; r < cnt; ++r)  // first arg-min, the comparison winner_kernel makes
+    if (a.cand_cost[tslot + r] < a.cand_cost[tslot + br]) br = r;
+  if (lane == 0) out[0] = (double)br;
+  for (int r = lane; r < a.K; r += 32) {
+    out[1 + r] = a.cand_cost[tslot + r];
+    out[1 + a.K + r] = a.cand_lamb[tslot + r];
+    out[1 + 2 * a.K + r] = (double)a.cand_iters[tslot + r];
+  }
+  const size_t cslot = ((size_t)e * a.L + l) * a.K + br;
+  const int nx = 4 * (a.N + 1), nu = 2 * a.N;
+  for (int i = lane; i < nx; i += 32) out[1 + 3 * a.K + i] = a.cand_x[cslot * nx + i];
+  for (int i = lane; i < nu; i += 32) out[1 + 3 * a.K + nx + i] = a.cand_u[cslot * nu + i];
+}
+
+__global__ void split_unpack_kernel(const __grid_constant__ SplitArgs a) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)a.n_episodes * a.L) return;
+  const int e = (int)(wid / a.L), l = (int)(wid % a.L);
+  const int owner = l % a.n_parts;
+  if (owner == a.part || a.sel_cnt[wid] == 0) return;  // own rows are already in place
+  const int row = split_row_doubles(a.K, a.N);
+  const double* in = a.rows + ((size_t)owner * a.n_episodes * a.L + wid) * row;
+  const size_t tslot = (((size_t)e * kOuter + a.it) * a.L + l) * a.K;
+  const int br = (int)in[0];
+  for (int r = lane; r < a.K; r += 32) {
+    a.cand_cost[tslot + r] = in[1 + r];
+    a.cand_lamb[tslot + r] = in[1 + a.K + r];
+    a.cand_iters[tslot + r] = (int)in[1 + 2 * a.K + r];
+  }
+  const size_t cslot = ((size_t)e * a.L + l) * a.K + br;
+  const int nx = 4 * (a.N + 1), nu = 2 * a.N;
+  for (int i = lane; i < nx; i += 32) a.cand_x[cslot * nx + i] = in[1 + 3 * a.K + i];
+  for (int i = lane; i < nu; i += 32) a.cand_u[cslot * nu + i] = in[1 + 3 * a.K + nx + i];
+}
+
 // ------------------------------------------------------------------------------------------------ K4
 // Batched closed-loop episodes: the plant, obstacle motion, termination test, playback bookkeeping and
 // the lap append all stay on the device (Simulator.sim utils/base.py:708-726, KineticBicycle.forward_one_step

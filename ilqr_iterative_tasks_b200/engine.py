@@ -26,7 +26,8 @@ EXPORTS = [
     "i2lqr_set_params", "i2lqr_solve_batch", "i2lqr_solve_batch_device", "i2lqr_add_lap", "i2lqr_num_laps",
     "i2lqr_set_obstacle", "i2lqr_select_knn", "i2lqr_solve_step", "i2lqr_get_step_trace",
     "i2lqr_episodes_begin", "i2lqr_episodes_run_lap", "i2lqr_episodes_status", "i2lqr_episodes_set_noise", "i2lqr_last_stats", "i2lqr_sync_stats",
-    "i2lqr_measure_fp64_peak",
+    "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
+    "i2lqr_split_end",
 ]  # fmt: skip
 
 
@@ -170,15 +171,18 @@ class Engine:
         return idx[: n.value]
 
     # -- controller step -------------------------------------------------------------------------------
-    def solve_step(self, x, n_episodes=None):
-        x = _f64(x).reshape(-1, 4)
-        E = x.shape[0] if n_episodes is None else n_episodes
+    def _step_outputs(self, E):
         N = self.N
-        out = {
+        return {
             "u": np.empty((E, 2)), "x_pred": np.empty((E, 4, N + 1)), "u_pred": np.empty((E, 2, N)),
             "winner_lap": np.empty(E, dtype=np.int32), "winner_rank": np.empty(E, dtype=np.int32),
             "winner_idx": np.empty(E, dtype=np.int64), "winner_cost": np.empty(E), "shrink": np.empty(E, dtype=np.int32),
         }  # fmt: skip
+
+    def solve_step(self, x, n_episodes=None):
+        x = _f64(x).reshape(-1, 4)
+        E = x.shape[0] if n_episodes is None else n_episodes
+        out = self._step_outputs(E)
         _check(lib().i2lqr_solve_step(
             self._h, C.c_int(E), _d(x), _d(out["u"]), _d(out["x_pred"]), _d(out["u_pred"]),
             out["winner_lap"].ctypes.data_as(_i32p), out["winner_rank"].ctypes.data_as(_i32p),
@@ -195,6 +199,33 @@ class Engine:
             t["cand_iters"].ctypes.data_as(_i32p),
         ))  # fmt: skip
         return t
+
+    # -- controller step split over handles (one per GPU) --------------------------------------------------
+    def split_row_doubles(self):
+        n = C.c_int64()
+        _check(lib().i2lqr_split_row_doubles(self._h, C.byref(n)))
+        return n.value
+
+    def split_begin(self, x, stream=None):
+        x = _f64(x).reshape(-1, 4)
+        _check(lib().i2lqr_split_begin(self._h, C.c_int(x.shape[0]), _d(x), C.c_void_p(stream) if stream else None))
+        return x.shape[0]
+
+    def split_solve(self, E, it, part, n_parts, rows_ptr, stream=None):
+        _check(lib().i2lqr_split_solve(self._h, C.c_int(E), C.c_int(it), C.c_int(part), C.c_int(n_parts), C.c_void_p(rows_ptr), C.c_void_p(stream) if stream else None))
+
+    def split_merge(self, E, it, part, n_parts, all_rows_ptr, stream=None):
+        _check(lib().i2lqr_split_merge(self._h, C.c_int(E), C.c_int(it), C.c_int(part), C.c_int(n_parts), C.c_void_p(all_rows_ptr), C.c_void_p(stream) if stream else None))
+
+    def split_end(self, E, stream=None):
+        out = self._step_outputs(E)
+        _check(lib().i2lqr_split_end(
+            self._h, C.c_int(E), _d(out["u"]), _d(out["x_pred"]), _d(out["u_pred"]),
+            out["winner_lap"].ctypes.data_as(_i32p), out["winner_rank"].ctypes.data_as(_i32p),
+            out["winner_idx"].ctypes.data_as(_i64p), _d(out["winner_cost"]), out["shrink"].ctypes.data_as(_i32p),
+            C.c_void_p(stream) if stream else None,
+        ))  # fmt: skip
+        return out
 
     # -- batched closed-loop episodes ------------------------------------------------------------------
     def episodes_begin(self, x_init, goal):

@@ -129,6 +129,33 @@ int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u
 int i2lqr_get_step_trace(i2lqr_handle* h, int n_episodes, int64_t* sel_idx, double* cand_cost, double* cand_lamb,
                          int32_t* cand_iters);
 
+/* ---- controller step whose laps are split over several handles / GPUs --------------------------------- */
+/* The K candidates of one lap form a sequential lambda chain, but the chains of different laps are independent
+ * (iterative_ilqr/utils/base.py:386-455: `for id in range(min_iter, iter)`), so the active laps of ONE step can
+ * be solved by different handles -- normally one per GPU, every handle holding the same safe set.  Handle
+ * `part` of `n_parts` owns the active laps whose position in the lap loop satisfies pos % n_parts == part.
+ * Per outer iteration `it` = 0..2 (the loop at :384):
+ *     i2lqr_split_solve   K-nearest for every lap, the owned laps' chains, then one packed row per
+ *                         (episode, lap) into rows_device (n_episodes, L, row_doubles) -- rows of laps this
+ *                         handle does not own are zero;
+ *     the caller all-gathers rows_device of all parts into all_rows_device (n_parts, n_episodes, L, row_doubles)
+ *                         (ncclAllGather over NVLink; any copy that produces that layout will do);
+ *     i2lqr_split_merge   unpacks the other parts' rows and applies the winner rule (:462-478); every handle then
+ *                         holds the same x_pred / u_pred, which seed the next outer iteration (:398-401).
+ * A row carries the lap's relaxed costs, lambdas and iteration counts (K each) and the trajectory of the lap's
+ * first arg-min candidate, the only one of the lap that can win: row_doubles = 1 + 3K + 4(N+1) + 2N.
+ * All device work is queued on `cuda_stream` (NULL = the handle's stream) without synchronising, so the calls
+ * can be interleaved with NCCL on the same stream; i2lqr_split_end downloads the results (same arguments as
+ * i2lqr_solve_step, any of which may be NULL) and blocks.  Results are bit-identical to i2lqr_solve_step. */
+int i2lqr_split_row_doubles(i2lqr_handle* h, int64_t* row_doubles);
+int i2lqr_split_begin(i2lqr_handle* h, int n_episodes, const double* x, void* cuda_stream);
+int i2lqr_split_solve(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts, double* rows_device,
+                      void* cuda_stream);
+int i2lqr_split_merge(i2lqr_handle* h, int n_episodes, int it, int part, int n_parts, const double* all_rows_device,
+                      void* cuda_stream);
+int i2lqr_split_end(i2lqr_handle* h, int n_episodes, double* u, double* x_pred, double* u_pred, int32_t* winner_lap,
+                    int32_t* winner_rank, int64_t* winner_idx, double* winner_cost, int32_t* shrink, void* cuda_stream);
+
 /* ---- batched closed-loop episodes (device-resident plant + controller) ------------------------------ */
 /* Replaces Simulator.sim + KineticBicycle.forward_one_step (iterative_ilqr/utils/base.py:157-213,708-726)
  * and the lap post-processing of iterative_ilqr/tests/ilqr_test.py:56-60 for all episodes of the handle.

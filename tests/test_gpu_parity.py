@@ -248,6 +248,41 @@ def test_multi_episode_step_equals_single(eng_mod):
     big.close()
 
 
+@pytest.mark.parametrize("name,n_parts", [("k64", 2), ("k64", 3), ("stock", 2), ("moving_left", 4)])
+def test_split_step_equals_single_handle(eng_mod, name, n_parts):
+    """One controller step with its laps split over n_parts handles (the split a multi-GPU step
+    uses, here with every part on this GPU and the all-gather replaced by a concatenation) is bit-identical to
+    i2lqr_solve_step -- outputs and the per-candidate trace -- on recorded steps of the reference's runs."""
+    from ilqr_iterative_tasks_b200 import dist as D
+
+    g = H.load("steps_%s.npz" % name)
+    p = H.step_params(g)
+    whole = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+    parts = [eng_mod.Engine(p, n_episodes=1, lap_capacity=128) for _ in range(n_parts)]
+    added = 0
+    ids = list(g["solve_ids"])
+    for s in ids[:: max(1, len(ids) // 12)]:
+        n_laps = int(g["step/n_laps"][s])
+        while added < n_laps:
+            for e in [whole] + parts:
+                e.add_lap(0, g["lap%d" % added])
+            added += 1
+        for e in [whole] + parts:
+            e.set_obstacle(0, H.step_obstacle(g, s))
+        x = g["step/x"][s].reshape(1, 4)
+        ref = whole.solve_step(x)
+        ref_tr = whole.step_trace(1)
+        outs = D.split_step_local(parts, x)
+        for part, out in enumerate(outs):
+            for key in ref:
+                assert np.array_equal(out[key], ref[key], equal_nan=True), (name, s, part, key)
+            tr = parts[part].step_trace(1)
+            for key in ref_tr:
+                assert np.array_equal(tr[key], ref_tr[key], equal_nan=True), (name, s, part, key)
+    for e in [whole] + parts:
+        e.close()
+
+
 def test_handle_recreation_is_race_free(eng_mod):
     """Regression: handle initialisation used legacy-stream cudaMemset calls that were not ordered against the
     handle's non-blocking stream, so the first add_lap could be wiped (episode 0 lost its lap ~3 % of the

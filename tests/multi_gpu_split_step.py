@@ -55,14 +55,39 @@ def main():
         for key in ref_tr:
             assert np.array_equal(tr[key], ref_tr[key], equal_nan=True), (rank, int(s), key)
         checked += 1
-        if n_laps >= int(g["L"]):  # steady state: all L laps active
-            t_whole.append(t1 - t0)
-            t_split.append(t2 - t1)
+    # latency of both forms at the BASELINE config-2 shape (K=64, L=8, eight stored laps): the recorded laps are
+    # stored again until eight are active, then recorded states are replayed
+    p8 = H.step_params(g)
+    p8.num_ss_iter = 8
+    whole8 = engine.Engine(p8, device=local, n_episodes=1, lap_capacity=128)
+    part8 = engine.Engine(p8, device=local, n_episodes=1, lap_capacity=128)
+    split8 = D.SplitStep(part8, rank, world, n_episodes=1)
+    for l in range(8):
+        lap = g["lap%d" % min(l, added - 1)]
+        whole8.add_lap(0, lap)
+        part8.add_lap(0, lap)
+    for s in list(g["solve_ids"])[:24]:
+        whole8.set_obstacle(0, H.step_obstacle(g, s))
+        part8.set_obstacle(0, H.step_obstacle(g, s))
+        x = g["step/x"][s].reshape(1, 4)
+        dist.barrier()
+        t0 = time.perf_counter()
+        ref = whole8.solve_step(x)
+        t1 = time.perf_counter()
+        dist.barrier()
+        t2 = time.perf_counter()
+        out = split8.solve_step(x)
+        t3 = time.perf_counter()
+        for key in ref:
+            assert np.array_equal(out[key], ref[key], equal_nan=True), (rank, int(s), key)
+        t_whole.append(t1 - t0)
+        t_split.append(t3 - t2)
+        checked += 1
     dist.barrier()
     if rank == 0:
         print(json.dumps({
             "check": "split controller step == single-GPU step, bit for bit", "world_size": world, "steps_checked": checked,
-            "K": int(g["K"]), "L": int(g["L"]), "row_doubles": split.row, "allgather_bytes_per_rank": int(split.rows.numel() * 8),
+            "K": int(g["K"]), "L_parity": int(g["L"]), "L_latency": 8, "row_doubles": split8.row, "allgather_bytes_per_rank": int(split8.rows.numel() * 8),
             "p50_ms_single_gpu": round(1e3 * float(np.median(t_whole)), 3), "p50_ms_split": round(1e3 * float(np.median(t_split)), 3),
         }))  # fmt: skip
         print("OK")

@@ -14,6 +14,7 @@
 
 #include "../../include/i2lqr.h"
 #include "kernels.cuh"
+#include "components.cuh"
 #include "kparams.h"
 
 using namespace i2lqr;
@@ -127,6 +128,9 @@ struct i2lqr_handle {
   DevBuf<int> s_sel_cnt_own;
   DevBuf<int> s_sel_cnt, s_cand_iters, s_wlap, s_wrank, s_shrink, q_cnt;
   DevBuf<double> q_x0;
+  // component entry points (components.cuh): grow-only staging
+  DevBuf<double> c_in[6], c_out[4], c_scratch;
+  DevBuf<DevObstacle> c_obs;
   // batched episodes (K4)
   bool ep_ready = false;
   unsigned long long ep_noise_seed = 0;  // 0 = noise off (every reference script calls set_zero_noise)
@@ -492,6 +496,10 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto* b : {&h->ep_upred, &h->ep_goal, &h->ep_lapx, &h->ep_lapu}) b->release();
   for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen}) b->release();
   h->d_obs0.release();
+  for (auto& b : h->c_in) b.release();
+  for (auto& b : h->c_out) b.release();
+  h->c_scratch.release();
+  h->c_obs.release();
   if (h->h_nrun) cudaFreeHost(h->h_nrun);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->stage) cudaFreeHost(h->stage);
@@ -1101,6 +1109,158 @@ int i2lqr_split_end(i2lqr_handle* h, int n_episodes, double* u, double* x_pred, 
   if (download_step_results(h, n_episodes, u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink, 0, st))
     return 1;
   return 0;
+}
+
+// ------------------------------------------------------------------------------ component entry points
+namespace {
+struct CompIO {  // host arrays of one component call: inputs go up, outputs come down, all on the handle's stream
+  i2lqr_handle* h;
+  cudaStream_t st;
+  int n_in = 0, n_out = 0;
+  double* host_out[4] = {};
+  size_t out_count[4] = {};
+  int in(const double* src, size_t count, const double** dev) {
+    *dev = nullptr;
+    if (!src) return 0;
+    DevBuf<double>& b = h->c_in[n_in++];
+    CU(b.ensure(count));
+    CU(cudaMemcpyAsync(b.p, src, count * sizeof(double), cudaMemcpyHostToDevice, st));
+    *dev = b.p;
+    return 0;
+  }
+  int out(double* dst, size_t count, double** dev) {
+    *dev = nullptr;
+    if (!dst) return 0;
+    DevBuf<double>& b = h->c_out[n_out];
+    CU(b.ensure(count));
+    host_out[n_out] = dst;
+    out_count[n_out] = count;
+    ++n_out;
+    *dev = b.p;
+    return 0;
+  }
+  int obstacles(const i2lqr_obstacle* obs, int64_t n_obs, const DevObstacle** dev) {
+    *dev = nullptr;
+    if (n_obs == 0) return 0;
+    CU(h->c_obs.ensure((size_t)n_obs));
+    CU(cudaMemcpyAsync(h->c_obs.p, obs, (size_t)n_obs * sizeof(DevObstacle), cudaMemcpyHostToDevice, st));
+    *dev = h->c_obs.p;
+    return 0;
+  }
+  int finish() {
+    CU(cudaGetLastError());
+    for (int i = 0; i < n_out; ++i)
+      CU(cudaMemcpyAsync(host_out[i], h->c_out[i].p, out_count[i] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    h->last_launches = 1;
+    return 0;
+  }
+};
+int comp_begin(i2lqr_handle* h, int64_t B, const i2lqr_obstacle* obs, int64_t n_obs) {
+  if (!h) return fail("null handle");
+  if (B < 1) return fail("batch size must be >= 1");
+  if (n_obs != 0 && n_obs != 1 && n_obs != B) return fail("n_obs must be 0, 1 or B");
+  if (n_obs != 0 && !obs) return fail("null obstacle array");
+  if (h->params.precision != 0) return fail("the component entry points are FP64 only");
+  CU(cudaSetDevice(h->device));
+  return 0;
+}
+inline unsigned comp_grid(int64_t B) { return (unsigned)((B + kCompThreads - 1) / kCompThreads); }
+}  // namespace
+
+int i2lqr_dynamics_batch(i2lqr_handle* h, int64_t B, const double* x, const double* u, double* x_next) {
+  if (comp_begin(h, B, nullptr, 0)) return 1;
+  if (!x || !u || !x_next) return fail("null argument");
+  CompIO io{h, h->stream};
+  const double *dx, *du;
+  double* dn;
+  if (io.in(x, B * 4, &dx) || io.in(u, B * 2, &du) || io.out(x_next, B * 4, &dn)) return 1;
+  comp_dynamics_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, dx, du, dn);
+  return io.finish();
+}
+
+int i2lqr_linearize_batch(i2lqr_handle* h, int64_t B, const double* v, const double* theta, const double* accel, double* A,
+                          double* Bm) {
+  if (comp_begin(h, B, nullptr, 0)) return 1;
+  if (!theta) return fail("null theta");
+  if (A && (!v || !accel)) return fail("get_A_matrix needs velocity and acceleration values");
+  const size_t N = h->kp.N;
+  CompIO io{h, h->stream};
+  const double *dv, *dth, *da;
+  double *dA, *dB;
+  if (io.in(v ? v : theta, B * N, &dv) || io.in(theta, B * N, &dth) || io.in(accel, B * N, &da)) return 1;
+  if (io.out(A, B * 16 * N, &dA) || io.out(Bm, B * 8 * N, &dB)) return 1;
+  comp_linearize_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, dv, dth, da, dA, dB);
+  return io.finish();
+}
+
+int i2lqr_cost_derivatives_batch(i2lqr_handle* h, int64_t B, const double* uvar, const double* dX, const double* xvar,
+                                 const i2lqr_obstacle* obs, int64_t n_obs, double* l_u, double* l_uu, double* l_x,
+                                 double* l_xx) {
+  if (comp_begin(h, B, obs, n_obs)) return 1;
+  if (!uvar || !dX || !xvar) return fail("null argument");
+  const size_t N = h->kp.N;
+  CompIO io{h, h->stream};
+  const double *du, *dd, *dx;
+  const DevObstacle* dobs;
+  double *o0, *o1, *o2, *o3;
+  if (io.in(uvar, B * 2 * N, &du) || io.in(dX, B * 4 * (N + 1), &dd) || io.in(xvar, B * 4 * (N + 1), &dx)) return 1;
+  if (io.obstacles(obs, n_obs, &dobs)) return 1;
+  if (io.out(l_u, B * 2 * N, &o0) || io.out(l_uu, B * 4 * N, &o1) || io.out(l_x, B * 4 * N, &o2) || io.out(l_xx, B * 16 * N, &o3))
+    return 1;
+  comp_cost_derivatives_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, du, dd, dx, dobs, n_obs, o0, o1, o2, o3);
+  return io.finish();
+}
+
+int i2lqr_cost_final_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* x_term, const i2lqr_obstacle* obs,
+                           int64_t n_obs, double* l_x, double* l_xx) {
+  if (comp_begin(h, B, obs, n_obs)) return 1;
+  if (!xvar || !x_term) return fail("null argument");
+  const size_t N = h->kp.N;
+  CompIO io{h, h->stream};
+  const double *dx, *dt;
+  const DevObstacle* dobs;
+  double *o0, *o1;
+  if (io.in(xvar, B * 4 * (N + 1), &dx) || io.in(x_term, B * 4, &dt) || io.obstacles(obs, n_obs, &dobs)) return 1;
+  if (io.out(l_x, B * 4, &o0) || io.out(l_xx, B * 16, &o1)) return 1;
+  comp_cost_final_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, dx, dt, dobs, n_obs, o0, o1);
+  return io.finish();
+}
+
+int i2lqr_backward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* uvar, const double* x_term,
+                              const double* lamb, const i2lqr_obstacle* obs, int64_t n_obs, double* k, double* K) {
+  if (comp_begin(h, B, obs, n_obs)) return 1;
+  if (!xvar || !uvar || !x_term || !k || !K) return fail("null argument");
+  const size_t N = h->kp.N;
+  CompIO io{h, h->stream};
+  const double *dx, *du, *dt, *dl;
+  const DevObstacle* dobs;
+  double *o0, *o1;
+  if (io.in(xvar, B * 4 * (N + 1), &dx) || io.in(uvar, B * 2 * N, &du) || io.in(x_term, B * 4, &dt) || io.in(lamb, B, &dl)) return 1;
+  if (io.obstacles(obs, n_obs, &dobs)) return 1;
+  if (io.out(k, B * 2 * N, &o0) || io.out(K, B * 8 * N, &o1)) return 1;
+  const long long lanes = (long long)comp_grid(B) * kCompThreads;
+  CU(h->c_scratch.ensure((size_t)lanes * 18 * N));
+  comp_backward_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, dx, du, dt, dl, dobs, n_obs, h->c_scratch.p, lanes, o0, o1);
+  return io.finish();
+}
+
+int i2lqr_forward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* uvar, const double* x_term,
+                             const double* k, const double* K, double* xvar_new, double* uvar_new, double* cost_new) {
+  if (comp_begin(h, B, nullptr, 0)) return 1;
+  if (!xvar || !uvar || !x_term || !k || !K) return fail("null argument");
+  const size_t N = h->kp.N;
+  CompIO io{h, h->stream};
+  const double *dx, *du, *dt, *dk, *dK;
+  double *o0, *o1, *o2;
+  if (io.in(xvar, B * 4 * (N + 1), &dx) || io.in(uvar, B * 2 * N, &du) || io.in(x_term, B * 4, &dt) || io.in(k, B * 2 * N, &dk) ||
+      io.in(K, B * 8 * N, &dK))
+    return 1;
+  if (io.out(xvar_new, B * 4 * (N + 1), &o0) || io.out(uvar_new, B * 2 * N, &o1) || io.out(cost_new, B, &o2)) return 1;
+  const long long lanes = (long long)comp_grid(B) * kCompThreads;
+  CU(h->c_scratch.ensure((size_t)lanes * 18 * N));
+  comp_forward_kernel<<<comp_grid(B), kCompThreads, 0, io.st>>>(h->kp, B, dx, du, dt, dk, dK, h->c_scratch.p, lanes, o0, o1, o2);
+  return io.finish();
 }
 
 // ------------------------------------------------------------------------------------ batched episodes

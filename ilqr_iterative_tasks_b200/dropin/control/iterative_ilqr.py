@@ -48,3 +48,33 @@ def ilqr(ilqr_param, num_horizon, xtarget, timestep, obstacle, system_param, x_t
         uvar_init=uinit.reshape(1, 2, -1) if uinit.any() else None,
     )
     return out["uvar"][0], out["xvar"][0], float(out["lamb_out"][0])
+
+
+def _component_engine(ilqr_param, num_horizon, timestep, sys_param):
+    params = _abi.params_from_reference(ilqr_param, sys_param, timestep)
+    params.obstacle_horizon = int(ilqr_param.num_horizon)  # control/ilqr_helper.py:134-139
+    params.num_horizon = int(num_horizon)
+    return _engine_for(params)
+
+
+def backward_pass(xvar, uvar, x_terminal, dX, lamb, num_horizon, timestep, ilqr_param, obstacle, sys_param):
+    """Drop-in for `backward_pass` (reference: iterative_ilqr/control/iterative_ilqr.py:88-130): the Riccati recursion
+    on the GPU (i2lqr_backward_pass_batch), returning `(matrix_k (2,N), matrix_K (2,4,N))`.  `dX` must be what
+    ilqr() maintains, xvar - xtarget with xtarget = 0 (utils/base.py:374); anything else raises ValueError."""
+    xvar = np.asarray(xvar, dtype=np.float64)
+    if not np.array_equal(np.asarray(dX, dtype=np.float64)[:, :num_horizon], xvar[:, :num_horizon]):
+        raise ValueError("backward_pass: dX must equal xvar - xtarget (xtarget = 0), as ilqr() maintains it")
+    eng = _component_engine(ilqr_param, num_horizon, timestep, sys_param)
+    k, K = eng.backward_pass(xvar[None], np.asarray(uvar, dtype=np.float64)[None], np.asarray(x_terminal, dtype=np.float64).reshape(1, 4),
+                             np.array([float(lamb)]), _abi.obstacle_struct(obstacle))  # fmt: skip
+    return k[0], K[0]
+
+
+def forward_pass(xvar, uvar, x_terminal, ilqr_param, timestep, num_horizon, matrix_k, matrix_K, sys_param):
+    """Drop-in for `forward_pass` (reference: iterative_ilqr/control/iterative_ilqr.py:133-160): full-step rollout
+    with clipping on the GPU (i2lqr_forward_pass_batch); returns `(xvar_new, uvar_new, cost_new)`."""
+    eng = _component_engine(ilqr_param, num_horizon, timestep, sys_param)
+    xn, un, cost = eng.forward_pass(np.asarray(xvar, dtype=np.float64)[None], np.asarray(uvar, dtype=np.float64)[None],
+                                    np.asarray(x_terminal, dtype=np.float64).reshape(1, 4), np.asarray(matrix_k, dtype=np.float64)[None],
+                                    np.asarray(matrix_K, dtype=np.float64)[None])  # fmt: skip
+    return xn[0], un[0], float(cost[0])

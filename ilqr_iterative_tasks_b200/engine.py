@@ -27,7 +27,8 @@ EXPORTS = [
     "i2lqr_set_obstacle", "i2lqr_select_knn", "i2lqr_solve_step", "i2lqr_get_step_trace",
     "i2lqr_episodes_begin", "i2lqr_episodes_run_lap", "i2lqr_episodes_status", "i2lqr_episodes_set_noise", "i2lqr_last_stats", "i2lqr_sync_stats",
     "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
-    "i2lqr_split_end",
+    "i2lqr_split_end", "i2lqr_dynamics_batch", "i2lqr_linearize_batch", "i2lqr_cost_derivatives_batch",
+    "i2lqr_cost_final_batch", "i2lqr_backward_pass_batch", "i2lqr_forward_pass_batch",
 ]  # fmt: skip
 
 
@@ -226,6 +227,67 @@ class Engine:
             C.c_void_p(stream) if stream else None,
         ))  # fmt: skip
         return out
+
+    # -- the functions an iteration is made of (include/i2lqr.h, "one by one") ------------------------------
+    def dynamics(self, x, u):
+        x, u = _f64(x).reshape(-1, 4), _f64(u).reshape(-1, 2)
+        out = np.empty_like(x)
+        _check(lib().i2lqr_dynamics_batch(self._h, C.c_int64(x.shape[0]), _d(x), _d(u), _d(out)))
+        return out
+
+    def linearize(self, v, theta, accel, want_A=True, want_B=True):
+        N = self.N
+        theta = _f64(theta).reshape(-1, N)
+        B = theta.shape[0]
+        v = None if v is None else _f64(v, (B, N))
+        accel = None if accel is None else _f64(accel, (B, N))
+        A = np.empty((B, 4, 4, N)) if want_A else None
+        Bm = np.empty((B, 4, 2, N)) if want_B else None
+        _check(lib().i2lqr_linearize_batch(self._h, C.c_int64(B), _d(v), _d(theta), _d(accel), _d(A), _d(Bm)))
+        return A, Bm
+
+    def cost_derivatives(self, uvar, dX, xvar, obs=None):
+        N = self.N
+        xvar = _f64(xvar).reshape(-1, 4, N + 1)
+        B = xvar.shape[0]
+        uvar, dX = _f64(uvar, (B, 2, N)), _f64(dX, (B, 4, N + 1))
+        optr, n_obs, keep = self._obs_arg(obs, B)
+        l_u, l_uu, l_x, l_xx = np.empty((B, 2, N)), np.empty((B, 2, 2, N)), np.empty((B, 4, N)), np.empty((B, 4, 4, N))
+        _check(lib().i2lqr_cost_derivatives_batch(self._h, C.c_int64(B), _d(uvar), _d(dX), _d(xvar), optr, C.c_int64(n_obs), _d(l_u), _d(l_uu), _d(l_x), _d(l_xx)))
+        del keep
+        return l_u, l_uu, l_x, l_xx
+
+    def cost_final(self, xvar, x_term, obs=None):
+        N = self.N
+        xvar = _f64(xvar).reshape(-1, 4, N + 1)
+        B = xvar.shape[0]
+        x_term = _f64(x_term, (B, 4))
+        optr, n_obs, keep = self._obs_arg(obs, B)
+        l_x, l_xx = np.empty((B, 4)), np.empty((B, 4, 4))
+        _check(lib().i2lqr_cost_final_batch(self._h, C.c_int64(B), _d(xvar), _d(x_term), optr, C.c_int64(n_obs), _d(l_x), _d(l_xx)))
+        del keep
+        return l_x, l_xx
+
+    def backward_pass(self, xvar, uvar, x_term, lamb=None, obs=None):
+        N = self.N
+        xvar = _f64(xvar).reshape(-1, 4, N + 1)
+        B = xvar.shape[0]
+        uvar, x_term = _f64(uvar, (B, 2, N)), _f64(x_term, (B, 4))
+        lamb = None if lamb is None else _f64(lamb, (B,))
+        optr, n_obs, keep = self._obs_arg(obs, B)
+        k, K = np.empty((B, 2, N)), np.empty((B, 2, 4, N))
+        _check(lib().i2lqr_backward_pass_batch(self._h, C.c_int64(B), _d(xvar), _d(uvar), _d(x_term), _d(lamb), optr, C.c_int64(n_obs), _d(k), _d(K)))
+        del keep
+        return k, K
+
+    def forward_pass(self, xvar, uvar, x_term, k, K):
+        N = self.N
+        xvar = _f64(xvar).reshape(-1, 4, N + 1)
+        B = xvar.shape[0]
+        uvar, x_term, k, K = _f64(uvar, (B, 2, N)), _f64(x_term, (B, 4)), _f64(k, (B, 2, N)), _f64(K, (B, 2, 4, N))
+        xn, un, cost = np.empty((B, 4, N + 1)), np.empty((B, 2, N)), np.empty(B)
+        _check(lib().i2lqr_forward_pass_batch(self._h, C.c_int64(B), _d(xvar), _d(uvar), _d(x_term), _d(k), _d(K), _d(xn), _d(un), _d(cost)))
+        return xn, un, cost
 
     # -- batched closed-loop episodes ------------------------------------------------------------------
     def episodes_begin(self, x_init, goal):

@@ -176,6 +176,39 @@ int i2lqr_episodes_set_noise(i2lqr_handle* h, uint64_t seed);
  * :722-726), 2 playback ran out of inputs (IndexError in the reference), 3 lap too short/long to store. */
 int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status);
 
+/* ---- the functions an iLQR iteration is made of, one by one ---------------------------------------------- */
+/* The solve entry points above run these fused.  They are also exported separately, batched over B independent
+ * problems, for callers that drive their own outer loop and for parity at function granularity; each runs the
+ * same device code the solve kernels inline.  Arrays use the reference's shapes with a leading batch axis and
+ * time on the LAST axis; host pointers; FP64 only.  obs / n_obs as in i2lqr_solve_batch.
+ *
+ * kinetic_bicycle(x, u, dt) (iterative_ilqr/systems/kinetic_bicycle.py:10-27): x (B,4), u (B,2) -> x_next (B,4). */
+int i2lqr_dynamics_batch(i2lqr_handle* h, int64_t B, const double* x, const double* u, double* x_next);
+/* get_A_matrix(velocity_vals, theta, acceleration_vals, num_horizon, dt) and get_B_matrix(theta, num_horizon, dt)
+ * (iterative_ilqr/systems/kinetic_bicycle.py:30-52): v, theta, accel (B,N) -> A (B,4,4,N), Bm (B,4,2,N).  Either
+ * output may be NULL; v and accel are only read for A. */
+int i2lqr_linearize_batch(i2lqr_handle* h, int64_t B, const double* v, const double* theta, const double* accel, double* A,
+                          double* Bm);
+/* get_cost_derivation(ctrl_U, dX, ilqr_param, num_horizon, xvar, obstacle, sys_param)
+ * (iterative_ilqr/control/ilqr_helper.py:9-56, with add_control_constraint :83-103 and repelling_cost_function
+ * :59-64): uvar (B,2,N), dX (B,4,N+1), xvar (B,4,N+1) -> l_u (B,2,N), l_uu (B,2,2,N), l_x (B,4,N), l_xx (B,4,4,N). */
+int i2lqr_cost_derivatives_batch(i2lqr_handle* h, int64_t B, const double* uvar, const double* dX, const double* xvar,
+                                 const i2lqr_obstacle* obs, int64_t n_obs, double* l_u, double* l_uu, double* l_x,
+                                 double* l_xx);
+/* get_cost_final(x, x_terminal, matrix_Qterminal, obstacle, ilqr_param) (iterative_ilqr/control/ilqr_helper.py:106-150):
+ * xvar (B,4,N+1), x_term (B,4) -> l_x (B,4), l_xx (B,4,4); the obstacle is advanced by params.obstacle_horizon. */
+int i2lqr_cost_final_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* x_term, const i2lqr_obstacle* obs,
+                           int64_t n_obs, double* l_x, double* l_xx);
+/* backward_pass(xvar, uvar, x_terminal, dX, lamb, ...) (iterative_ilqr/control/iterative_ilqr.py:88-130):
+ * -> k (B,2,N), K (B,2,4,N).  dX is taken as xvar - params.xtarget, which is what ilqr() maintains (:41-42);
+ * lamb (B) or NULL (= params.lamb). */
+int i2lqr_backward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* uvar, const double* x_term,
+                              const double* lamb, const i2lqr_obstacle* obs, int64_t n_obs, double* k, double* K);
+/* forward_pass(xvar, uvar, x_terminal, ..., matrix_k, matrix_K, sys_param) (iterative_ilqr/control/iterative_ilqr.py:133-160):
+ * -> xvar_new (B,4,N+1), uvar_new (B,2,N), cost_new (B); any output may be NULL. */
+int i2lqr_forward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, const double* uvar, const double* x_term,
+                             const double* k, const double* K, double* xvar_new, double* uvar_new, double* cost_new);
+
 /* ---- instrumentation -------------------------------------------------------------------------------- */
 /* Device time (CUDA events on the stream of the call) of the last compute call, the number of kernels it
  * launched, and the iLQR iterations / solves it executed (device-side counters, for the roofline).  For

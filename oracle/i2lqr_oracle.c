@@ -470,6 +470,50 @@ int orc_calc_input(const i2lqr_params* p, const i2lqr_obstacle* o, int n_laps, c
   return 0;
 }
 
+/* backward_pass / forward_pass in the reference's own array layout (time on the last axis): xvar (4,N+1),
+ * uvar (2,N), dX (4,N+1), k (2,N), K (2,4,N).  control/iterative_ilqr.py:88-160. */
+static void to_time_major(const double* a, int rows, int cols, double* out) { /* (rows, cols) -> (cols, rows) */
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) out[c * rows + r] = a[r * cols + c];
+}
+int orc_backward_pass(const i2lqr_params* p, const i2lqr_obstacle* o, const double* xvar, const double* uvar,
+                      const double* dX, const double* xterm, double lamb, double* k_out, double* K_out) {
+  int N = p->num_horizon;
+  double* mem = (double*)malloc(sizeof(double) * (size_t)(2 * NX * (N + 1) + NU * N + NU * N + NU * NX * N));
+  if (!mem) return 1;
+  double *X = mem, *D = X + NX * (N + 1), *U = D + NX * (N + 1), *gk = U + NU * N, *gK = gk + NU * N;
+  to_time_major(xvar, NX, N + 1, X);
+  to_time_major(dX, NX, N + 1, D);
+  to_time_major(uvar, NU, N, U);
+  backward_pass(p, o, N, X, U, D, xterm, lamb, gk, gK);
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i < NU; ++i) k_out[i * N + k] = gk[k * NU + i];
+    for (int i = 0; i < NU * NX; ++i) K_out[i * N + k] = gK[k * NU * NX + i];
+  }
+  free(mem);
+  return 0;
+}
+int orc_forward_pass(const i2lqr_params* p, const double* xvar, const double* uvar, const double* xterm,
+                     const double* k_in, const double* K_in, double* xvar_new, double* uvar_new, double* cost_new) {
+  int N = p->num_horizon;
+  double* mem = (double*)malloc(sizeof(double) * (size_t)(2 * NX * (N + 1) + 2 * NU * N + NU * N + NU * NX * N));
+  if (!mem) return 1;
+  double *X = mem, *Xn = X + NX * (N + 1), *U = Xn + NX * (N + 1), *Un = U + NU * N, *gk = Un + NU * N, *gK = gk + NU * N;
+  to_time_major(xvar, NX, N + 1, X);
+  to_time_major(uvar, NU, N, U);
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i < NU; ++i) gk[k * NU + i] = k_in[i * N + k];
+    for (int i = 0; i < NU * NX; ++i) gK[k * NU * NX + i] = K_in[i * N + k];
+  }
+  *cost_new = forward_pass(p, N, X, U, xterm, gk, gK, Xn, Un);
+  for (int k = 0; k <= N; ++k)
+    for (int i = 0; i < NX; ++i) xvar_new[i * (N + 1) + k] = Xn[k * NX + i];
+  for (int k = 0; k < N; ++k)
+    for (int i = 0; i < NU; ++i) uvar_new[i * N + k] = Un[k * NU + i];
+  free(mem);
+  return 0;
+}
+
 /* systems/kinetic_bicycle.py:10-27, exported for the plant-step checks */
 void orc_kinetic_bicycle(const double* x, const double* u, double dt, double* xn) { kinetic_bicycle(x, u, dt, xn); }
 

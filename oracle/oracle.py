@@ -83,6 +83,29 @@ def ilqr_batch(params, x0, x_term, lamb_in, obs=None, nthreads=1, uvar_init=None
     return uvar, xvar, lamb_out, iters
 
 
+def backward_pass(params, xvar, uvar, dX, x_term, lamb, obstacle=None):
+    """control/iterative_ilqr.py:88-130 for one problem, reference layout: -> k (2,N), K (2,4,N)."""
+    N = params.num_horizon
+    xvar, uvar, dX = (np.ascontiguousarray(a, dtype=np.float64) for a in (xvar, uvar, dX))
+    x_term = np.ascontiguousarray(x_term, dtype=np.float64)
+    k, K = np.zeros((2, N)), np.zeros((2, 4, N))
+    optr = C.byref(obstacle) if obstacle is not None else None
+    rc = lib().orc_backward_pass(C.byref(params), optr, _d(xvar), _d(uvar), _d(dX), _d(x_term), C.c_double(lamb), _d(k), _d(K))
+    assert rc == 0
+    return k, K
+
+
+def forward_pass(params, xvar, uvar, x_term, k, K):
+    """control/iterative_ilqr.py:133-160 for one problem: -> xvar_new (4,N+1), uvar_new (2,N), cost_new."""
+    N = params.num_horizon
+    xvar, uvar, k, K = (np.ascontiguousarray(a, dtype=np.float64) for a in (xvar, uvar, k, K))
+    x_term = np.ascontiguousarray(x_term, dtype=np.float64)
+    xn, un, cost = np.zeros((4, N + 1)), np.zeros((2, N)), C.c_double()
+    rc = lib().orc_forward_pass(C.byref(params), _d(xvar), _d(uvar), _d(x_term), _d(k), _d(K), _d(xn), _d(un), C.byref(cost))
+    assert rc == 0
+    return xn, un, cost.value
+
+
 def select_knn(lap, x0, K):
     lap = np.ascontiguousarray(lap, dtype=np.float64)
     x0 = np.ascontiguousarray(x0, dtype=np.float64)

@@ -331,6 +331,60 @@ def make_step_synth():
     print("step_synth done")
 
 
+def make_components():
+    """The functions an iLQR iteration is made of, called one by one on mid-solve trajectories
+    (iterative_ilqr/systems/kinetic_bicycle.py:10-52, control/ilqr_helper.py:9-150, control/iterative_ilqr.py:88-160)."""
+    ref = Reference(stable_argsort=False)
+    base, mod = ref.base, ref.ilqr_mod
+    import control.ilqr_helper as helper  # the reference's module (on sys.path through Reference)
+    import systems.kinetic_bicycle as sysmod
+
+    sysp = base.KineticBicycleParam()
+    out = {}
+    groups = [("n6", 6, 64, None, None), ("n6_qr", 6, 48, np.diag([0.1, 0.1, 0.05, 0.01]) + 0.01, np.array([[0.05, 0.01], [0.01, 0.08]])),
+              ("n25", 25, 16, None, None)]  # fmt: skip
+    for name, N, B, Q, R in groups:
+        data = synth.flat_candidates(B, num_horizon=N, seed=synth.SEED + 900 + N + (0 if Q is None else 1))
+        rng = np.random.default_rng(synth.SEED + 77 + N)
+        param = _param(ref, N, Q=Q, R=R)
+        lamb = rng.choice(np.array([1e-2, 1.0, 100.0]), size=B)
+        xvar, uvar = np.zeros((B, 4, N + 1)), np.zeros((B, 2, N))
+        A, Bm = np.zeros((B, 4, 4, N)), np.zeros((B, 4, 2, N))
+        l_u, l_uu, l_x, l_xx = np.zeros((B, 2, N)), np.zeros((B, 2, 2, N)), np.zeros((B, 4, N)), np.zeros((B, 4, 4, N))
+        Vx, Vxx = np.zeros((B, 4)), np.zeros((B, 4, 4))
+        gk, gK = np.zeros((B, 2, N)), np.zeros((B, 2, 4, N))
+        xn, un, cn = np.zeros((B, 4, N + 1)), np.zeros((B, 2, N)), np.zeros(B)
+        for b in range(B):
+            # a trajectory as ilqr() holds it mid-solve: clipped inputs, states rolled out with the model
+            u = rng.standard_normal((2, N)) * np.array([[0.8], [0.25]])
+            u[0] = np.clip(u[0], -sysp.a_max, sysp.a_max)
+            u[1] = np.clip(u[1], -round(sysp.delta_max, 2), round(sysp.delta_max, 2))
+            x = np.zeros((4, N + 1))
+            x[:, 0] = data["x0"][b]
+            for k in range(N):
+                x[:, k + 1] = sysmod.kinetic_bicycle(x[:, k], u[:, k], 1)
+            xvar[b], uvar[b] = x, u
+            dX = x - np.zeros((4, 1))
+            obstacle = ref.make_obstacle(data["obs"][b], data["mode"][b]) if b % 5 else None
+            xt = np.array(data["x_term"][b])
+            A[b] = sysmod.get_A_matrix(x[2, 1:], x[3, 1:], u[0, :], N, 1)
+            Bm[b] = sysmod.get_B_matrix(x[3, 1:], N, 1)
+            l_u[b], l_uu[b], l_x[b], l_xx[b] = helper.get_cost_derivation(u, dX, param, N, x, obstacle, sysp)
+            Vx[b], Vxx[b] = helper.get_cost_final(x, xt, param.matrix_Qterminal, obstacle, param)
+            gk[b], gK[b] = mod._pristine[0](x, u, xt, dX, float(lamb[b]), N, 1, param, obstacle, sysp)
+            xn[b], un[b], cn[b] = mod.forward_pass(x, u, xt, param, 1, N, gk[b], gK[b], sysp)
+        has_obs = np.array([1 if b % 5 else 0 for b in range(B)], dtype=np.int32)
+        g = name + "/"
+        for k, v in dict(N=np.int32(N), x_term=data["x_term"], obs=data["obs"], mode=data["mode"], has_obs=has_obs, lamb=lamb,
+                         Q=np.zeros((4, 4)) if Q is None else Q, R=np.zeros((2, 2)) if R is None else R, xvar=xvar, uvar=uvar, A=A, B=Bm,
+                         l_u=l_u, l_uu=l_uu, l_x=l_x, l_xx=l_xx, Vx=Vx, Vxx=Vxx, k=gk, K=gK, xvar_new=xn, uvar_new=un, cost_new=cn).items():  # fmt: skip
+            out[g + k] = v
+    out["groups"] = np.array([g[0] for g in groups])
+    np.savez_compressed(os.path.join(HERE, "components.npz"), **out)
+    ref.close()
+    print("components done")
+
+
 TARGETS = {
     "flat": make_flat,
     "knn": make_knn,
@@ -341,6 +395,7 @@ TARGETS = {
     "steps_k64": make_steps_k64,
     "steps_static_big": make_steps_static_big,
     "step_synth": make_step_synth,
+    "components": make_components,
 }
 
 if __name__ == "__main__":

@@ -8,6 +8,7 @@ the reference uses NumPy SIMD transcendentals and LAPACK dgeev).
 import numpy as np
 import pytest
 
+from ilqr_iterative_tasks_b200 import _abi
 from oracle import oracle
 from tests import helpers as H
 
@@ -109,3 +110,28 @@ def test_relax_cost_ladder():
     assert oracle.relax_cost(p, np.array([3.0, 4.0, 0, 0]), xt, 10, 1) == 10 + 6 + 100  # r=5 <= 8
     assert oracle.relax_cost(p, np.array([3.0, 4.0, 0, 0]), xt, 10, 2) == 10 + 6 + 700  # 5 <= 0.8*i -> i=7
     assert oracle.relax_cost(p, np.array([300.0, 400.0, 0, 0]), xt, 10, 1) == np.inf  # 500 > 440
+
+
+def _component_case(g, grp, b):
+    N = int(g[grp + "/N"])
+    p = _abi.default_params(num_horizon=N, matrix_Q=g[grp + "/Q"], matrix_R=g[grp + "/R"])
+    obs = _abi.Obstacle(*[float(v) for v in g[grp + "/obs"][b]], int(g[grp + "/mode"][b]), 1) if g[grp + "/has_obs"][b] else None
+    return p, obs
+
+
+@pytest.mark.parametrize("grp", ["n6", "n6_qr", "n25"])
+def test_backward_forward_pass_match_reference(grp):
+    """`backward_pass` / `forward_pass` (iterative_ilqr/control/iterative_ilqr.py:88-160) called on their own, on
+    mid-solve trajectories: gains, trial trajectory and trial cost against the reference's outputs."""
+    g = H.load("components.npz")
+    B = g[grp + "/xvar"].shape[0]
+    for b in range(B):
+        p, obs = _component_case(g, grp, b)
+        x, u, xt = g[grp + "/xvar"][b], g[grp + "/uvar"][b], g[grp + "/x_term"][b]
+        k, K = oracle.backward_pass(p, x, u, x.copy(), xt, float(g[grp + "/lamb"][b]), obs)
+        assert H.rel_err(k[None], g[grp + "/k"][b][None])[0] <= 1e-10, (grp, b)
+        assert H.rel_err(K[None], g[grp + "/K"][b][None])[0] <= 1e-10, (grp, b)
+        xn, un, c = oracle.forward_pass(p, x, u, xt, g[grp + "/k"][b], g[grp + "/K"][b])
+        assert H.rel_err(xn[None], g[grp + "/xvar_new"][b][None])[0] <= 1e-12, (grp, b)
+        assert H.rel_err(un[None], g[grp + "/uvar_new"][b][None])[0] <= 1e-12, (grp, b)
+        assert abs(c - g[grp + "/cost_new"][b]) <= 1e-12 * max(1.0, abs(g[grp + "/cost_new"][b])), (grp, b)

@@ -202,13 +202,10 @@ class KineticBicycle:
         self.set_state(np.zeros((X_DIM,)))
 
     def save(self, path):
-        """Pickle in the reference's `.obj` convention (result/ilqr_test_no_obstacle.py:61-62)."""
-        policy, self.ctrl_policy = self.ctrl_policy, None  # the GPU handle is not picklable
-        try:
-            with open(path, "wb") as handle:
-                pkl.dump(self, handle, protocol=pkl.HIGHEST_PROTOCOL)
-        finally:
-            self.ctrl_policy = policy
+        """Pickle in the reference's `.obj` convention (result/ilqr_test_no_obstacle.py:61-62); the controller
+        travels along (its GPU handle is dropped and rebuilt on first use, see iLqr.__getstate__)."""
+        with open(path, "wb") as handle:
+            pkl.dump(self, handle, protocol=pkl.HIGHEST_PROTOCOL)
 
 
 class ControlBase:
@@ -325,6 +322,16 @@ class iLqr(ControlBase):
             self._engine.set_params(params)
         self._engine_key = key
         return self._engine
+
+    # ---- pickling (result/ilqr_test_*.py end with `pkl.dump(ego, ...)`, and ego holds its controller) -----------
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engine"] = None  # the GPU handle stays behind; it is rebuilt from self.ss on the next call
+        state["_engine_key"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
 
     # ---- reference API ---------------------------------------------------------------------------
     def select_close_ss(self, iter, x0):

@@ -57,6 +57,16 @@ u, x, lamb = ilqr(p2, 6, np.zeros(4), 1, ob, base.KineticBicycleParam(), gf["n6_
                   gf["n6_warm/uvar_init"][b].copy(), xv, float(gf["n6_warm/lamb_in"][b]))
 res["l1_err"] = float(np.abs(x - gf["n6_warm/xvar"][b]).max())
 res["l1_lamb_ok"] = bool(lamb == float(gf["n6_warm/lamb_out"][b]))
+# the reference's result scripts end with pkl.dump(ego, ...) (result/ilqr_test_no_obstacle.py:61-62): the plant holds
+# its controller, so both must pickle; the copy rebuilds its GPU handle from the stored laps and solves identically
+import pickle
+clone = pickle.loads(pickle.dumps(ego, protocol=pickle.HIGHEST_PROTOCOL))
+x_probe = np.array(ego.data["state"][-1][2])
+outs = []
+for c in (ctrl, clone.ctrl_policy):
+    c.set_state(x_probe); c.calc_input(); outs.append((np.array(c.u), np.array(c.x_pred)))
+res["pickle_ok"] = bool(np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+                        and len(clone.data["state"]) == len(ego.data["state"]))
 print("RESULT" + json.dumps(res))
 """
 
@@ -73,6 +83,7 @@ def test_dropin_closed_loop_stock_scenario():
     assert res["lens"] == res["ref_lens"], res
     assert res["max_abs_err"] < 1e-6, res
     assert res["knn_ok"] and res["l1_lamb_ok"] and res["l1_err"] < 1e-9 * 50, res
+    assert res["pickle_ok"], res
 
 
 @pytest.mark.parametrize("name", ["stock", "moving_up"])

@@ -361,7 +361,8 @@ int sync_obstacles(i2lqr_handle* h) {
 }
 
 int knn_smem_config(i2lqr_handle* h, int* warps, size_t* smem) {
-  const size_t per_warp = (size_t)h->Tcap * sizeof(double);
+  // Tcap distances + Tcap ints (index array of the tie path), kept 8-byte aligned per warp
+  const size_t per_warp = ((size_t)h->Tcap + ((size_t)h->Tcap + 1) / 2) * sizeof(double);
   int w = (int)std::min<size_t>(4, (200 * 1024) / per_warp);
   if (w < 1) return fail("lap_capacity %d too large for the K-nearest kernel", h->Tcap);
   *warps = w;

@@ -629,9 +629,114 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------ K1
 // One warp per (episode, active lap).  The lap's SoA rows are read coalesced, the 1-norm distances
-// ((|dx|+|dy|)+|dv|)+|dtheta| (same association as scipy's norm, bit-exact) are staged in
-// shared memory, and K rounds of a warp-shuffle arg-min on the key (distance, index) emit the indices in
-// rank order -- the order is semantically significant (lambda-chain order, winner rule).
+// ((|dx|+|dy|)+|dv|)+|dtheta| (same association as scipy's norm, bit-exact) are staged in shared
+// memory, and K (+1) rounds of a warp-shuffle arg-min on the key (distance, index) emit the indices in rank
+// order -- the order is semantically significant (lambda-chain order, winner rule).
+//
+// Ties.  The reference sorts with numpy.argsort's default kind (utils/base.py:339), an introsort that leaves EQUAL
+// distances in an order which is a deterministic function of the whole array -- and the stock initial lap ends in
+// three identical rows, so ties do reach the selection.  When no two of the K+1 smallest distances are equal the
+// first K of any sort agree and the shuffle rounds are the answer; when a tie touches them, lane 0 replays NumPy's
+// scalar algorithm (np_argsort_device: median-of-3 quicksort above 16 elements, insertion sort below, heapsort past
+// the depth budget -- the published npysort `aquicksort`, checked against NumPy itself through the oracle's copy) on
+// the staged distances, so the emitted indices are NumPy's in that case too.  A rare, sequential path: ~T log T
+// shared-memory operations by one lane.
+__device__ __forceinline__ bool np_less(double a, double b) { return a < b || (b != b && a == a); }
+
+__device__ __noinline__ void np_aheapsort_device(const double* v, int* tosort, int n) {
+  int* a = tosort - 1;  // 1-based
+  int i, j, l, tmp;
+  for (l = n >> 1; l > 0; --l) {
+    tmp = a[l];
+    for (i = l, j = l << 1; j <= n;) {
+      if (j < n && np_less(v[a[j]], v[a[j + 1]])) j += 1;
+      if (np_less(v[tmp], v[a[j]])) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else {
+        break;
+      }
+    }
+    a[i] = tmp;
+  }
+  for (; n > 1;) {
+    tmp = a[n];
+    a[n] = a[1];
+    n -= 1;
+    for (i = 1, j = 2; j <= n;) {
+      if (j < n && np_less(v[a[j]], v[a[j + 1]])) j++;
+      if (np_less(v[tmp], v[a[j]])) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else {
+        break;
+      }
+    }
+    a[i] = tmp;
+  }
+}
+
+__device__ __noinline__ void np_argsort_device(const double* v, int num, int* t) {
+  for (int j = 0; j < num; ++j) t[j] = j;
+  if (num < 2) return;
+  constexpr int kSmall = 15;  // ranges of up to 16 elements go to the insertion sort
+  int stack[64], depth[32];
+  int sp = 0, dp = 0, cdepth = 0;
+  for (int n = num; n > 1; n >>= 1) cdepth += 2;  // 2 * floor(log2 num)
+  int pl = 0, pr = num - 1;
+  for (;;) {
+    if (cdepth < 0) {
+      np_aheapsort_device(v, t + pl, pr - pl + 1);
+    } else {
+      while (pr - pl > kSmall) {
+        const int pm = pl + ((pr - pl) >> 1);
+        int tmp;
+        if (np_less(v[t[pm]], v[t[pl]])) { tmp = t[pm]; t[pm] = t[pl]; t[pl] = tmp; }
+        if (np_less(v[t[pr]], v[t[pm]])) { tmp = t[pr]; t[pr] = t[pm]; t[pm] = tmp; }
+        if (np_less(v[t[pm]], v[t[pl]])) { tmp = t[pm]; t[pm] = t[pl]; t[pl] = tmp; }
+        const double vp = v[t[pm]];
+        int pi = pl, pj = pr - 1;
+        tmp = t[pm]; t[pm] = t[pj]; t[pj] = tmp;
+        for (;;) {
+          do ++pi;
+          while (np_less(v[t[pi]], vp));
+          do --pj;
+          while (np_less(vp, v[t[pj]]));
+          if (pi >= pj) break;
+          tmp = t[pi]; t[pi] = t[pj]; t[pj] = tmp;
+        }
+        tmp = t[pi]; t[pi] = t[pr - 1]; t[pr - 1] = tmp;
+        if (pi - pl < pr - pi) {  // larger part on the stack
+          stack[sp++] = pi + 1;
+          stack[sp++] = pr;
+          pr = pi - 1;
+        } else {
+          stack[sp++] = pl;
+          stack[sp++] = pi - 1;
+          pl = pi + 1;
+        }
+        depth[dp++] = --cdepth;
+      }
+      for (int pi = pl + 1; pi <= pr; ++pi) {
+        const int vi = t[pi];
+        const double vp = v[vi];
+        int pj = pi;
+        while (pj > pl && np_less(vp, v[t[pj - 1]])) {
+          t[pj] = t[pj - 1];
+          --pj;
+        }
+        t[pj] = vi;
+      }
+    }
+    if (sp == 0) break;
+    pr = stack[--sp];
+    pl = stack[--sp];
+    cdepth = depth[--dp];
+  }
+}
+
 struct KnnArgs {
   SafeSet set;
   int K, it, n_episodes;
@@ -652,7 +757,9 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
   extern __shared__ double dist_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  double* dist = dist_smem + (size_t)wib * a.set.Tcap;
+  // per warp: Tcap distances, then Tcap ints for the tie path's index array
+  double* dist = dist_smem + (size_t)wib * (a.set.Tcap + (a.set.Tcap + 1) / 2);
+  int* order = reinterpret_cast<int*>(dist + a.set.Tcap);
   const long long wid = (long long)blockIdx.x * warps_per_block + wib;
   int e, lrel, slot;
   double g[4];
@@ -693,7 +800,9 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
   const int n = a.K < T ? a.K : T;
   double dprev = -INFINITY;
   int jprev = -1;
-  for (int r = 0; r < n; ++r) {
+  bool tie = false;
+  const int rounds = n < T ? n + 1 : n;  // one more than emitted: does the K-th distance tie with the next?
+  for (int r = 0; r < rounds; ++r) {
     double dbest = INFINITY;
     int jbest = 0x7fffffff;
     for (int j = lane; j < T; j += 32) {
@@ -712,9 +821,17 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
         jbest = j2;
       }
     }
-    if (lane == 0) out[r] = jbest;
+    tie = tie || (r > 0 && dbest == dprev);
+    if (lane == 0 && r < n) out[r] = jbest;
     dprev = dbest;
     jprev = jbest;
+  }
+  if (tie) {  // warp-uniform: every lane holds the same (dbest, dprev) after the butterfly
+    if (lane == 0) {
+      np_argsort_device(dist, T, order);
+      for (int r = 0; r < n; ++r) out[r] = order[r];
+    }
+    __syncwarp();
   }
   if (lane == 0) {
     *out_cnt = n;

@@ -16,9 +16,11 @@ What runs where
   * LMPC / NLMPC (reference :482-690, control/nonlinear_lmpc.py) are out of scope and raise
     NotImplementedError.
 
-Observable differences: the inner-loop prints ("k neighbors", "Convergence achieved") are dropped; K-nearest
-ties resolve in ascending (distance, index) order (the reference's default argsort is not reproducible on
-ties).
+Observable differences: the inner-loop prints ("k neighbors", "Convergence achieved") are dropped.  K-nearest
+ties (the stock initial lap ends in identical rows) come out in the order numpy.argsort's scalar introsort leaves
+them -- what the reference's pinned numpy==1.19.5 does; a NumPy >= 1.25 on an AVX2 / AVX-512 host sorts float64
+with x86-simd-sort and orders ties differently (run the reference with NPY_DISABLE_CPU_FEATURES="AVX512F
+AVX512_SKX AVX2" to compare like with like).
 """
 import datetime
 import os

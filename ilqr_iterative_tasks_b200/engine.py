@@ -13,7 +13,7 @@ from . import _abi
 from ._abi import OUTER_ITERS, Obstacle, Params  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libi2lqr.so")
+LIB_PATH = os.environ.get("I2LQR_LIB") or os.path.join(_HERE, "libi2lqr.so")  # I2LQR_LIB: A/B builds of the same library
 _lib = None
 
 _dp = C.POINTER(C.c_double)

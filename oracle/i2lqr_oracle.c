@@ -339,25 +339,115 @@ int orc_ilqr_batch(const i2lqr_params* p, int64_t B, const double* x0, const dou
   return atomic_load(&job.bad);
 }
 
-/* utils/base.py:332-341 under the (distance, index) tie policy: lap (T,4) row-major. */
+/* numpy.argsort(d) with the default kind, as the reference calls it (utils/base.py:339).  The arithmetic lives in an
+ * un-vendored dependency (requirements.txt pins numpy==1.19.5): its scalar `aquicksort` is an introsort -- median-of-3
+ * partition while a range holds more than 16 elements, insertion sort below, heapsort once the depth budget
+ * 2*floor(log2 n) is spent.  The order it leaves EQUAL keys in is a deterministic function of the input and matters
+ * here (the initial lap ends in duplicated rows).  Restated from the published algorithm and checked
+ * against NumPy 2.3.5 executed with its SIMD dispatch switched off (tests/golden/make_golden.py: knn.npz, every
+ * steps_*.npz); NumPy >= 1.25 on AVX2 / AVX-512 hosts dispatches float64 argsort to x86-simd-sort, whose tie order is
+ * hardware-specific and is not what the pinned version does. */
+static int dless(double a, double b) { return a < b || (b != b && a == a); }
+static void np_aheapsort(const double* v, int64_t* tosort, int64_t n) {
+  int64_t* a = tosort - 1; /* 1-based */
+  int64_t i, j, l, tmp;
+  for (l = n >> 1; l > 0; --l) {
+    tmp = a[l];
+    for (i = l, j = l << 1; j <= n;) {
+      if (j < n && dless(v[a[j]], v[a[j + 1]])) j += 1;
+      if (dless(v[tmp], v[a[j]])) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else
+        break;
+    }
+    a[i] = tmp;
+  }
+  for (; n > 1;) {
+    tmp = a[n];
+    a[n] = a[1];
+    n -= 1;
+    for (i = 1, j = 2; j <= n;) {
+      if (j < n && dless(v[a[j]], v[a[j + 1]])) j++;
+      if (dless(v[tmp], v[a[j]])) {
+        a[i] = a[j];
+        i = j;
+        j += j;
+      } else
+        break;
+    }
+    a[i] = tmp;
+  }
+}
+#define NP_SMALL_QUICKSORT 15 /* ranges of up to 16 elements go to the insertion sort */
+void orc_np_argsort(const double* v, int64_t num, int64_t* tosort) {
+  for (int64_t j = 0; j < num; ++j) tosort[j] = j;
+  if (num < 2) return;
+  int64_t *pl = tosort, *pr = tosort + num - 1, *stack[128], **sptr = stack, *pm, *pi, *pj, *pk, vi, tmp;
+  int depth[128], *psdepth = depth, cdepth = 0;
+  for (int64_t n = num; n > 1; n >>= 1) cdepth += 2; /* 2 * msb(num) */
+  double vp;
+#define ISWAP(a, b) (tmp = (a), (a) = (b), (b) = tmp)
+  for (;;) {
+    if (cdepth < 0) {
+      np_aheapsort(v, pl, pr - pl + 1);
+    } else {
+      while (pr - pl > NP_SMALL_QUICKSORT) {
+        pm = pl + ((pr - pl) >> 1);
+        if (dless(v[*pm], v[*pl])) ISWAP(*pm, *pl);
+        if (dless(v[*pr], v[*pm])) ISWAP(*pr, *pm);
+        if (dless(v[*pm], v[*pl])) ISWAP(*pm, *pl);
+        vp = v[*pm];
+        pi = pl;
+        pj = pr - 1;
+        ISWAP(*pm, *pj);
+        for (;;) {
+          do ++pi;
+          while (dless(v[*pi], vp));
+          do --pj;
+          while (dless(vp, v[*pj]));
+          if (pi >= pj) break;
+          ISWAP(*pi, *pj);
+        }
+        pk = pr - 1;
+        ISWAP(*pi, *pk);
+        if (pi - pl < pr - pi) { /* larger part on the stack */
+          *sptr++ = pi + 1;
+          *sptr++ = pr;
+          pr = pi - 1;
+        } else {
+          *sptr++ = pl;
+          *sptr++ = pi - 1;
+          pl = pi + 1;
+        }
+        *psdepth++ = --cdepth;
+      }
+      for (pi = pl + 1; pi <= pr; ++pi) {
+        vi = *pi;
+        vp = v[vi];
+        pj = pi;
+        pk = pi - 1;
+        while (pj > pl && dless(vp, v[*pk])) *pj-- = *pk--;
+        *pj = vi;
+      }
+    }
+    if (sptr == stack) break;
+    pr = *(--sptr);
+    pl = *(--sptr);
+    cdepth = *(--psdepth);
+  }
+#undef ISWAP
+}
+
+/* iLqr.select_close_ss (utils/base.py:332-341): 1-norm distances, numpy.argsort, first K. */
 int orc_select_knn(const double* lap, int T, const double* x0, int K, int64_t* idx_out) {
   double* d = (double*)malloc(sizeof(double) * (size_t)T);
   int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)T);
-  for (int j = 0; j < T; ++j) {
+  for (int j = 0; j < T; ++j)
     d[j] = ((fabs(lap[j * NX + 0] - x0[0]) + fabs(lap[j * NX + 1] - x0[1])) + fabs(lap[j * NX + 2] - x0[2])) +
            fabs(lap[j * NX + 3] - x0[3]);
-    order[j] = j;
-  }
-  /* stable insertion sort on d */
-  for (int j = 1; j < T; ++j) {
-    int64_t o = order[j];
-    int i = j - 1;
-    while (i >= 0 && d[order[i]] > d[o]) {
-      order[i + 1] = order[i];
-      --i;
-    }
-    order[i + 1] = o;
-  }
+  orc_np_argsort(d, T, order);
   int n = K < T ? K : T;
   for (int j = 0; j < n; ++j) idx_out[j] = order[j];
   free(d);

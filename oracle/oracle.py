@@ -106,6 +106,14 @@ def forward_pass(params, xvar, uvar, x_term, k, K):
     return xn, un, cost.value
 
 
+def np_argsort(v):
+    """numpy.argsort(v) as the scalar introsort of NumPy does it (tie order included)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.empty(v.shape[0], dtype=np.int64)
+    lib().orc_np_argsort(_d(v), C.c_int64(v.shape[0]), out.ctypes.data_as(_lp))
+    return out
+
+
 def select_knn(lap, x0, K):
     lap = np.ascontiguousarray(lap, dtype=np.float64)
     x0 = np.ascontiguousarray(x0, dtype=np.float64)

@@ -9,16 +9,27 @@ The reference's own tests hold no assertions and no golden vectors for this path
 the fixtures below are the pin: outputs of the reference itself, executed here on NumPy 2.3 / SciPy 1.18,
 committed as small .npz files together with this script.
 
-Tie policy: closed-loop traces are recorded with `np.argsort(kind="stable")` patched into
-utils.base from outside (refharness._StableNumpy) because the default argsort's tie order is not
-reproducible across NumPy builds; `knn.npz` holds both tie-free cases from the unpatched reference and the
-tie cases under the stable patch.
+Tie policy: `np.argsort` with the default kind (iterative_ilqr/utils/base.py:339) leaves equal
+distances in an order that depends on which sort NumPy runs.  The reference pins numpy==1.19.5, whose float64
+argsort is the scalar introsort; NumPy >= 1.25 dispatches to x86-simd-sort on AVX2 / AVX-512 hosts, with a
+hardware-specific tie order.  Every fixture is therefore minted from the UNPATCHED reference with NumPy's SIMD
+dispatch switched off through NumPy's own environment switch (this script re-executes itself with
+NPY_DISABLE_CPU_FEATURES set), i.e. with the sort the pinned version uses.  No monkeypatching of argsort.
 """
 import os
 import subprocess
 import sys
 
-import numpy as np
+SCALAR_SORT = "AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX512_KNL AVX512_KNM AVX2"
+if os.environ.get("NPY_DISABLE_CPU_FEATURES") is None:  # must be in the environment before numpy is imported
+    os.environ["NPY_DISABLE_CPU_FEATURES"] = SCALAR_SORT
+    os.execv(sys.executable, [sys.executable] + sys.argv)
+
+import warnings
+
+warnings.filterwarnings("ignore", message=".*NPY_DISABLE_CPU_FEATURES.*")
+
+import numpy as np  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
@@ -112,8 +123,8 @@ def make_knn():
             case += 1
     ref.close()
     out["n_unpatched"] = np.int32(case)
-    # tie cases under the stable policy: the stock first lap ends with 3 identical rows
-    ref = Reference(stable_argsort=True)
+    # tie cases: the stock first lap ends with 3 identical rows (flag name kept: 1 = ties reach the selection)
+    ref = Reference(stable_argsort=False)
     base = ref.base
     xcl, _ = synth.initial_lap()
     for K, x0 in ((8, xcl[117] + 0.01), (8, xcl[-1].copy()), (64, xcl[100] - 0.2), (8, xcl[115] + np.array([0.3, 0, 0.1, 0]))):
@@ -162,7 +173,7 @@ def record_closed_loop(name, K, L, laps, obstacle_plan, append_goal_row=False, N
     obstacle_plan(lap_index, base) -> Obstacle or None, evaluated before each lap
     (as iterative_ilqr/result/ilqr_test_add_moving_obstacle.py:63-75 does).
     """
-    ref = Reference(stable_argsort=True)
+    ref = Reference(stable_argsort=False)
     base = ref.base
     dt = 1
     with ref.quiet():
@@ -300,6 +311,27 @@ def make_steps_static_big():
     record_closed_loop("static_big", 8, 2, 2, lambda lap, base: base.Obstacle(100, -5, 20, 40))
 
 
+def make_steps_add_static():
+    # result/ilqr_test_add_static_obstacle.py:49-58: a static obstacle appears on lap 5 of a run that has converged without one
+    record_closed_loop("add_static", 8, 2, 7, lambda lap, base: base.Obstacle(35, 0, 30, 30) if lap == 5 else None)
+
+
+def make_steps_add_up():
+    # result/ilqr_test_add_moving_obstacle.py:17-23,63-75 (--moving-option up)
+    def plan(lap, base):
+        return base.Obstacle(35, -16, 34, 34, spd=1, timestep=1, moving_option=1) if lap == 5 else None
+
+    record_closed_loop("add_up", 8, 2, 7, plan)
+
+
+def make_steps_add_left():
+    # result/ilqr_test_add_moving_obstacle.py:24-30,63-75 (--moving-option left)
+    def plan(lap, base):
+        return base.Obstacle(50, -1, 35, 35, spd=0.2, timestep=1, moving_option=2) if lap == 5 else None
+
+    record_closed_loop("add_left", 8, 2, 7, plan)
+
+
 def make_step_synth():
     """Config 4b: one full `calc_input` on a synthetic one-lap safe set for several horizons."""
     out = {}
@@ -394,11 +426,17 @@ TARGETS = {
     "steps_pytest": make_steps_pytest,
     "steps_k64": make_steps_k64,
     "steps_static_big": make_steps_static_big,
+    "steps_add_static": make_steps_add_static,
+    "steps_add_up": make_steps_add_up,
+    "steps_add_left": make_steps_add_left,
     "step_synth": make_step_synth,
     "components": make_components,
 }
 
 if __name__ == "__main__":
+    _probe = np.array([1, 1, 2, 2, 0, 0, 2, 2, 0, 0, 2, 1, 0, 2, 0, 1, 1], dtype=np.float64)
+    if list(np.argsort(_probe)) != [8, 14, 12, 4, 5, 9, 11, 15, 0, 1, 16, 6, 10, 3, 2, 13, 7]:
+        sys.exit("numpy.argsort is not running the scalar introsort (NPY_DISABLE_CPU_FEATURES not honoured?)")
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "all":
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")

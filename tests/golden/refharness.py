@@ -12,8 +12,8 @@ Instrumentation is harness-side monkeypatching only:
   * iteration counting: wrap `backward_pass` in control.iterative_ilqr (called once per iLQR iteration,
     iterative_ilqr/control/iterative_ilqr.py:50);
   * per-candidate trace: wrap the `ilqr` name that utils.base calls (iterative_ilqr/utils/base.py:414);
-  * tie policy: optionally give utils.base a numpy proxy whose argsort is kind="stable"
-    (iterative_ilqr/utils/base.py:339 uses the default, unstable kind).
+  * (unused since the goldens are minted with NumPy's scalar sort, see make_golden.py) optionally give utils.base
+    a numpy proxy whose argsort is kind="stable" (iterative_ilqr/utils/base.py:339 uses the default kind).
 """
 import contextlib
 import io

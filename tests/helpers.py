@@ -7,7 +7,7 @@ from ilqr_iterative_tasks_b200 import _abi
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FLAT_GROUPS = ["n6", "n6_lamb", "n6_noobs", "n6_qr", "n6_warm", "n2", "n10", "n25", "n50", "n100", "n200"]
-STEP_SCENARIOS = ["stock", "moving_up", "moving_left", "pytest", "static_big", "k64"]
+STEP_SCENARIOS = ["stock", "moving_up", "moving_left", "pytest", "static_big", "k64", "add_static", "add_up", "add_left"]
 # FP64 parity bar of BASELINE.json north_star: states / inputs / costs within 1e-9 relative
 RTOL = 1e-9
 

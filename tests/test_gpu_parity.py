@@ -118,6 +118,33 @@ def test_knn_vs_reference_golden(eng_mod):
         e.close()
 
 
+def test_knn_tie_order_is_numpys(eng_mod):
+    """Laps full of exactly equal distances (points on an integer grid, duplicated rows): the K-nearest kernel must
+    emit NumPy's scalar-introsort order, which the oracle restates and is itself checked against NumPy
+    (tests/test_oracle.py::test_argsort_restatement_is_numpys_scalar_introsort)."""
+    from ilqr_iterative_tasks_b200 import _abi
+    from oracle import oracle
+
+    rng = np.random.default_rng(11)
+    for case in range(40):
+        T = int(rng.choice([5, 16, 17, 18, 33, 64, 121, 257, 500]))
+        K = int(rng.choice([8, 64]))
+        if case % 3 == 0:
+            lap = rng.integers(0, 4, (T, 4)).astype(np.float64)
+        elif case % 3 == 1:
+            lap = np.cumsum(rng.standard_normal((T, 4)), axis=0)
+            lap[-int(rng.integers(2, 6)) :] = lap[-1]  # duplicated final rows, like the stock initial lap
+        else:
+            lap = np.repeat(rng.standard_normal((max(1, T // 4), 4)), 4, axis=0)[:T]
+            T = lap.shape[0]
+        x0 = lap[int(rng.integers(0, T))] + (0.0 if case % 2 else 0.5)
+        p = _abi.default_params(num_horizon=2, num_ss_points=K)
+        e = eng_mod.Engine(p, n_episodes=1, lap_capacity=max(8, T))
+        e.add_lap(0, lap)
+        assert np.array_equal(e.select_knn(0, 0, x0, K), oracle.select_knn(lap, x0, K)), (case, T, K)
+        e.close()
+
+
 @pytest.mark.parametrize("name", H.STEP_SCENARIOS)
 def test_controller_step_vs_reference_golden(eng_mod, name):
     """Every recorded `calc_input` of a closed-loop reference run, replayed from its recorded inputs."""

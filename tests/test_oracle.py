@@ -5,6 +5,8 @@ Discrete results (selected indices, iteration counts, the lambda chain, winner, 
 be exact; states and inputs within 1e-9 relative (the oracle uses libm and a Jacobi 2x2 eigen form where
 the reference uses NumPy SIMD transcendentals and LAPACK dgeev).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -43,9 +45,54 @@ def test_knn_matches_reference():
         assert np.array_equal(idx, g["c%d/idx" % c]), "case %d" % c
 
 
+_ARGSORT = r"""
+import sys, numpy as np
+sys.path.insert(0, r"{root}")
+from oracle import oracle
+probe = np.array([1, 1, 2, 2, 0, 0, 2, 2, 0, 0, 2, 1, 0, 2, 0, 1, 1], dtype=np.float64)
+if list(np.argsort(probe)) != [8, 14, 12, 4, 5, 9, 11, 15, 0, 1, 16, 6, 10, 3, 2, 13, 7]:
+    print("SKIP"); sys.exit(0)
+rng = np.random.default_rng(7)
+for trial in range(3000):
+    T = int(rng.integers(1, 600)); mode = trial % 5
+    if mode == 0: v = rng.standard_normal(T)
+    elif mode == 1: v = rng.integers(0, max(2, T // 8), T).astype(float)
+    elif mode == 2:
+        v = rng.standard_normal(T); k = int(rng.integers(1, 6)); v[-k:] = v[-k - 1] if T > k else v[-1]
+    elif mode == 3: v = np.sort(rng.integers(0, 5, T)).astype(float)[::-1].copy()
+    else:
+        v = np.full(T, 1.5); v[rng.integers(0, T, 3)] = 0.5
+    assert np.array_equal(np.argsort(v), oracle.np_argsort(v)), (trial, T, mode)
+k = 2048  # median-of-3 killer: drives the introsort into its heapsort fallback
+a = np.zeros(2 * k + 1)
+for i in range(1, k + 1):
+    if i % 2 == 1:
+        a[i], a[i + 1] = i, k + i
+    a[k + i] = 2 * i
+for v in (a[1:], np.floor(a[1:] / 7)):
+    assert np.array_equal(np.argsort(v), oracle.np_argsort(v))
+print("OK")
+"""
+
+
+def test_argsort_restatement_is_numpys_scalar_introsort():
+    """The oracle's argsort against numpy.argsort itself, tie order included.  NumPy must run its scalar sort (what the
+    reference's pinned numpy==1.19.5 has): a child interpreter is started with NumPy's SIMD dispatch disabled."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, NPY_DISABLE_CPU_FEATURES="AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL AVX512_SPR AVX2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", _ARGSORT.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    if "SKIP" in r.stdout:
+        pytest.skip("this NumPy build does not fall back to the scalar argsort")
+    assert "OK" in r.stdout
+
+
 def test_knn_edge_cases():
     lap = np.array([[0.0, 0, 0, 0], [1.0, 0, 0, 0], [1.0, 0, 0, 0], [-1.0, 0, 0, 0]])
-    # K > T returns T indices; exact ties resolve by index
+    # K > T returns T indices; short arrays go through the insertion sort, which keeps ties in index order
     assert list(oracle.select_knn(lap, np.zeros(4), 8)) == [0, 1, 2, 3]
     assert list(oracle.select_knn(lap, np.array([1.0, 0, 0, 0]), 2)) == [1, 2]
     assert list(oracle.select_knn(lap[:1], np.ones(4), 3)) == [0]

@@ -227,6 +227,25 @@ def latency_probe(device, max_seconds=60.0):
     }  # fmt: skip
 
 
+def bind_to_gpu_numa_node(index, verbose=False):
+    """Pins this process to the CPUs the driver reports as local to GPU `index` (NVML's ideal CPU affinity) BEFORE any
+    pinned buffer is allocated, so that the end-to-end arm's host buffers live on the GPU's own NUMA node: with
+    several ranks per box the host side of PCIe is the bottleneck of `e2e`, and remote-node buffers halve it."""
+    if os.environ.get("I2LQR_NO_AFFINITY"):
+        return
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        if verbose:
+            print("[bench] rank 0 bound to CPUs %s (NVML ideal affinity of GPU %d)" % (sorted(os.sched_getaffinity(0)), index), file=sys.stderr)
+    except Exception as err:  # affinity is an optimisation, never a requirement
+        if verbose:
+            print("[bench] CPU affinity not set: %s" % str(err)[:120], file=sys.stderr)
+
+
 def run_ours(args):
     import torch
 
@@ -238,6 +257,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local, verbose=(rank == 0))
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -6,7 +6,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it, and
  * only as the checker or the timed CPU baseline.  The product library (libi2lqr.so) never links or calls it.
  *
- * Pin: tests/test_oracle.py checks every function here against tests/golden/*.npz, which are outputs of the
+ * Pin: tests/test_oracle.py checks every function here against the .npz files under tests/golden/, which are outputs of the
  * unmodified Python reference run in the build container (tests/golden/make_golden.py).
  *
  * Arithmetic: dense 4x4 / 4x2 / 2x2 products with sequential left-to-right sums, evaluated in the
@@ -442,7 +442,8 @@ void orc_np_argsort(const double* v, int64_t num, int64_t* tosort) {
 
 /* iLqr.select_close_ss (utils/base.py:332-341): 1-norm distances, numpy.argsort, first K. */
 int orc_select_knn(const double* lap, int T, const double* x0, int K, int64_t* idx_out) {
-  double* d = (double*)malloc(sizeof(double) * (size_t)T);
+  if (T < 1) return 0;
+  double* d = (double*)calloc((size_t)T, sizeof(double));
   int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)T);
   for (int j = 0; j < T; ++j)
     d[j] = ((fabs(lap[j * NX + 0] - x0[0]) + fabs(lap[j * NX + 1] - x0[1])) + fabs(lap[j * NX + 2] - x0[2])) +

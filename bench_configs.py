@@ -79,7 +79,7 @@ def latency(device=0):
 def episodes_cfg(device=0, E=512, laps=3):
     sc = synth.episode_scenarios(4096)
     rank = int(os.environ.get("RANK", "0"))
-    lo = rank * E
+    lo = (rank * E) % 4096 if E < 4096 else 0
     p = _abi.default_params(num_ss_points=8, num_ss_iter=2)
     lap0, _ = synth.initial_lap()
     obs = _abi.obstacle_array(sc["obs"][lo : lo + E], sc["mode"][lo : lo + E])
@@ -161,4 +161,7 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "latency"
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     fn = {"stock": stock, "latency": latency, "episodes": episodes_cfg, "horizon": horizon_sweep}[what]
-    print(json.dumps(fn(dev)))
+    if what == "episodes" and len(sys.argv) > 2:  # episodes on this GPU (default: its 512-episode share of the 4096)
+        print(json.dumps(episodes_cfg(dev, E=int(sys.argv[2]))))
+    else:
+        print(json.dumps(fn(dev)))

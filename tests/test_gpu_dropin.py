@@ -121,11 +121,11 @@ def test_episode_batch_matches_reference_closed_loop(name):
 
 
 def test_episode_batch_random_scenarios_vs_oracle():
-    """BASELINE config 3 shape on a subset: per-episode obstacle (static / up / left) and start state,
-    K=8, L=2, two laps, every episode compared with an oracle-driven closed loop."""
+    """BASELINE config 3 shape on the 64-episode subset SURVEY 8d names: per-episode obstacle (static / up / left)
+    and start state, K=8, L=2, two laps, every episode compared with an oracle-driven closed loop."""
     from ilqr_iterative_tasks_b200 import _abi, episodes, synth
 
-    E, n_laps = 12, 2
+    E, n_laps = 64, 2
     sc = synth.episode_scenarios(E)
     p = _abi.default_params(num_ss_points=8, num_ss_iter=2)
     lap0, _ = synth.initial_lap()

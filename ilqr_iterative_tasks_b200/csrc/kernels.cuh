@@ -81,7 +81,10 @@ struct Work {
 // the few lanes that switch candidates in a trip never stalls the warp.  kMode 1: lambda chains of a
 // controller step; a lane walks the K candidates of its (episode, lap) in rank order carrying lambda
 // (utils/base.py:393,414).
-enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3 };
+enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3, ST_FIN = 4, ST_PARK = 5 };
+#ifndef I2LQR_SERVICE_TRIPS
+#define I2LQR_SERVICE_TRIPS 2  // flat batches: candidate switches every this many trips of the warp loop (see solve_kernel)
+#endif
 constexpr int kSolveThreads = 32;    // block size of the memory-backed variants (one warp: its SM slot frees as soon as it is done)
 constexpr int kTmemThreads = 128;    // block size of the tensor-memory variant (a CTA's TMEM allocation spans four lane quarters)
 constexpr int kTmemColumns = 128;    // 32-bit TMEM columns per CTA: 20 per stage, N <= 6
@@ -144,57 +147,106 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     double n_x0[4], n_xt[4], n_lamb = (double)p.lamb0;
     DevObstacle n_obs;
     n_obs.present = 0;
+    // Candidate switches are batched: a lane that finishes (or reaches the pass's iteration cap) only flags itself and
+    // idles; every kServiceTrips-th trip of the warp loop is a "service trip" in which all flagged lanes store their
+    // results / park, and lanes without a candidate take the next one.  The switch code runs with only the lanes that
+    // switch active -- 2.7 of 32 when it ran every trip, a quarter of the kernel's time at 10 % lane efficiency
+    // (profiles/r01_solve_kernel_v6_summary.txt) -- so running it every other trip with twice the lanes halves that cost;
+    // the price is a finished lane idling half a trip on average (4 % of an 11.7-iteration candidate).  Scheduling
+    // only: every candidate's arithmetic is unchanged.
+    constexpr int kServiceTrips = I2LQR_SERVICE_TRIPS;
+    int trip = 0;
+    bool no_park = false;
     for (;;) {
-      // (a) lanes without a pending candidate fetch an index and issue its loads (consumed trips later)
-      const unsigned want = __ballot_sync(0xffffffffu, !have_next && !exhausted);
-      if (want) {
-        unsigned long long base = 0;
-        const int leader = __ffs(want) - 1;
-        if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (!have_next && !exhausted) {
-          n_idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
-          if (n_idx >= n_total) {
-            exhausted = true;
-          } else {
-            n_item = w.pass > 0 ? (long long)w.resume_list[n_idx] : n_idx;
-            have_next = true;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              n_x0[i] = w.x0[n_item * 4 + i];
-              n_xt[i] = w.x_term[n_item * 4 + i];
+      const bool service = kServiceTrips == 1 || trip == 0;  // warp-uniform
+      trip = trip + 1 == kServiceTrips ? 0 : trip + 1;
+      if (service) {
+        // (z) lanes flagged in the previous trips: results out, or park
+        if (state == ST_FIN) {
+          store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
+          if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
+          if (w.iters) w.iters[item] = c.iters;
+          state = ST_NEED;
+        }
+        // Iteration slicing: a candidate that is still unfinished at the pass's cap is parked (trajectory,
+        // lambda, J, count) and its lane takes the next one.  The following pass resumes the parked ones packed
+        // into full warps, so the few-percent long tail (up to max_ilqr_iter = 150 iterations against a mean
+        // of ~12) no longer runs as hundreds of trips of nearly empty warps.
+        const bool park = state == ST_PARK;
+        const unsigned parkers = __ballot_sync(0xffffffffu, park);
+        if (parkers) {
+          unsigned long long pbase = 0;
+          const int leader = __ffs(parkers) - 1;
+          if ((int)lane == leader) pbase = atomicAdd(w.park_count, (unsigned long long)__popc(parkers));
+          pbase = __shfl_sync(0xffffffffu, pbase, leader);
+          const long long pslot = (long long)pbase + __popc(parkers & ((1u << lane) - 1u));
+          if (park) {
+            if (pslot < w.park_capacity) {
+              double* ps = w.park_state + (size_t)pslot * park_words;
+              for (int e = 0; e < 8 * N; ++e) ps[e] = (double)s.ldc(e);
+              ps[8 * N] = (double)c.lamb;
+              ps[8 * N + 1] = (double)c.J;
+              ps[8 * N + 2] = (double)c.iters;
+              w.park_list[pslot] = (int)item;
+              state = ST_NEED;
+            } else {
+              state = ST_RUN;  // park buffers full: this candidate runs to its end in this pass
+              no_park = true;
             }
-            if (w.lamb_in) n_lamb = w.lamb_in[n_item];
-            if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : n_item];
           }
         }
-      }
-      // (b) lanes that need a candidate take the prefetched one
-      if (state == ST_NEED) {
-        if (have_next) {
-          item = n_item;
-          idx = n_idx;
+        // (a) lanes without a pending candidate fetch an index and issue its loads (consumed trips later)
+        const unsigned want = __ballot_sync(0xffffffffu, !have_next && !exhausted);
+        if (want) {
+          unsigned long long base = 0;
+          const int leader = __ffs(want) - 1;
+          if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (!have_next && !exhausted) {
+            n_idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+            if (n_idx >= n_total) {
+              exhausted = true;
+            } else {
+              n_item = w.pass > 0 ? (long long)w.resume_list[n_idx] : n_idx;
+              have_next = true;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            c.x0[i] = R(n_x0[i]);
-            c.xt[i] = R(n_xt[i]);
+              for (int i = 0; i < 4; ++i) {
+                n_x0[i] = w.x0[n_item * 4 + i];
+                n_xt[i] = w.x_term[n_item * 4 + i];
+              }
+              if (w.lamb_in) n_lamb = w.lamb_in[n_item];
+              if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : n_item];
+            }
           }
-          c.lamb = R(n_lamb);
-          load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
-          sincos_fast(c.x0[3], &c.s0, &c.c0);
-          if (w.pass == 0) {
-            init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
-          } else {  // resume a candidate parked by the previous pass
-            const double* ps = w.resume_state + (size_t)idx * park_words;
-            for (int e = 0; e < 8 * N; ++e) s.stc(e, R(ps[e]));
-            c.lamb = R(ps[8 * N]);
-            c.J = R(ps[8 * N + 1]);
-            c.iters = (int)ps[8 * N + 2];
+        }
+        // (b) lanes that need a candidate take the prefetched one
+        if (state == ST_NEED) {
+          if (have_next) {
+            item = n_item;
+            idx = n_idx;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              c.x0[i] = R(n_x0[i]);
+              c.xt[i] = R(n_xt[i]);
+            }
+            c.lamb = R(n_lamb);
+            load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
+            sincos_fast(c.x0[3], &c.s0, &c.c0);
+            if (w.pass == 0) {
+              init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
+            } else {  // resume a candidate parked by the previous pass
+              const double* ps = w.resume_state + (size_t)idx * park_words;
+              for (int e = 0; e < 8 * N; ++e) s.stc(e, R(ps[e]));
+              c.lamb = R(ps[8 * N]);
+              c.J = R(ps[8 * N + 1]);
+              c.iters = (int)ps[8 * N + 2];
+            }
+            have_next = false;
+            no_park = false;
+            state = ST_RUN;
+          } else if (exhausted) {
+            state = ST_DONE;
           }
-          have_next = false;
-          state = ST_RUN;
-        } else if (exhausted) {
-          state = ST_DONE;
         }
       }
       if (__all_sync(0xffffffffu, state == ST_DONE)) break;
@@ -209,39 +261,14 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
       } else {
         finished = live && ilqr_iteration<kQR, kN>(p, c, s);
       }
-      bool park = false;
       if (live) {
         if (finished) {
           my_solves += 1;
-          store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
-          if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
-          if (w.iters) w.iters[item] = c.iters;
-          state = ST_NEED;
-        } else if (w.iter_cap > 0 && c.iters >= w.iter_cap) {
-          park = true;
+          state = ST_FIN;
+        } else if (w.iter_cap > 0 && c.iters >= w.iter_cap && !no_park) {
+          state = ST_PARK;
         }
         my_iters += 1;
-      }
-      // Iteration slicing: a candidate that is still unfinished at the pass's cap is parked (trajectory,
-      // lambda, J, count) and its lane takes the next one.  The following pass resumes the parked ones packed
-      // into full warps, so the few-percent long tail (up to max_ilqr_iter = 150 iterations against a mean
-      // of ~12) no longer runs as hundreds of trips of nearly empty warps.
-      const unsigned parkers = __ballot_sync(0xffffffffu, park);
-      if (parkers) {
-        unsigned long long pbase = 0;
-        const int leader = __ffs(parkers) - 1;
-        if ((int)lane == leader) pbase = atomicAdd(w.park_count, (unsigned long long)__popc(parkers));
-        pbase = __shfl_sync(0xffffffffu, pbase, leader);
-        const long long pslot = (long long)pbase + __popc(parkers & ((1u << lane) - 1u));
-        if (park && pslot < w.park_capacity) {
-          double* ps = w.park_state + (size_t)pslot * park_words;
-          for (int e = 0; e < 8 * N; ++e) ps[e] = (double)s.ldc(e);
-          ps[8 * N] = (double)c.lamb;
-          ps[8 * N + 1] = (double)c.J;
-          ps[8 * N + 2] = (double)c.iters;
-          w.park_list[pslot] = (int)item;
-          state = ST_NEED;
-        }
       }
     }
   } else {

@@ -459,7 +459,7 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
 #pragma unroll
           for (int i = 0; i < 8; ++i) s.stc(I2_CUR(k) + i, s.ldg_lane(delta, k * 10 + i));
         }
-        if (fabs((Jn_w - c.J) / c.J) < p.eps) fin = true;
+        if (rel_change_below(Jn_w, c.J, p.eps)) fin = true;
         c.J = kQR ? Jt_w : Jn_w;
       }
       c.lamb = lamb;
@@ -607,7 +607,7 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
       if (winner >= 0) {
         cur = v.trial_of(winner, wb_w);  // the winner's trial is the current trajectory from here on
         if (rung == winner) wb ^= 1;
-        if (fabs((Jn_w - c.J) / c.J) < p.eps) fin = true;
+        if (rel_change_below(Jn_w, c.J, p.eps)) fin = true;
         c.J = kQR ? Jt_w : Jn_w;
       }
       c.lamb = lamb;

@@ -30,8 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram bytes of the dominant launch (pass 0 over 2^20 candidates) from profiles/r01_solve_kernel_v6_summary.txt
-NCU_TRAFFIC_BYTES = 129622528 + 300095232
+# dram bytes of the dominant launch (pass 0 over 2^20 candidates) from profiles/r01_solve_kernel_v7_summary.txt
+NCU_TRAFFIC_BYTES = 129926656 + 298526976
 METRIC = "candidate iLQR solves/sec"
 UNIT = "solves/s"
 
@@ -409,7 +409,7 @@ def run_ours(args):
                 "bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": NCU_TRAFFIC_BYTES if (B == 1 << 20 and N == 6) else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the pass-0 launch (2^20 candidates), one ncu --set full "
-                                "capture: profiles/r01_solve_kernel_v6_summary.txt; algorithmic bytes per launch = %d" % (B * bytes_per_solve(N)),
+                                "capture: profiles/r01_solve_kernel_v7_summary.txt; algorithmic bytes per launch = %d" % (B * bytes_per_solve(N)),
                 "kernel": "solve_kernel<double, kQR=false, kScratch=3 (tensor-memory gains), kMode=0, 128 threads>", "kernel_ms": avg_ms,
                 "isolated": {"launch_ms": kernel_ms, "achieved": flops / (kernel_ms * 1e-3) / 1e12,
                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,

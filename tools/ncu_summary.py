@@ -34,7 +34,11 @@ for w in want:
         lines.append("%-85s %s %s" % (w, vals[i], units[i]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src[src.index('"Address"'):])))
-sh, data = srows[0], srows[1:]
+sh, data = srows[0], []
+for r in srows[1:]:  # a report with several launches: the first one only (the raw-page row summarised above)
+    if len(r) < len(sh):
+        break
+    data.append(r)
 ia, it, isrc, ismp = sh.index("Instructions Executed"), sh.index("Thread Instructions Executed"), sh.index("Source"), sh.index("# Samples")
 cnt = collections.Counter()
 tot = thr = 0

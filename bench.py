@@ -268,7 +268,7 @@ def run_ours(args):
     d, obs = make_workload(B, N, rank)
     # two handles = two streams: consecutive steps are independent batches, so step k+1 starts while the
     # iteration-count tail of step k (a few 150-iteration stragglers) is still draining
-    n_pipe = 1 if args.no_pipeline else 2
+    n_pipe = 1 if args.no_pipeline else max(1, args.pipeline)
     engs = [engine.Engine(params, device=local) for _ in range(n_pipe)]
     eng = engs[0]
     dev = torch.device("cuda", local)
@@ -449,6 +449,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the controller-step latency probe")
     ap.add_argument("--no-pipeline", action="store_true", help="one handle / one stream: steps strictly back to back")
+    ap.add_argument("--pipeline", type=int, default=2, help="handles (streams) that consecutive steps rotate over")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -170,7 +170,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(B, N, args.gpus),
+        "config": workload_config(B, N, args.gpus, 1 if args.no_pipeline else max(1, args.pipeline)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -180,11 +180,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(B, N, gpus):
+def workload_config(B, N, gpus, n_pipe=4):
     return {
         "workload": "BASELINE config 5: flat batch of independent candidate iLQR solves, synthetic obstacles near the path",
         "candidates_per_gpu": B, "global_candidates": B * gpus, "num_horizon": N, "state_dim": 4, "input_dim": 2,
-        "seed": 20260101, "parallelism": "candidates sharded by rank, no data-path collective; steps pipelined over 2 streams per GPU",
+        "seed": 20260101, "parallelism": "candidates sharded by rank, no data-path collective; steps pipelined over %d streams per GPU" % n_pipe,
         "l2": "per-step working set (inputs 120 B + outputs 300 B per candidate) is %.0f MB > 126 MB L2" % (B * 420 / 1e6),
     }  # fmt: skip
 
@@ -266,8 +266,9 @@ def run_ours(args):
     params = _abi.default_params()
     N, B = params.num_horizon, args.batch
     d, obs = make_workload(B, N, rank)
-    # two handles = two streams: consecutive steps are independent batches, so step k+1 starts while the
-    # iteration-count tail of step k (a few 150-iteration stragglers) is still draining
+    # several handles = several streams: consecutive steps are independent batches, so the next steps start while the
+    # iteration-count tail of step k (its resume passes: a few 150-iteration stragglers, 1.5 ms of sequential trips) is
+    # still draining.  Measured on one B200 at 24 steps: 2 streams 367, 3: 390, 4: 402, 8: 412 M solves/s
     n_pipe = 1 if args.no_pipeline else max(1, args.pipeline)
     engs = [engine.Engine(params, device=local) for _ in range(n_pipe)]
     eng = engs[0]
@@ -399,7 +400,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(B, N, world),
+            "dtype": "f64", "data": "synthetic", "config": workload_config(B, N, world, n_pipe),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "api": "i2lqr_solve_batch (ctypes), pinned host buffers, %d host threads each driving its own handle" % n_pipe},
@@ -449,7 +450,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the controller-step latency probe")
     ap.add_argument("--no-pipeline", action="store_true", help="one handle / one stream: steps strictly back to back")
-    ap.add_argument("--pipeline", type=int, default=2, help="handles (streams) that consecutive steps rotate over")
+    ap.add_argument("--pipeline", type=int, default=4, help="handles (streams) that consecutive steps rotate over")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -764,6 +764,8 @@ __device__ __noinline__ void np_argsort_device(const double* v, int num, int* t)
   }
 }
 
+constexpr int kKnnCountLimit = 512;  // laps up to this many points are ranked by counting, longer ones by arg-min rounds
+
 struct KnnArgs {
   SafeSet set;
   int K, it, n_episodes;
@@ -825,35 +827,58 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
               fabs(lap[3 * Tc + j] - g[3]);
   __syncwarp();
   const int n = a.K < T ? a.K : T;
-  double dprev = -INFINITY;
-  int jprev = -1;
   bool tie = false;
-  const int rounds = n < T ? n + 1 : n;  // one more than emitted: does the K-th distance tie with the next?
-  for (int r = 0; r < rounds; ++r) {
-    double dbest = INFINITY;
-    int jbest = 0x7fffffff;
+  if (T <= kKnnCountLimit) {
+    // Short laps (every lap of the reference's scenarios): rank by counting.  Element j's rank in the order
+    // (distance, index) is below = #{d' < d_j} plus the equal distances with a smaller index; it is emitted if
+    // rank < K.  T^2 / 32 comparisons per lane on shared memory, no dependent shuffle rounds -- at K = 64 the K + 1
+    // arg-min rounds below are ~20 us of a 2.5 ms controller step, this is ~2 us.  A tie touches the K + 1 smallest
+    // exactly when some distance occurs more than once and fewer than K distances lie below it.
     for (int j = lane; j < T; j += 32) {
       const double d = dist[j];
-      const bool after = d > dprev || (d == dprev && j > jprev);
-      if (after && (d < dbest || (d == dbest && j < jbest))) {
-        dbest = d;
-        jbest = j;
+      int below = 0, equal_before = 0, equal_all = 0;
+      for (int i = 0; i < T; ++i) {
+        const double di = dist[i];
+        below += di < d;
+        equal_all += di == d;
+        equal_before += (di == d) & (i < j);
       }
+      const int rank = below + equal_before;
+      if (d == d && rank < n) out[rank] = j;  // (a NaN distance never ranks; the arg-min rounds below skip it as well)
+      tie = tie || (equal_all > 1 && below < a.K && below + 1 < T);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double d2 = __shfl_xor_sync(0xffffffffu, dbest, o);
-      const int j2 = __shfl_xor_sync(0xffffffffu, jbest, o);
-      if (d2 < dbest || (d2 == dbest && j2 < jbest)) {
-        dbest = d2;
-        jbest = j2;
+    tie = __any_sync(0xffffffffu, tie);
+  } else {
+    double dprev = -INFINITY;
+    int jprev = -1;
+    const int rounds = n < T ? n + 1 : n;  // one more than emitted: does the K-th distance tie with the next?
+    for (int r = 0; r < rounds; ++r) {
+      double dbest = INFINITY;
+      int jbest = 0x7fffffff;
+      for (int j = lane; j < T; j += 32) {
+        const double d = dist[j];
+        const bool after = d > dprev || (d == dprev && j > jprev);
+        if (after && (d < dbest || (d == dbest && j < jbest))) {
+          dbest = d;
+          jbest = j;
+        }
       }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double d2 = __shfl_xor_sync(0xffffffffu, dbest, o);
+        const int j2 = __shfl_xor_sync(0xffffffffu, jbest, o);
+        if (d2 < dbest || (d2 == dbest && j2 < jbest)) {
+          dbest = d2;
+          jbest = j2;
+        }
+      }
+      tie = tie || (r > 0 && dbest == dprev);
+      if (lane == 0 && r < n) out[r] = jbest;
+      dprev = dbest;
+      jprev = jbest;
     }
-    tie = tie || (r > 0 && dbest == dprev);
-    if (lane == 0 && r < n) out[r] = jbest;
-    dprev = dbest;
-    jprev = jbest;
   }
-  if (tie) {  // warp-uniform: every lane holds the same (dbest, dprev) after the butterfly
+  if (tie) {  // warp-uniform in both forms
+    __syncwarp();  // the indices written above by other lanes are overwritten below by lane 0
     if (lane == 0) {
       np_argsort_device(dist, T, order);
       for (int r = 0; r < n; ++r) out[r] = order[r];

@@ -315,7 +315,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     fp64_peak = engine.measure_fp64_peak(local, reps=5)
-    for k in range(args.warmup):
+    # W warm-up steps, and at least one on every handle: a handle allocates its device buffers on first use, which must
+    # not happen inside the timed region (it did once, with 4 handles and W = 3: 31 ms per step instead of 2.6)
+    for k in range(max(args.warmup, n_pipe)):
         device_step(k)
     barrier()
     # isolated launches (one stream, back to back): the per-launch duration ncu also sees

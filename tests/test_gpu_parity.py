@@ -127,7 +127,7 @@ def test_knn_tie_order_is_numpys(eng_mod):
 
     rng = np.random.default_rng(11)
     for case in range(40):
-        T = int(rng.choice([5, 16, 17, 18, 33, 64, 121, 257, 500]))
+        T = int(rng.choice([5, 16, 17, 18, 33, 64, 121, 257, 500, 513, 700]))  # <= 512: ranked by counting, above: arg-min rounds
         K = int(rng.choice([8, 64]))
         if case % 3 == 0:
             lap = rng.integers(0, 4, (T, 4)).astype(np.float64)
@@ -306,6 +306,39 @@ def test_split_step_equals_single_handle(eng_mod, name, n_parts):
             tr = parts[part].step_trace(1)
             for key in ref_tr:
                 assert np.array_equal(tr[key], ref_tr[key], equal_nan=True), (name, s, part, key)
+    for e in [whole] + parts:
+        e.close()
+
+
+def test_split_step_several_episodes(eng_mod):
+    """The split form with more than one controller per handle: three episodes at different points of the same
+    recorded run, two parts, against i2lqr_solve_step on one handle."""
+    from ilqr_iterative_tasks_b200 import dist as D
+
+    g = H.load("steps_add_up.npz")
+    p = H.step_params(g)
+    ids = [int(s) for s in g["solve_ids"] if int(g["step/n_laps"][s]) == 6][:40:13]
+    assert len(ids) == 3
+    E = len(ids)
+    whole = eng_mod.Engine(p, n_episodes=E, lap_capacity=128)
+    parts = [eng_mod.Engine(p, n_episodes=E, lap_capacity=128) for _ in range(2)]
+    for k, s in enumerate(ids):
+        for e in [whole] + parts:
+            for l in range(6):
+                e.add_lap(k, g["lap%d" % l])
+            e.set_obstacle(k, H.step_obstacle(g, s))
+    x = g["step/x"][ids]
+    ref = whole.solve_step(x)
+    ref_tr = whole.step_trace(E)
+    for part, out in enumerate(D.split_step_local(parts, x)):
+        for key in ref:
+            assert np.array_equal(out[key], ref[key], equal_nan=True), (part, key)
+        tr = parts[part].step_trace(E)
+        for key in ref_tr:
+            assert np.array_equal(tr[key], ref_tr[key], equal_nan=True), (part, key)
+    for k, s in enumerate(ids):  # and the whole-handle result is the recorded reference step
+        si = list(g["solve_ids"]).index(s)
+        assert np.abs(ref["x_pred"][k] - g["solve/x_pred"][si]).max() <= H.RTOL * max(1.0, np.abs(g["solve/x_pred"][si]).max())
     for e in [whole] + parts:
         e.close()
 

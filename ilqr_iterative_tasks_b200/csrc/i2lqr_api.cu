@@ -218,9 +218,13 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
   if (per_sm < 1) return fail("solve kernel does not fit on an SM (horizon %d)", kp.N);
-  // tensor memory: 512 columns per SM, 128 per CTA; registers (168 x 128 threads) allow three CTAs.  The
-  // occupancy calculator reports 1 for kernels that allocate tensor memory, so the grid is sized by hand.
-  if (scratch == 3) per_sm = 3;  // (a 4-CTA build capped at 128 registers spills and measured 12 % slower)
+  // tensor memory: 512 columns per SM, 128 / 256 / 512 per CTA (horizon up to 6 / 12 / 25); registers (168 x 128
+  // threads) allow three CTAs.  The occupancy calculator does not know about tensor memory, so the grid is sized by
+  // hand: what the columns, the registers and the shared memory each allow.
+  if (scratch == 3) {  // (a 4-CTA build capped at 128 registers spills and measured 12 % slower)
+    per_sm = std::min(3, 512 / tmem_columns(kp.N));
+    per_sm = std::max(1, std::min<int>(per_sm, (int)((kSmemLimit - 1024) / (smem + 1024))));
+  }
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
   if (scratch == 1 || scratch == 2) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;

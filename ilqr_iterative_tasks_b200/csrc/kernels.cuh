@@ -87,8 +87,8 @@ enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3, ST_FIN = 4, ST_P
 #endif
 constexpr int kSolveThreads = 32;    // block size of the memory-backed variants (one warp: its SM slot frees as soon as it is done)
 constexpr int kTmemThreads = 128;    // block size of the tensor-memory variant (a CTA's TMEM allocation spans four lane quarters)
-constexpr int kTmemColumns = 128;    // 32-bit TMEM columns per CTA: 20 per stage, N <= 6
-constexpr int kTmemMaxHorizon = 6;
+constexpr int kTmemMaxHorizon = 25;  // 20 32-bit TMEM columns per stage: 128 columns up to N = 6, 256 up to 12, 512 up to 25
+__host__ __device__ __forceinline__ int tmem_columns(int N) { return 20 * N <= 128 ? 128 : (20 * N <= 256 ? 256 : 512); }
 
 // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab),
 //           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8)
@@ -113,7 +113,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     if (threadIdx.x < 32) {  // one warp allocates the CTA's tensor-memory columns
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                        (uint32_t)__cvta_generic_to_shared(&tmem_base)),
-                   "r"(kTmemColumns)
+                   "r"(tmem_columns(p.N))
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -349,7 +349,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32)
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemColumns) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_columns(p.N)) : "memory");
   }
 }
 

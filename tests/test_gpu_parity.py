@@ -60,6 +60,27 @@ def test_flat_batch_vs_oracle_sample(eng_mod):
     e.close()
 
 
+@pytest.mark.parametrize("N", [10, 12, 13, 25])
+def test_flat_batch_mid_horizons_vs_oracle(eng_mod, N):
+    """Batches of >= 8192 candidates at horizons 7...25 run the tensor-memory variant with 256 / 512 columns per CTA
+    (the reference goldens for these horizons are small batches, which take the shared-memory variants)."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    B = 8192
+    d = synth.flat_candidates(B, N, seed=synth.SEED + 300 + N)
+    p = _abi.default_params(num_horizon=N)
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+    e.close()
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
+    same = (out["iters"] == iters) & (out["lamb_out"] == lamb)
+    assert same.mean() >= 0.999, "discrete path diverged for %d of %d" % (int((~same).sum()), B)
+    assert H.rel_err(out["xvar"][same], x[same]).max() <= H.RTOL
+    assert H.rel_err(out["uvar"][same], u[same]).max() <= H.RTOL
+
+
 def test_shared_and_absent_obstacle(eng_mod):
     from ilqr_iterative_tasks_b200 import _abi, synth
     from oracle import oracle

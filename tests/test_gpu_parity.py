@@ -81,6 +81,28 @@ def test_flat_batch_mid_horizons_vs_oracle(eng_mod, N):
     assert H.rel_err(out["uvar"][same], u[same]).max() <= H.RTOL
 
 
+def test_flat_batch_size_boundaries(eng_mod):
+    """Batch sizes around every launch-shape threshold (one lane, one warp, one CTA, the tensor-memory variant from
+    8192 candidates, iteration-sliced passes from 131072): each equals the first B candidates of one big oracle run."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    Bmax = 131072 + 33
+    d = synth.flat_candidates(Bmax, 6, seed=synth.SEED + 77)
+    p = _abi.default_params()
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
+    e = eng_mod.Engine(p)
+    for B in (1, 31, 33, 127, 129, 8191, 8192, 8193, 131071, 131072, Bmax):
+        out = e.solve_batch(d["x0"][:B], d["x_term"][:B], d["lamb_in"][:B], obs[:B])
+        same = (out["iters"] == iters[:B]) & (out["lamb_out"] == lamb[:B])
+        assert same.mean() >= 0.999, (B, int((~same).sum()))
+        assert H.rel_err(out["xvar"][same], x[:B][same]).max() <= H.RTOL, B
+        assert H.rel_err(out["uvar"][same], u[:B][same]).max() <= H.RTOL, B
+        assert e.last_stats()["solves"] == B
+    e.close()
+
+
 def test_shared_and_absent_obstacle(eng_mod):
     from ilqr_iterative_tasks_b200 import _abi, synth
     from oracle import oracle

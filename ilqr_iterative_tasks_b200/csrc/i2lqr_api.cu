@@ -159,7 +159,7 @@ constexpr long long kSliceMinBatch = 131072;  // smaller flat batches run as a s
 int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   const KParams& kp = h->kp;
   // scratch placement: 0 shared memory (18N doubles per lane), 3 trajectory in shared memory + gains in tensor
-  // memory (flat batches up to horizon 6: 12 resident warps per SM), 2 hybrid (8N in shared memory, 10N in
+  // memory (flat batches up to horizon 25: 12 / 8 / 4 resident warps per SM), 2 hybrid (8N in shared memory, 10N in
   // an L2-resident slab), 1 all in the slab (horizons whose trajectory does not fit shared memory)
   static const int force = getenv("I2LQR_SCRATCH") ? atoi(getenv("I2LQR_SCRATCH")) : -1;  // tuning switch
   const size_t smem_full = (size_t)kSolveThreads * 18 * kp.N * sizeof(double);

@@ -909,7 +909,9 @@ int launch_winner_step(i2lqr_handle* h, int it, int n_episodes, const int* d_act
   wa.winner_cost = h->s_wcost.p;
   wa.shrink = h->s_shrink.p;
   const int wthreads = 128;
-  winner_kernel<<<(unsigned)(((long long)n_episodes * 32 + wthreads - 1) / wthreads), wthreads, 0, st>>>(wa);
+  const size_t wsmem = (size_t)(wthreads / 32) * h->L * h->K * sizeof(double);
+  wa.stage_costs = wsmem <= 48 * 1024;
+  winner_kernel<<<(unsigned)(((long long)n_episodes * 32 + wthreads - 1) / wthreads), wthreads, wa.stage_costs ? wsmem : 0, st>>>(wa);
   CU(cudaGetLastError());
   h->last_launches += 1;
   return 0;

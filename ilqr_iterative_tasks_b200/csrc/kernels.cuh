@@ -913,6 +913,7 @@ struct WinnerArgs {
   long long* winner_idx;
   double* winner_cost;
   int* shrink;
+  int stage_costs;         // 1: dynamic shared memory holds (warps per block) x L x K doubles
 };
 
 __global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
@@ -925,8 +926,17 @@ __global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
   const int n_act = count < a.L ? count : a.L;
   const int min_iter = count - a.L > 0 ? count - a.L : 0;
   int bl = 0, br = 0;
+  // The rule below is a chain of dependent reads (a comparison stops at the first differing element), ~1 us each from
+  // global memory; when the step's cost table fits, all lanes first copy it to shared memory in one parallel sweep.
+  extern __shared__ double winner_smem[];
+  const double* cost = a.cand_cost + ((size_t)e * kOuter + a.it) * a.L * a.K;
+  if (a.stage_costs) {
+    double* mine = winner_smem + (size_t)(threadIdx.x >> 5) * a.L * a.K;
+    for (int i = lane; i < n_act * a.K; i += 32) mine[i] = cost[i];
+    __syncwarp();
+    cost = mine;
+  }
   if (lane == 0) {
-    const double* cost = a.cand_cost + ((size_t)e * kOuter + a.it) * a.L * a.K;
     const int* cnt = a.sel_cnt + (size_t)e * a.L;
     for (int l = 1; l < n_act; ++l) {
       const double* ca = cost + (size_t)l * a.K;

@@ -96,7 +96,9 @@ def params_from_reference(ilqr_param, system_param=None, timestep=None):
         "eps", "lamb", "lamb_factor", "max_lamb",
     ):  # fmt: skip
         if hasattr(ilqr_param, name):
-            setattr(p, name, getattr(ilqr_param, name))
+            value = getattr(ilqr_param, name)
+            # ctypes int fields reject floats
+            setattr(p, name, int(value) if isinstance(getattr(p, name), int) else float(value))
     for name in ("matrix_Q", "matrix_R", "matrix_Qterminal"):
         if hasattr(ilqr_param, name):
             set_field(p, name, getattr(ilqr_param, name))

@@ -459,4 +459,124 @@ __device__ __forceinline__ R chain_forward(const KParamsT<R>& p, const CandT<R>&
   return Jn + T;
 }
 
+// One candidate solve by a group of kGroup adjacent lanes (the first kRungs of them are the speculative lambda
+// rungs, all of them share the stage tasks), as a small state machine that a warp drives convergently: every lane
+// of the warp calls trip() each round (it contains warp-wide barriers and votes); groups without a live candidate
+// pass through idle.  One trip consumes 1..kRungs reference iterations (iterative_ilqr.py:29-84), accepted in the
+// reference's order.  Used by the controller-step kernels (kernels.cuh: chain_lat_kernel; spec_step.cuh).
+template <typename R, bool kQR, int kRungs, int kGroup, int S>
+struct GroupSolver {
+  static constexpr unsigned kFull = 0xffffffffu;
+  ChainLane<R, S> v;
+  int rung, gbase_lane;
+  bool is_rung;
+  CandT<R> c;          // x0 / c0 / s0 / obstacle / xt / lamb are set by the caller before start()
+  int wb;              // trial buffer this lane writes next
+  const R* cur;        // current trajectory of the group: some lane's trial buffer
+  bool dirty;          // the shared terms do not belong to `cur` yet
+  bool running;
+
+  __device__ __forceinline__ void bind(R* smem, int lane, int N) {
+    rung = lane % kGroup;
+    is_rung = rung < kRungs;
+    gbase_lane = lane - rung;
+    v.col = smem + lane;
+    v.grp = smem + gbase_lane;
+    v.N = N;
+    v.rungs = kGroup;
+    wb = 0;
+    cur = v.trial_of(0, 0);
+    dirty = true;
+    running = false;
+    c = CandT<R>{};
+  }
+  // candidate start (utils/base.py:405-410 + the first rollout): zero inputs
+  __device__ __forceinline__ void start(const KParamsT<R>& p) {
+    c.J = chain_init<kQR, S>(p, c, rung == 0 ? v.trial(0) : nullptr);
+    c.iters = 0;
+    cur = v.trial_of(0, 0);
+    wb = rung == 0 ? 1 : 0;
+    dirty = true;
+    running = true;
+  }
+  // One round for the whole warp.  Returns true on the lanes of a group whose candidate ended in this round; its
+  // result is then `cur` (trajectory), c.lamb, c.iters, c.J.
+  __device__ __forceinline__ bool trip(const KParamsT<R>& p) {
+    __syncwarp();
+    const bool run = running;
+    if (run && dirty) chain_terms<kQR, S>(p, c, v, cur, rung);
+    __syncwarp();
+    R Jn = R(0.0), Jt = R(0.0);
+    if (run && is_rung) {
+      R lamb_r = c.lamb;
+      for (int r = 0; r < rung; ++r) lamb_r *= p.lamb_factor;  // the value r rejects lead to, same operations
+      chain_riccati<kQR, S>(p, v, lamb_r);
+      Jn = chain_forward<kQR, S>(p, c, cur, v.gains(), v.trial(wb), Jt);
+    }
+    __syncwarp();
+    const unsigned acc_all = __ballot_sync(kFull, run && is_rung && Jn < c.J);
+    const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
+    // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
+    int winner = -1;
+    bool fin = false;
+    int consumed = 0;
+    R lamb = c.lamb;
+    if (run) {
+#pragma unroll
+      for (int r = 0; r < kRungs; ++r) {
+        if (winner >= 0 || fin) break;
+        if (c.iters + consumed >= p.max_iter) {
+          fin = true;
+          break;
+        }
+        ++consumed;
+        if ((acc >> r) & 1u) {
+          winner = r;
+          lamb /= p.lamb_factor;
+        } else {
+          lamb *= p.lamb_factor;
+          if (lamb > p.max_lamb) fin = true;
+        }
+      }
+    }
+    const int src = winner >= 0 ? gbase_lane + winner : (int)(threadIdx.x & 31);
+    const R Jn_w = __shfl_sync(kFull, Jn, src), Jt_w = __shfl_sync(kFull, Jt, src);
+    const int wb_w = __shfl_sync(kFull, wb, src);
+    if (run) {
+      dirty = winner >= 0;
+      if (winner >= 0) {
+        cur = v.trial_of(winner, wb_w);  // the winner's trial is the current trajectory from here on
+        if (rung == winner) wb ^= 1;
+        if (rel_change_below(Jn_w, c.J, p.eps)) fin = true;
+        c.J = kQR ? Jt_w : Jn_w;
+      }
+      c.lamb = lamb;
+      c.iters += consumed;
+      if (c.iters >= p.max_iter) fin = true;
+      if (fin) running = false;
+    }
+    return run && fin;
+  }
+  // Result in the reference's layout, xvar (4, N+1) and uvar (2, N), written by the lanes of the group together.
+  __device__ __forceinline__ void store(double* xv, double* uv) const {
+    const int N = v.N;
+    for (int k = rung; k < N; k += kGroup) {
+      const R* s = cur + (size_t)(8 * k) * S;
+      uv[k] = (double)s[0];
+      uv[N + k] = (double)s[S];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i * (N + 1) + k + 1] = (double)s[(2 + i) * S];
+    }
+    if (rung == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i * (N + 1)] = (double)c.x0[i];
+    }
+  }
+  __device__ __forceinline__ void terminal_state(R (&xN)[4]) const {
+    const R* s = cur + (size_t)(8 * (v.N - 1)) * S;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xN[i] = s[(2 + i) * S];
+  }
+};
+
 }  // namespace i2lqr

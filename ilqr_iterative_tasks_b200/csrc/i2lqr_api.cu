@@ -84,6 +84,7 @@ struct i2lqr_handle {
   int n_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t dev_done = nullptr;  // end of the last *_device call: the next one, on whatever stream, starts behind it
   i2lqr_params params;
   KParams kp;
   int E = 0, L = 0, K = 0, Tcap = 0;
@@ -136,9 +137,12 @@ struct i2lqr_handle {
   unsigned long long ep_noise_seed = 0;  // 0 = noise off (every reference script calls set_zero_noise)
   int ep_lap_index = 0;
   DevBuf<double> ep_upred, ep_goal, ep_lapx, ep_lapu;
-  DevBuf<int> ep_step, ep_done, ep_horizon, ep_pb, ep_active, ep_status, ep_nrun, ep_laplen;
+  DevBuf<int> ep_step, ep_done, ep_horizon, ep_pb, ep_active, ep_status, ep_nrun, ep_laplen, ep_list, ep_nep;
   DevBuf<DevObstacle> d_obs0;
-  int* h_nrun = nullptr;  // pinned
+  int* h_nrun = nullptr;      // mapped pinned: [0] episodes still running, [1] episodes that solve the current step
+  int* h_nrun_dev = nullptr;  // device alias of h_nrun
+  static constexpr int kEpEvents = 8;
+  cudaEvent_t ep_ev[kEpEvents] = {};
 };
 
 namespace {
@@ -296,7 +300,9 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   if (rungs == 4 && (force_group == 4 || force_group == 8 || force_group == 32)) group = force_group;
   const size_t smem_lat = (size_t)kSolveThreads * chain_lane_elems(kp.N, group) * rsz;
   int lanes_per_chain = rungs;
+  bool lat_form = false;
   if (!no_lat && smem_lat <= kSmemLimit) {
+    lat_form = true;
     scratch = 0;
     smem = smem_lat;
     lanes_per_chain = group;
@@ -305,15 +311,29 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   if (smem > 32 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (smem > 0) CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const long long lanes = w.n_items * lanes_per_chain;
-  const long long grid = std::max<long long>(1, (lanes + kSolveThreads - 1) / kSolveThreads);
+  long long grid = std::max<long long>(1, (lanes + kSolveThreads - 1) / kSolveThreads);
+  CU(h->ctl.ensure(kCtlWords));
+  w.counter = nullptr;
+  if (lat_form) {
+    // latency form: never launch more warps than are resident at once -- with more chains than lane groups the groups
+    // fetch further chains from a counter as they finish (a second wave of whole warps would double the time)
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
+    const long long resident = (long long)std::max(1, per_sm) * h->n_sms;
+    if (grid > resident) {
+      grid = resident;
+      const int slot = h->ctl_next;
+      h->ctl_next = (slot + 1) % kCtlSlots;
+      CU(zero_words(h->ctl.p + 2 + slot, 1, st));
+      w.counter = h->ctl.p + 2 + slot;
+    }
+  }
   if (scratch != 0) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
     CU(h->gscratch[0].ensure((size_t)grid * kSolveThreads * per_lane));
     w.gscratch = h->gscratch[0].p;
     w.gstride = grid * kSolveThreads;
   }
-  CU(h->ctl.ensure(kCtlWords));
-  w.counter = nullptr;
   w.stats = h->ctl.p;
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
   if (debug) fprintf(stderr, "[i2lqr] chain launch: rungs %d lanes/chain %d scratch %d grid %lld smem %zu chains %lld\n", rungs, lanes_per_chain, scratch, grid, smem, w.n_items);
@@ -366,6 +386,16 @@ int sync_obstacles(i2lqr_handle* h) {
   return 0;
 }
 
+int stage_reserve(i2lqr_handle* h, size_t bytes) {
+  if (bytes <= h->stage_bytes) return 0;
+  if (h->stage) cudaFreeHost(h->stage);
+  h->stage = nullptr;
+  h->stage_bytes = 0;
+  CU(cudaMallocHost((void**)&h->stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+
 int knn_smem_config(i2lqr_handle* h, int* warps, size_t* smem) {
   // Tcap distances + Tcap ints (index array of the tie path), kept 8-byte aligned per warp
   const size_t per_warp = ((size_t)h->Tcap + ((size_t)h->Tcap + 1) / 2) * sizeof(double);
@@ -374,6 +404,58 @@ int knn_smem_config(i2lqr_handle* h, int* warps, size_t* smem) {
   *warps = w;
   *smem = per_warp * w;
   if (*smem > 48 * 1024) CU(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+  return 0;
+}
+
+// Streams, events and device buffers of a new handle; on failure the caller destroys the half-built handle.
+int create_resources(i2lqr_handle* h, const i2lqr_params* p, int n_episodes, int lap_capacity) {
+  h->E = n_episodes;
+  h->L = p->num_ss_iter;
+  h->K = p->num_ss_points;
+  h->Tcap = lap_capacity;
+  CU(cudaSetDevice(h->device));
+  // pipeline stream i carries chunk i of a host-pointer batch: earlier chunks get the higher priority so that their
+  // last passes are scheduled ahead of later chunks' first passes and their download starts early
+  int prio_least = 0, prio_greatest = 0;
+  CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  static const bool no_prio = getenv("I2LQR_NO_PRIO") != nullptr;  // tuning switch
+  auto pipe_priority = [&](int i) { return no_prio ? prio_least : std::min(prio_least, prio_greatest + i); };
+  CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, pipe_priority(0)));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreateWithFlags(&h->d2h_done, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
+  CU(cudaEventRecord(h->dev_done, h->stream));
+  CU(cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking));
+  for (int i = 0; i < i2lqr_handle::kMaxChunks; ++i) {
+    CU(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_solved[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < kAuxStreams; ++i) {
+    CU(cudaStreamCreateWithPriority(&h->aux[i], cudaStreamNonBlocking, pipe_priority(1 + i)));
+    CU(cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming));
+  }
+  CU(h->ctl.ensure(kCtlWords));
+  // initialisation goes through the handle's own (non-blocking) stream: a legacy-stream cudaMemset is not
+  // ordered against it and could land after the first add_lap / launch
+  CU(cudaMemsetAsync(h->ctl.p, 0, kCtlWords * sizeof(unsigned long long), h->stream));
+  if (n_episodes > 0) {
+    const size_t ss_n = (size_t)h->E * h->L * 4 * h->Tcap;
+    CU(cudaMalloc(&h->set.ss, ss_n * sizeof(double)));
+    CU(cudaMemsetAsync(h->set.ss, 0, ss_n * sizeof(double), h->stream));
+    CU(cudaMalloc(&h->set.lap_len, sizeof(int) * h->E * h->L));
+    CU(cudaMalloc(&h->set.lap_count, sizeof(int) * h->E));
+    CU(cudaMemsetAsync(h->set.lap_len, 0, sizeof(int) * h->E * h->L, h->stream));
+    CU(cudaMemsetAsync(h->set.lap_count, 0, sizeof(int) * h->E, h->stream));
+    h->set.L = h->L;
+    h->set.Tcap = h->Tcap;
+    h->h_lap_len.assign((size_t)h->E * h->L, 0);
+    h->h_lap_count.assign(h->E, 0);
+    DevObstacle none{};
+    h->h_obs.assign(h->E, none);
+  }
+  CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
@@ -424,6 +506,11 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
   if (!p || !out) return fail("null argument");
   if (p->precision != 0 && p->precision != 1) return fail("precision must be 0 (FP64) or 1 (FP32)");
   if (n_episodes < 0 || lap_capacity < 0) return fail("negative size");
+  if (n_episodes > 0 && lap_capacity <= p->num_horizon) return fail("lap_capacity must exceed num_horizon");
+  {
+    KParams probe;  // every argument check happens before the first allocation
+    if (make_kparams(*p, &probe)) return 1;
+  }
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -435,57 +522,14 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
   i2lqr_handle* h = new i2lqr_handle();
   h->device = device;
   h->n_sms = prop.multiProcessorCount;
-  if (make_kparams(*p, &h->kp)) {
-    delete h;
+  make_kparams(*p, &h->kp);
+  h->params = *p;
+  if (create_resources(h, p, n_episodes, lap_capacity)) {  // a CUDA failure half way: release what exists
+    const std::string err = g_err;
+    i2lqr_destroy(h);
+    g_err = err;
     return 1;
   }
-  h->params = *p;
-  h->E = n_episodes;
-  h->L = p->num_ss_iter;
-  h->K = p->num_ss_points;
-  h->Tcap = lap_capacity;
-  CU(cudaSetDevice(device));
-  // pipeline stream i carries chunk i of a host-pointer batch: earlier chunks get the higher priority so that their
-  // last passes are scheduled ahead of later chunks' first passes and their download starts early
-  int prio_least = 0, prio_greatest = 0;
-  CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-  static const bool no_prio = getenv("I2LQR_NO_PRIO") != nullptr;  // tuning switch
-  auto pipe_priority = [&](int i) { return no_prio ? prio_least : std::min(prio_least, prio_greatest + i); };
-  CU(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, pipe_priority(0)));
-  CU(cudaEventCreate(&h->ev0));
-  CU(cudaEventCreate(&h->ev1));
-  CU(cudaEventCreateWithFlags(&h->d2h_done, cudaEventDisableTiming));
-  CU(cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking));
-  for (int i = 0; i < i2lqr_handle::kMaxChunks; ++i) {
-    CU(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_solved[i], cudaEventDisableTiming));
-  }
-  for (int i = 0; i < kAuxStreams; ++i) {
-    CU(cudaStreamCreateWithPriority(&h->aux[i], cudaStreamNonBlocking, pipe_priority(1 + i)));
-    CU(cudaEventCreateWithFlags(&h->aux_done[i], cudaEventDisableTiming));
-  }
-  CU(h->ctl.ensure(kCtlWords));
-  // initialisation goes through the handle's own (non-blocking) stream: a legacy-stream cudaMemset is not
-  // ordered against it and could land after the first add_lap / launch
-  CU(cudaMemsetAsync(h->ctl.p, 0, kCtlWords * sizeof(unsigned long long), h->stream));
-  if (n_episodes > 0) {
-    if (lap_capacity <= p->num_horizon) return fail("lap_capacity must exceed num_horizon");
-    const size_t ss_n = (size_t)h->E * h->L * 4 * h->Tcap;
-    CU(cudaMalloc(&h->set.ss, ss_n * sizeof(double)));
-    CU(cudaMemsetAsync(h->set.ss, 0, ss_n * sizeof(double), h->stream));
-    CU(cudaMalloc(&h->set.lap_len, sizeof(int) * h->E * h->L));
-    CU(cudaMalloc(&h->set.lap_count, sizeof(int) * h->E));
-    CU(cudaMemsetAsync(h->set.lap_len, 0, sizeof(int) * h->E * h->L, h->stream));
-    CU(cudaMemsetAsync(h->set.lap_count, 0, sizeof(int) * h->E, h->stream));
-    h->set.L = h->L;
-    h->set.Tcap = h->Tcap;
-    h->h_lap_len.assign((size_t)h->E * h->L, 0);
-    h->h_lap_count.assign(h->E, 0);
-    DevObstacle none{};
-    h->h_obs.assign(h->E, none);
-  }
-  CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return 0;
 }
@@ -493,7 +537,7 @@ int i2lqr_create(const i2lqr_params* p, int device, int n_episodes, int lap_capa
 int i2lqr_destroy(i2lqr_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto* b : {&h->b_x0, &h->b_xt, &h->b_lamb, &h->b_uinit, &h->b_uvar, &h->b_xvar, &h->b_lamb_out, &h->s_x, &h->s_u,
                   &h->s_xpred, &h->s_upred, &h->s_cand_x, &h->s_cand_u, &h->s_cand_cost, &h->s_cand_lamb, &h->s_wcost,
                   &h->q_x0})
@@ -501,7 +545,9 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto* b : {&h->s_sel_idx, &h->s_widx, &h->q_idx}) b->release();
   for (auto* b : {&h->b_iters, &h->s_sel_cnt, &h->s_sel_cnt_own, &h->s_cand_iters, &h->s_wlap, &h->s_wrank, &h->s_shrink, &h->q_cnt}) b->release();
   for (auto* b : {&h->ep_upred, &h->ep_goal, &h->ep_lapx, &h->ep_lapu}) b->release();
-  for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen}) b->release();
+  for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_nrun, &h->ep_laplen, &h->ep_list, &h->ep_nep}) b->release();
+  for (auto& e : h->ep_ev)
+    if (e) cudaEventDestroy(e);
   h->d_obs0.release();
   for (auto& b : h->c_in) b.release();
   for (auto& b : h->c_out) b.release();
@@ -516,8 +562,9 @@ int i2lqr_destroy(i2lqr_handle* h) {
   if (h->set.ss) cudaFree(h->set.ss);
   if (h->set.lap_len) cudaFree(h->set.lap_len);
   if (h->set.lap_count) cudaFree(h->set.lap_count);
-  cudaEventDestroy(h->ev0);
-  cudaEventDestroy(h->ev1);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->dev_done) cudaEventDestroy(h->dev_done);
   if (h->d2h_done) cudaEventDestroy(h->d2h_done);
   for (int i = 0; i < i2lqr_handle::kMaxChunks; ++i) {
     if (h->ev_up[i]) cudaEventDestroy(h->ev_up[i]);
@@ -537,7 +584,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
     if (h->aux_done[i]) cudaEventDestroy(h->aux_done[i]);
     if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
   }
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
@@ -611,9 +658,15 @@ int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const
   if (check_batch_args(h, B, x0, x_term, obs, n_obs)) return 1;
   CU(cudaSetDevice(h->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  // A handle owns ONE set of scratch (parked candidates, the long-horizon slab, the statistics words): two calls on
+  // the same handle must not overlap even when the caller passes different streams, so each call starts behind
+  // the end of the previous one.  Callers that want overlapping batches use one handle per stream (bench.py).
+  CU(cudaStreamWaitEvent(st, h->dev_done, 0));
   if (begin_stats(h, st)) return 1;
   if (B > 0 && launch_flat(h, 0, B, x0, x_term, lamb_in, obs, n_obs, uvar_init, uvar, xvar, lamb_out, iters, st)) return 1;
-  return end_stats(h, st, false);
+  if (end_stats(h, st, false)) return 1;
+  CU(cudaEventRecord(h->dev_done, st));
+  return 0;
 }
 
 // Host-pointer form.  Uploads (one stream that only ever uploads), solves (a stream per chunk) and downloads (one
@@ -761,6 +814,71 @@ int i2lqr_add_lap(i2lqr_handle* h, int episode, const double* x, int T) {
   return 0;
 }
 
+namespace {
+// One thread per (episode, point): the staged lap (T,4) is transposed into every episode's next ring slot.
+__global__ void add_lap_all_kernel(SafeSet set, int E, const double* lap, int T) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)E * set.Tcap) return;
+  const int e = (int)(i / set.Tcap), j = (int)(i % set.Tcap);
+  const int count = set.lap_count[e];
+  const int slot = count % set.L;
+  double* dst = set.ss + ((size_t)e * set.L + slot) * 4 * (size_t)set.Tcap;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[(size_t)c * set.Tcap + j] = j < T ? lap[(size_t)j * 4 + c] : 0.0;
+}
+__global__ void add_lap_all_commit_kernel(SafeSet set, int E, int T) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int count = set.lap_count[e];
+  set.lap_len[(size_t)e * set.L + count % set.L] = T;
+  set.lap_count[e] = count + 1;
+}
+}  // namespace
+
+int i2lqr_add_lap_all(i2lqr_handle* h, const double* x, int T) {
+  if (!h) return fail("null handle");
+  if (h->E < 1) return fail("handle was created without episodes");
+  if (!x) return fail("null lap");
+  if (T <= h->kp.N) return fail("lap of %d points is not longer than the horizon %d (utils/base.py:348)", T, h->kp.N);
+  if (T > h->Tcap) return fail("lap of %d points exceeds lap_capacity %d", T, h->Tcap);
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  CU(h->c_in[0].ensure((size_t)T * 4));
+  if (stage_reserve(h, (size_t)T * 4 * sizeof(double))) return 1;
+  memcpy(h->stage, x, (size_t)T * 4 * sizeof(double));
+  CU(cudaMemcpyAsync(h->c_in[0].p, h->stage, (size_t)T * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const long long n = (long long)h->E * h->Tcap;
+  add_lap_all_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->set, h->E, h->c_in[0].p, T);
+  CU(cudaGetLastError());
+  add_lap_all_commit_kernel<<<(h->E + 127) / 128, 128, 0, st>>>(h->set, h->E, T);
+  CU(cudaGetLastError());
+  for (int e = 0; e < h->E; ++e) {
+    const int count = h->h_lap_count[e];
+    h->h_lap_len[(size_t)e * h->L + count % h->L] = T;
+    h->h_lap_count[e] = count + 1;
+  }
+  CU(cudaStreamSynchronize(st));  // the staging block is reused by the next call
+  return 0;
+}
+
+int i2lqr_set_obstacles(i2lqr_handle* h, int first, int n, const i2lqr_obstacle* obs) {
+  if (!h) return fail("null handle");
+  if (first < 0 || n < 0 || first + n > h->E) return fail("episodes [%d, %d) out of range [0,%d)", first, first + n, h->E);
+  for (int i = 0; i < n; ++i) {
+    DevObstacle o{};
+    if (obs) {
+      memcpy(&o, obs + i, sizeof o);
+      if (o.present && (o.moving_option < 0 || o.moving_option > 2)) return fail("episode %d: moving_option must be 0, 1 or 2", first + i);
+      if (o.present && o.moving_option == 0 && o.spd != 0.0)
+        return fail("episode %d: obstacle with spd != 0 needs moving_option 1 or 2 (control/ilqr_helper.py:34-43)", first + i);
+      if (!o.present) o = DevObstacle{};
+    }
+    h->h_obs[first + i] = o;
+  }
+  h->obs_dirty = true;
+  return 0;
+}
+
 int i2lqr_num_laps(i2lqr_handle* h, int episode, int* n_laps) {
   if (check_episode(h, episode)) return 1;
   if (n_laps) *n_laps = h->h_lap_count[episode];
@@ -839,9 +957,21 @@ int ensure_step_workspace(i2lqr_handle* h) {
   return 0;
 }
 
+// Which episodes a step's launches cover: the first n_episodes of the handle, or (batched closed loops) the
+// device-side compacted list of the episodes that solve this step -- n_episodes is then only the host's upper
+// bound of the list length, used to size the grids.
+struct StepScope {
+  int n_episodes;
+  const int* active = nullptr;
+  const int* ep_list = nullptr;
+  const int* n_ep = nullptr;
+};
+
 // One outer iteration of calc_input (utils/base.py:384-478) as three launches; the split form of the step
 // (i2lqr_split_*) calls them one by one with an exchange between K2 and K3.
-int launch_knn_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, cudaStream_t st) {
+int launch_knn_step(i2lqr_handle* h, int it, const StepScope& sc, cudaStream_t st) {
+  const int n_episodes = sc.n_episodes;
+  const int* d_active = sc.active;
   int warps;
   size_t smem;
   if (knn_smem_config(h, &warps, &smem)) return 1;
@@ -854,6 +984,8 @@ int launch_knn_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active
   ka.x_pred = h->s_xpred.p;
   ka.N = h->kp.N;
   ka.active = d_active;
+  ka.ep_list = sc.ep_list;
+  ka.n_ep = sc.n_ep;
   ka.sel_idx = h->s_sel_idx.p;
   ka.sel_cnt = h->s_sel_cnt.p;
   const long long n_warps = (long long)n_episodes * h->L;
@@ -865,10 +997,13 @@ int launch_knn_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active
 
 // `sel_cnt` = candidates per (episode, lap) the chains walk: the K-nearest counts, or a masked copy of them
 // when this handle only owns some of the laps.
-int launch_chain_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, const int* sel_cnt, cudaStream_t st) {
+int launch_chain_step(i2lqr_handle* h, int it, const StepScope& sc, const int* sel_cnt, cudaStream_t st) {
+  const int* d_active = sc.active;
   Work w{};
   w.mode = 1;
-  w.n_items = (long long)n_episodes * h->L;
+  w.n_items = (long long)sc.n_episodes * h->L;
+  w.ep_list = sc.ep_list;
+  w.n_ep = sc.n_ep;
   w.it = it;
   w.scale = it == 0 ? 1.0 : (it == 1 ? 10.0 : 100.0);  // 10**it, utils/base.py:428-435
   w.set = h->set;
@@ -885,8 +1020,12 @@ int launch_chain_step(i2lqr_handle* h, int it, int n_episodes, const int* d_acti
   return launch_chain(h, w, st);
 }
 
-int launch_winner_step(i2lqr_handle* h, int it, int n_episodes, const int* d_active, cudaStream_t st) {
+int launch_winner_step(i2lqr_handle* h, int it, const StepScope& sc, cudaStream_t st) {
+  const int n_episodes = sc.n_episodes;
+  const int* d_active = sc.active;
   WinnerArgs wa{};
+  wa.ep_list = sc.ep_list;
+  wa.n_ep = sc.n_ep;
   wa.n_episodes = n_episodes;
   wa.it = it;
   wa.L = h->L;
@@ -928,28 +1067,19 @@ int clear_step_trace(i2lqr_handle* h, cudaStream_t st) {
 }
 
 // The three outer iterations of calc_input on device-resident state x (E,4); results stay on the device.
-int run_step(i2lqr_handle* h, int n_episodes, const int* d_active, cudaStream_t st) {
+int run_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, bool clear_trace = true) {
   if (sync_obstacles(h)) return 1;
-  if (clear_step_trace(h, st)) return 1;
+  if (clear_trace && clear_step_trace(h, st)) return 1;
   for (int it = 0; it < kOuter; ++it) {
-    if (launch_knn_step(h, it, n_episodes, d_active, st)) return 1;
-    if (launch_chain_step(h, it, n_episodes, d_active, h->s_sel_cnt.p, st)) return 1;
-    if (launch_winner_step(h, it, n_episodes, d_active, st)) return 1;
+    if (launch_knn_step(h, it, sc, st)) return 1;
+    if (launch_chain_step(h, it, sc, h->s_sel_cnt.p, st)) return 1;
+    if (launch_winner_step(h, it, sc, st)) return 1;
   }
   return 0;
 }
 
 // The caller's arrays are ordinary (pageable) memory: the state goes up and the results come down through one
 // pinned staging block, so a controller-step call issues asynchronous copies only and blocks once.
-int stage_reserve(i2lqr_handle* h, size_t bytes) {
-  if (bytes <= h->stage_bytes) return 0;
-  if (h->stage) cudaFreeHost(h->stage);
-  h->stage = nullptr;
-  h->stage_bytes = 0;
-  CU(cudaMallocHost((void**)&h->stage, bytes));
-  h->stage_bytes = bytes;
-  return 0;
-}
 size_t step_result_bytes(i2lqr_handle* h, int n_episodes) {
   const size_t E = n_episodes, N = h->kp.N;
   return 16 * 9 + E * (2 + 4 * (N + 1) + 2 * N + 1) * sizeof(double) + E * 3 * sizeof(int) + E * sizeof(long long);
@@ -994,7 +1124,7 @@ int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u
   memcpy(h->stage, x, n_in);
   CU(cudaMemcpyAsync(h->s_x.p, h->stage, n_in, cudaMemcpyHostToDevice, st));
   if (begin_stats(h, st)) return 1;
-  if (run_step(h, n_episodes, nullptr, st)) return 1;
+  if (run_step(h, StepScope{n_episodes}, st)) return 1;
   CU(cudaEventRecord(h->ev1, st));
   return download_step_results(h, n_episodes, u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink,
                                (n_in + 15) / 16 * 16, st);
@@ -1080,12 +1210,12 @@ int i2lqr_split_solve(i2lqr_handle* h, int n_episodes, int it, int part, int n_p
   if (!rows_device) return fail("null exchange buffer");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-  if (launch_knn_step(h, it, n_episodes, nullptr, st)) return 1;
+  if (launch_knn_step(h, it, StepScope{n_episodes}, st)) return 1;
   const SplitArgs a = split_args(h, n_episodes, it, part, n_parts, rows_device);
   const int n_laps = n_episodes * h->L;
   split_mask_kernel<<<(n_laps + 127) / 128, 128, 0, st>>>(a);
   CU(cudaGetLastError());
-  if (launch_chain_step(h, it, n_episodes, nullptr, h->s_sel_cnt_own.p, st)) return 1;
+  if (launch_chain_step(h, it, StepScope{n_episodes}, h->s_sel_cnt_own.p, st)) return 1;
   split_pack_kernel<<<(n_laps * 32 + 127) / 128, 128, 0, st>>>(a);
   CU(cudaGetLastError());
   h->last_launches += 2;
@@ -1103,7 +1233,7 @@ int i2lqr_split_merge(i2lqr_handle* h, int n_episodes, int it, int part, int n_p
   split_unpack_kernel<<<(n_laps * 32 + 127) / 128, 128, 0, st>>>(a);
   CU(cudaGetLastError());
   h->last_launches += 1;
-  return launch_winner_step(h, it, n_episodes, nullptr, st);
+  return launch_winner_step(h, it, StepScope{n_episodes}, st);
 }
 
 int i2lqr_split_end(i2lqr_handle* h, int n_episodes, double* u, double* x_pred, double* u_pred, int32_t* winner_lap,
@@ -1310,7 +1440,11 @@ int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* go
   CU(h->ep_lapu.ensure(E * S * 2));
   for (auto* b : {&h->ep_step, &h->ep_done, &h->ep_horizon, &h->ep_pb, &h->ep_active, &h->ep_status, &h->ep_laplen}) CU(b->ensure(E));
   CU(h->ep_nrun.ensure(1));
-  if (!h->h_nrun) CU(cudaMallocHost(&h->h_nrun, sizeof(int)));
+  if (!h->h_nrun) {
+    CU(cudaHostAlloc((void**)&h->h_nrun, 2 * sizeof(int), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&h->h_nrun_dev, h->h_nrun, 0));
+    for (auto& e : h->ep_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   CU(cudaMemcpyAsync(h->s_x.p, x_init, E * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(h->ep_goal.p, goal, 4 * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(h->ep_step.p, 0, E * sizeof(int), st));
@@ -1346,22 +1480,41 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
   // row 0 of every lap log = the state the lap starts from
   CU(cudaMemcpy2DAsync(h->ep_lapx.p, (size_t)(S + 1) * 4 * sizeof(double), h->s_x.p, 4 * sizeof(double), 4 * sizeof(double), E,
                        cudaMemcpyDeviceToDevice, st));
-  *h->h_nrun = E;
+  CU(cudaMemsetAsync(h->ep_status.p, 0, (size_t)E * sizeof(int), st));  // status is per lap, not sticky
+  // Two words of mapped pinned memory carry [episodes still running, episodes that solve this step] back to the
+  // host after every step.  The host never waits for them: both only fall during a lap, so whatever (stale) value
+  // it reads is an upper bound -- enough to size the next step's grids and to stop issuing steps once every episode
+  // has finished.  No stream synchronisation inside the lap.
+  h->h_nrun[0] = E;
+  h->h_nrun[1] = E;
+  CU(h->ep_list.ensure((size_t)E));
+  CU(h->ep_nep.ensure(1));
   CU(cudaMemcpyAsync(h->ep_nrun.p, h->h_nrun, sizeof(int), cudaMemcpyHostToDevice, st));
   if (begin_stats(h, st)) return 1;
   const int tb = 128, gb = (E + tb - 1) / tb;
+  volatile int* hw = h->h_nrun;
+  int issued = 0;
+  static const int lookahead = getenv("I2LQR_EP_LOOKAHEAD") ? atoi(getenv("I2LQR_EP_LOOKAHEAD")) : 4;  // tuning switch
   for (int i = 0; i < S; ++i) {
-    episode_pre_kernel<<<gb, tb, 0, st>>>(es, E, N);
+    // at most `lookahead` steps in flight: a deeper queue would size many steps from the same stale counts
+    if (i >= lookahead) CU(cudaEventSynchronize(h->ep_ev[(i - lookahead) % i2lqr_handle::kEpEvents]));
+    if (hw[0] <= 0) break;
+    const int n_upper = std::min(E, std::max(1, (int)hw[1]));
+    CU(cudaMemsetAsync(h->ep_nep.p, 0, sizeof(int), st));
+    episode_pre_kernel<<<gb, tb, 0, st>>>(es, E, N, h->ep_list.p, h->ep_nep.p);
     CU(cudaGetLastError());
-    if (run_step(h, E, h->ep_active.p, st)) return 1;
+    StepScope sc{n_upper, nullptr, h->ep_list.p, h->ep_nep.p};
+    if (run_step(h, sc, st, false)) return 1;
     episode_post_kernel<<<gb, tb, 0, st>>>(es, h->kp, h->s_u.p, h->s_upred.p, h->s_shrink.p, E, i, h->params.goal_tol,
                                            h->ep_noise_seed, h->ep_lap_index);
     CU(cudaGetLastError());
-    h->last_launches += 2;
-    CU(cudaMemcpyAsync(h->h_nrun, h->ep_nrun.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (*h->h_nrun <= 0) break;
+    episode_publish_kernel<<<1, 1, 0, st>>>(h->ep_nrun.p, h->ep_nep.p, h->h_nrun_dev);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ep_ev[i % i2lqr_handle::kEpEvents], st));
+    h->last_launches += 3;
+    ++issued;
   }
+  (void)issued;
   episode_finish_kernel<<<(unsigned)(((long long)E * 32 + tb - 1) / tb), tb, 0, st>>>(es, h->set, E, N, h->ep_laplen.p);
   CU(cudaGetLastError());
   h->last_launches += 1;

@@ -63,6 +63,8 @@ struct Work {
   const double* x;             // (E,4) current states
   const DevObstacle* ep_obs;   // (E)
   const int* active;           // (E) or null: episodes that solve this step
+  const int* ep_list;          // compacted list of the episodes that solve this step, or null (= all n_items / L episodes)
+  const int* n_ep;             // device: entries of ep_list
   const long long* sel_idx;    // (E,3,L,K)
   const int* sel_cnt;          // (E,L)
   double* cand_x;              // (E,L,K,4,N+1)
@@ -387,8 +389,9 @@ chain_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
   const double* lap = nullptr;
   long long jsel = 0;
   unsigned long long my_iters = 0, my_solves = 0;
-  if (item < w.n_items) {
+  if (item < (w.n_ep != nullptr ? (long long)*w.n_ep * w.set.L : w.n_items)) {
     ep = (int)(item / w.set.L);
+    if (w.ep_list != nullptr) ep = w.ep_list[ep];  // batched episodes: only the ones that solve this step
     lrel = (int)(item % w.set.L);
     cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
     if (cnt > 0) {
@@ -512,29 +515,30 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
   constexpr int S = kSolveThreads;
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int rung = lane % kGroup;  // position in the group; a rung when < kRungs
-  const bool is_rung = rung < kRungs;
-  const int gbase_lane = lane - rung;
   const int N = p.N;
-  ChainLane<R, S> v;
-  v.col = smem + lane;
-  v.grp = smem + gbase_lane;
-  v.N = N;
-  v.rungs = kGroup;
-  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
-  CandT<R> c = {};
+  GroupSolver<R, kQR, kRungs, kGroup, S> gs;
+  gs.bind(smem, lane, N);
+  const int rung = gs.rung;
+  CandT<R>& c = gs.c;
+  // A chain is a work item.  Group g of the grid starts with chain g; when the launch has more chains than lane groups
+  // (batched episodes: the grid is capped at what is resident at once) a group that finishes its chain takes the next
+  // unassigned one from `w.counter`, so the chains' very different lengths average out instead of adding up per wave.
+  const long long n_groups = (long long)gridDim.x * (blockDim.x / kGroup);
+  const long long n_chains = w.n_ep != nullptr ? (long long)*w.n_ep * w.set.L : w.n_items;
+  long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kGroup;
   int state = ST_DONE;
   int rank = 0, cnt = 0, ep = 0, lrel = 0, T = 0;
   const double* lap = nullptr;
   long long jsel = 0;
   unsigned long long my_iters = 0, my_solves = 0;
-  int wb = 0;               // trial buffer this lane writes next
-  const R* cur = v.trial_of(0, 0);  // current trajectory of the group: some lane's trial buffer
-  bool dirty = true;        // the shared terms do not belong to `cur` yet
-  if (item < w.n_items) {
+  auto take = [&]() {  // binds the group to chain `item` (all lanes of the group hold the same item)
+    state = ST_DONE;
+    if (item >= n_chains) return false;
     ep = (int)(item / w.set.L);
+    if (w.ep_list != nullptr) ep = w.ep_list[ep];  // batched episodes: only the ones that solve this step
     lrel = (int)(item % w.set.L);
     cnt = (w.active == nullptr || w.active[ep]) ? w.sel_cnt[(size_t)ep * w.set.L + lrel] : 0;
+    rank = 0;
     if (cnt > 0) {
       const int count = w.set.lap_count[ep];
       const int min_iter = count - w.set.L > 0 ? count - w.set.L : 0;
@@ -548,101 +552,58 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
       sincos_fast(c.x0[3], &c.s0, &c.c0);
       state = ST_INIT;
     }
-  }
+    return true;
+  };
+  // next chain of this group: the static one first, then from the shared counter (which starts at n_groups);
+  // empty chains (unused lap slots) are skipped on the spot
+  auto next_chain = [&](bool first) {
+    for (;;) {
+      if (!first) {
+        if (w.counter == nullptr || n_chains <= n_groups) {
+          state = ST_DONE;
+          return;
+        }
+        unsigned long long nx = 0;
+        if (rung == 0) nx = atomicAdd(w.counter, 1ull);
+        constexpr unsigned kOne = kGroup >= 32 ? 0xffffffffu : ((1u << (kGroup & 31)) - 1u);
+        item = n_groups + (long long)__shfl_sync(kOne << gs.gbase_lane, nx, gs.gbase_lane);  // the group finished together
+      }
+      first = false;
+      if (!take()) return;           // no chain left
+      if (state == ST_INIT) return;  // bound to a chain with candidates
+    }
+  };
+  next_chain(true);
   for (;;) {
     if (__all_sync(kFull, state == ST_DONE)) break;
     if (state == ST_INIT) {
       jsel = w.sel_idx[(((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank];
 #pragma unroll
       for (int i = 0; i < 4; ++i) c.xt[i] = R(lap[(size_t)i * w.set.Tcap + jsel]);
-      c.J = chain_init<kQR, S>(p, c, rung == 0 ? v.trial(0) : nullptr);
-      c.iters = 0;
-      cur = v.trial_of(0, 0);
-      wb = rung == 0 ? 1 : 0;
-      dirty = true;
+      gs.start(p);
       state = ST_RUN;
     }
-    __syncwarp();
-    const bool run = state == ST_RUN;
-    if (run && dirty) chain_terms<kQR, S>(p, c, v, cur, rung);
-    __syncwarp();
-    R Jn = R(0.0), Jt = R(0.0);
-    if (run && is_rung) {
-      R lamb_r = c.lamb;
-      for (int r = 0; r < rung; ++r) lamb_r *= p.lamb_factor;  // the value r rejects lead to, same operations
-      chain_riccati<kQR, S>(p, v, lamb_r);
-      Jn = chain_forward<kQR, S>(p, c, cur, v.gains(), v.trial(wb), Jt);
-    }
-    __syncwarp();
-    const unsigned acc_all = __ballot_sync(kFull, run && is_rung && Jn < c.J);
-    const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
-    // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
-    int winner = -1;
-    bool fin = false;
-    int consumed = 0;
-    R lamb = c.lamb;
-    if (run) {
-#pragma unroll
-      for (int r = 0; r < kRungs; ++r) {
-        if (winner >= 0 || fin) break;
-        if (c.iters + consumed >= p.max_iter) {
-          fin = true;
-          break;
-        }
-        ++consumed;
-        if ((acc >> r) & 1u) {
-          winner = r;
-          lamb /= p.lamb_factor;
-        } else {
-          lamb *= p.lamb_factor;
-          if (lamb > p.max_lamb) fin = true;
-        }
-      }
-    }
-    const int src = winner >= 0 ? gbase_lane + winner : lane;
-    const R Jn_w = __shfl_sync(kFull, Jn, src), Jt_w = __shfl_sync(kFull, Jt, src);
-    const int wb_w = __shfl_sync(kFull, wb, src);
-    if (run) {
-      dirty = winner >= 0;
-      if (winner >= 0) {
-        cur = v.trial_of(winner, wb_w);  // the winner's trial is the current trajectory from here on
-        if (rung == winner) wb ^= 1;
-        if (rel_change_below(Jn_w, c.J, p.eps)) fin = true;
-        c.J = kQR ? Jt_w : Jn_w;
-      }
-      c.lamb = lamb;
-      c.iters += consumed;
-      if (c.iters >= p.max_iter) fin = true;
-    }
-    if (run && fin) {
+    if (gs.trip(p)) {
       const size_t cslot = ((size_t)ep * w.set.L + lrel) * p.K + rank;
       const size_t tslot = (((size_t)ep * kOuter + w.it) * w.set.L + lrel) * p.K + rank;
-      double* xv = w.cand_x + cslot * 4 * (N + 1);
-      double* uv = w.cand_u + cslot * 2 * N;
-      for (int k = rung; k < N; k += kGroup) {  // result in the reference's layout: xvar (4, N+1), uvar (2, N)
-        const R* s = cur + (size_t)(8 * k) * S;
-        uv[k] = (double)s[0];
-        uv[N + k] = (double)s[S];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i * (N + 1) + k + 1] = (double)s[(2 + i) * S];
-      }
+      gs.store(w.cand_x + cslot * 4 * (N + 1), w.cand_u + cslot * 2 * N);
       if (rung == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i * (N + 1)] = (double)c.x0[i];
         my_iters += (unsigned long long)c.iters;
         my_solves += 1;
         R xN[4];
-        const R* s = cur + (size_t)(8 * (N - 1)) * S;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) xN[i] = s[(2 + i) * S];
+        gs.terminal_state(xN);
         w.cand_cost[tslot] = relax_cost(p, xN, c.xt, (double)(T - 1 - jsel), w.scale);
         w.cand_lamb[tslot] = (double)c.lamb;
         w.cand_iters[tslot] = c.iters;
       }
       ++rank;
-      state = rank < cnt ? ST_INIT : ST_DONE;  // lambda is carried to the lap's next candidate
+      if (rank < cnt) {
+        state = ST_INIT;  // lambda is carried to the lap's next candidate
+      } else {
+        next_chain(false);
+      }
     }
-    __syncwarp();
+    __syncwarp();  // the finished trajectory is read above before the next candidate's start overwrites trial buffer 0
   }
   for (int o = 16; o > 0; o >>= 1) {
     my_iters += __shfl_xor_sync(kFull, my_iters, o);
@@ -773,6 +734,8 @@ struct KnnArgs {
   const double* x_pred;   // (E,4,N+1) previous winner          (outer iterations 1,2: its last column)
   int N;
   const int* active;      // (E) or null
+  const int* ep_list;     // compacted episode list or null
+  const int* n_ep;        // device: entries of ep_list
   long long* sel_idx;     // (E,3,L,K)
   int* sel_cnt;           // (E,L)
   // single-query form (i2lqr_select_knn): episode / absolute lap / explicit x0
@@ -803,8 +766,9 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
     out = a.q_idx;
     out_cnt = a.q_cnt;
   } else {
-    if (wid >= (long long)a.n_episodes * a.set.L) return;
+    if (wid >= (long long)(a.n_ep != nullptr ? *a.n_ep : a.n_episodes) * a.set.L) return;
     e = (int)(wid / a.set.L);
+    if (a.ep_list != nullptr) e = a.ep_list[e];
     lrel = (int)(wid % a.set.L);
     const int count = a.set.lap_count[e];
     const int n_act = count < a.set.L ? count : a.set.L;
@@ -900,6 +864,8 @@ struct WinnerArgs {
   const int* lap_count;
   const int* lap_len;      // (E,L)
   const int* active;
+  const int* ep_list;      // compacted episode list or null
+  const int* n_ep;         // device: entries of ep_list
   const int* sel_cnt;      // (E,L)
   const long long* sel_idx;
   const double* cand_cost; // (E,3,L,K)
@@ -918,9 +884,10 @@ struct WinnerArgs {
 
 __global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
   // one warp per episode: lane 0 decides, all lanes copy
-  const int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (e >= a.n_episodes) return;
+  if (e >= (a.n_ep != nullptr ? *a.n_ep : a.n_episodes)) return;
+  if (a.ep_list != nullptr) e = a.ep_list[e];
   if (a.active != nullptr && !a.active[e]) return;
   const int count = a.lap_count[e];
   const int n_act = count < a.L ? count : a.L;
@@ -1075,10 +1042,26 @@ struct EpisodeState {
   int* n_running;       // episodes whose lap is still running
 };
 
-__global__ void episode_pre_kernel(EpisodeState s, int E, int N_param) {
+// Also compacts the episodes that solve this step into `ep_list` (warp-aggregated append; the order is arbitrary and
+// does not matter, every episode's step is computed independently of where it sits in the list) and publishes the
+// counts to mapped host memory, which the host reads WITHOUT synchronising: both counts only fall during a lap, so
+// a stale value is an upper bound -- good enough to size the next launches and to stop issuing steps.
+__global__ void episode_pre_kernel(EpisodeState s, int E, int N_param, int* ep_list, int* n_ep) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  s.active[e] = (!s.done[e] && s.horizon[e] == N_param) ? 1 : 0;
+  const bool act = e < E && !s.done[e] && s.horizon[e] == N_param;
+  if (e < E) s.active[e] = act ? 1 : 0;
+  const unsigned m = __ballot_sync(0xffffffffu, act);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(n_ep, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (act) ep_list[base + __popc(m & ((1u << lane) - 1u))] = e;
+}
+__global__ void episode_publish_kernel(const int* n_running, const int* n_ep, volatile int* host_words) {
+  host_words[0] = *n_running;
+  host_words[1] = *n_ep;
+  __threadfence_system();
 }
 
 // Philox4x32-10 counter-based generator (Salmon et al. 2011): one 128-bit block per (episode, lap, step).

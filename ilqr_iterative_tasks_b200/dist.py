@@ -2,10 +2,10 @@
 
 The path partitions into independent units at three granularities:
   * flat candidates and whole episodes: contiguous block split, no data-path collective (`shard_range`);
-  * the laps of ONE controller step: each rank solves a subset of the active laps' lambda chains, then the
-    per-lap cost vectors (K doubles + K indices per lap, <= 4 KB at L=8, K=64) are all-gathered and every rank
-    applies the reference's lexicographic winner rule locally (`gather_lap_costs`, `lexicographic_winner`).
-    NCCL over NVLink when the tensors are CUDA tensors; gloo works for the CPU tests.
+  * the laps of ONE controller step: each rank solves a subset of the active laps' lambda chains, then one packed
+    row per lap (costs, lambdas, iteration counts, the lap's best trajectory) is all-gathered over NCCL and every
+    rank runs the same device-side winner kernel on the same table (`SplitStep`).  (A host-side model of that
+    exchange, used by the world-size-2 gloo test, lives in tests/host_exchange.py.)
 """
 import numpy as np
 
@@ -15,61 +15,6 @@ def shard_range(n_items, rank, world_size):
     base, rem = divmod(int(n_items), int(world_size))
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
-
-
-def lap_owner(n_active_laps, world_size):
-    """Round-robin owner rank of each active lap of one controller step."""
-    return [l % world_size for l in range(n_active_laps)]
-
-
-def lexicographic_winner(costs, counts):
-    """The reference's winner rule (iterative_ilqr/utils/base.py:462-465): `min(cost_list)` is Python's
-    lexicographic list comparison over per-lap cost vectors, then the first arg-min inside that lap.
-
-    costs (L,K) float array, counts (L,) valid entries per lap.  Returns (lap, rank).
-    """
-    best = 0
-    for l in range(1, len(counts)):
-        a, b = costs[l, : counts[l]], costs[best, : counts[best]]
-        n = min(len(a), len(b))
-        less = len(a) < len(b)
-        for i in range(n):
-            if a[i] != b[i]:
-                less = a[i] < b[i]
-                break
-        if less:
-            best = l
-    row = costs[best, : counts[best]]
-    rank = 0
-    for r in range(1, len(row)):
-        if row[r] < row[rank]:
-            rank = r
-    return best, rank
-
-
-def gather_lap_costs(local_costs, local_counts, owners, rank, group=None, device=None):
-    """All-gather of the per-lap (cost, count) rows when one step's laps span ranks.
-
-    local_costs (L,K): rows of laps this rank owns are filled, others ignored.  Every rank returns the full
-    (L,K) cost matrix and (L,) counts.  One all_gather of L*(K+1) doubles per outer iteration.
-    """
-    import torch
-    import torch.distributed as dist
-
-    L, K = local_costs.shape
-    payload = np.zeros((L, K + 1))
-    payload[:, :K] = local_costs
-    payload[:, K] = local_counts
-    t = torch.from_numpy(payload)
-    if device is not None:
-        t = t.to(device)
-    world = dist.get_world_size(group)
-    bucket = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(bucket, t, group=group)
-    full = np.zeros((L, K + 1))
-    for l in range(L):
-        full[l] = bucket[owners[l]][l].cpu().numpy()
-    return full[:, :K], full[:, K].astype(np.int64)
 
 
 class SplitStep:

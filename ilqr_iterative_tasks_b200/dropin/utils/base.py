@@ -16,7 +16,10 @@ What runs where
   * LMPC / NLMPC (reference :482-690, control/nonlinear_lmpc.py) are out of scope and raise
     NotImplementedError.
 
-Observable differences: the inner-loop prints ("k neighbors", "Convergence achieved") are dropped.  K-nearest
+Observable differences: the inner-loop prints ("k neighbors", "Convergence achieved") are dropped; the plotting
+methods are no-ops; the LMPC-only attributes of `iLqr` (`ss_point_selected_id`, `x_sol`, `u_sol`, `cost_improve`,
+`old_cost`, `old_iter`) are not kept; `max_outloop_iter < 3` raises ValueError (the reference would then do fewer
+refinements and never shrink the horizon).  K-nearest
 ties (the stock initial lap ends in identical rows) come out in the order numpy.argsort's scalar introsort leaves
 them -- what the reference's pinned numpy==1.19.5 does; a NumPy >= 1.25 on an AVX2 / AVX-512 host sorts float64
 with x86-simd-sort and orders ties differently (run the reference with NPY_DISABLE_CPU_FEATURES="AVX512F
@@ -38,11 +41,6 @@ from ilqr_iterative_tasks_b200 import _abi, engine  # noqa: E402
 from systems.kinetic_bicycle import kinetic_bicycle  # noqa: E402
 from utils.constants_kinetic_bicycle import *  # noqa: E402,F401,F403
 from utils.constants_kinetic_bicycle import U_DIM, U_ID, X_DIM, X_ID  # noqa: E402
-
-try:  # plotting is optional (out of scope); the reference imports pyplot at module load
-    import matplotlib.pyplot as plt  # noqa: F401
-except Exception:  # pragma: no cover
-    plt = None
 
 
 class KineticBicycleParam:
@@ -83,19 +81,7 @@ class Obstacle:
         self.states = np.array([self.x0, self.y0])
 
     def plot_obstacle(self):
-        if plt is None:
-            return
-        for count, centre in enumerate(self.data["state"][-1]):
-            if count % 5 == 0:
-                ang = np.linspace(0, 2 * np.pi, 1000)
-                plt.plot(
-                    centre[0] + self.width * np.cos(ang),
-                    centre[1] + self.height * np.sin(ang),
-                    "-k",
-                    label="Obstacle",
-                    linewidth=5,
-                    alpha=max(0, 1 - count / 90),
-                )
+        """Plotting is outside the accelerated path; kept as a no-op so that scripts calling it run."""
 
 
 class KineticBicycle:
@@ -152,6 +138,10 @@ class KineticBicycle:
             xcl[i + 1] = kinetic_bicycle(xcl[i], ucl[i], dt)
         if os.path.isdir("data"):
             np.savetxt("data/closed_loop_feasible.txt", xcl, fmt="%f")
+        if steps > 1:
+            # the reference logs `ucl = u` on step 0 -- an alias of the array it mutates on step 1 -- so its first
+            # logged input row shows step 1's input (reference :109-131); the states are unaffected
+            ucl[0] = ucl[1]
         self.xcl, self.ucl = xcl, ucl
 
     def set_ctrl_policy(self, ctrl_policy):
@@ -281,15 +271,13 @@ class iLqr(ControlBase):
         self.ilqr_param = ilqr_param
         self.system_param = system_param
         self.ss, self.u_ss, self.Qfun = [], [], []
-        self.ss_point_selected_id = []
         self.x_terminal_guess = None
         self.x_guess = None
         self.iter = 0
         self.iter_cost = []
         self.itCost = []
-        self.cost = self.old_cost = self.old_iter = None
+        self.cost = None
         self.u_old = self.x_pred = self.u_pred = None
-        self.cost_improve = None
         self.num_horizon = ilqr_param.num_horizon
         self.matrix_Qterminal = ilqr_param.matrix_Qterminal
         self.matrix_Q = ilqr_param.matrix_Q
@@ -350,21 +338,7 @@ class iLqr(ControlBase):
         self.x_terminal_guess = x.T[:, self.num_horizon]  # IndexError for laps shorter than the horizon, as :348
         self.cost = self.Qfun[-1][0]
         self.iter_cost.append(deepcopy(self.cost))
-        self.old_cost = self.cost + 1
-        self.old_iter = self.iter
-        self.x_sol = x.T[:, 0 : (self.num_horizon + 1)]
-        self.u_sol = u.T[:, 0 : self.num_horizon]
-        self.cost_improve = -1
-        self.iter += 1
-        min_cost = np.min(self.iter_cost)
-        self.ss_point_selected_id = []
-        for lap in range(self.iter):
-            lap_cost = self.ss[lap].shape[1] - 1
-            if self.ilqr_param.all_ss_point:
-                self.ss_point_selected_id.append(np.arange(0, self.ss[lap].shape[1]))
-            else:
-                start = lap_cost - min_cost + self.num_horizon
-                self.ss_point_selected_id.append(np.arange(start, start + self.ilqr_param.num_ss_points))
+        self.iter += 1  # (the reference's LMPC-only bookkeeping, :353-369, is not kept: nothing on the i2LQR path reads it)
         if x.shape[0] > self._capacity:
             while x.shape[0] > self._capacity:
                 self._capacity *= 2
@@ -383,6 +357,10 @@ class iLqr(ControlBase):
             self.u_old = self.u_pred[:, 1:]
             self.num_horizon -= 1
         else:
+            if int(param.max_outloop_iter) < 3:
+                # the reference loops range(max_outloop_iter) and only tests the horizon shrink / breaks at iter == 2
+                # (:384,:472-478); the device step is exactly those three outer iterations
+                raise ValueError("max_outloop_iter < 3 is not supported: the controller step runs the reference's three outer iterations")
             eng = self._sync_engine()
             eng.set_obstacle(0, _abi.obstacle_struct(self.obstacle) if self.obstacle is not None else None)
             self.x_guess = self.x
@@ -440,26 +418,10 @@ class Simulator:
                 break
 
     def plot_inputs(self):
-        if plt is None:
-            return
-        fig, axs = plt.subplots(2, figsize=(8, 7))
-        inputs = np.vstack(self.robotic.data["input"])
-        times = np.arange(0, len(inputs))
-        axs[0].plot(times, inputs[:, U_ID["accel"]], "-o", linewidth=1, markersize=1)
-        axs[1].plot(times, inputs[:, U_ID["delta"]], "-o", linewidth=1, markersize=1)
-        plt.show()
+        """No-op: plotting is outside the accelerated path (tests/ilqr_test.py:57-58 calls it unconditionally)."""
 
     def plot_simulation(self):
-        if plt is None:
-            return
-        fig, ax = plt.subplots()
-        obstacle = self.robotic.ctrl_policy.obstacle
-        if obstacle is not None:
-            obstacle.plot_obstacle()
-        last = self.robotic.data["state"][-1]
-        ax.plot(last[:, X_ID["x"]], last[:, X_ID["y"]], label="trajectory at last iteration")
-        ax.plot(self.robotic.xcl[:, X_ID["x"]], self.robotic.xcl[:, X_ID["y"]], label="initial trajectory")
-        plt.show()
+        """No-op, see plot_inputs."""
 
 
 class LMPCParam:

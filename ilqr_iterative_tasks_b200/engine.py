@@ -29,6 +29,7 @@ EXPORTS = [
     "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
     "i2lqr_split_end", "i2lqr_dynamics_batch", "i2lqr_linearize_batch", "i2lqr_cost_derivatives_batch",
     "i2lqr_cost_final_batch", "i2lqr_backward_pass_batch", "i2lqr_forward_pass_batch",
+    "i2lqr_add_lap_all", "i2lqr_set_obstacles",
 ]  # fmt: skip
 
 
@@ -154,6 +155,19 @@ class Engine:
     def add_lap(self, episode, x):
         x = _f64(x).reshape(-1, 4)
         _check(lib().i2lqr_add_lap(self._h, C.c_int(episode), _d(x), C.c_int(x.shape[0])))
+
+    def add_lap_all(self, x):
+        """The same lap appended to every episode's safe set (one upload)."""
+        x = _f64(x).reshape(-1, 4)
+        _check(lib().i2lqr_add_lap_all(self._h, _d(x), C.c_int(x.shape[0])))
+
+    def set_obstacles(self, obstacles, first=0):
+        """Obstacles of episodes [first, first + len(obstacles)) from a structured array (None clears all)."""
+        if obstacles is None:
+            _check(lib().i2lqr_set_obstacles(self._h, C.c_int(0), C.c_int(self.n_episodes), None))
+            return
+        arr = np.ascontiguousarray(obstacles, dtype=_abi.OBSTACLE_DTYPE)
+        _check(lib().i2lqr_set_obstacles(self._h, C.c_int(first), C.c_int(arr.shape[0]), C.c_void_p(arr.ctypes.data)))
 
     def num_laps(self, episode=0):
         n = C.c_int()

@@ -7,7 +7,7 @@ controller state never leave the device between steps.
 """
 import numpy as np
 
-from . import _abi, engine, synth
+from . import engine, synth
 
 
 class EpisodeBatch:
@@ -22,13 +22,9 @@ class EpisodeBatch:
         self.initial_lap = np.ascontiguousarray(initial_lap, dtype=np.float64)
         cap = lap_capacity or max(self.initial_lap.shape[0], params.max_sim_steps + 1)
         self.engine = engine.Engine(params, device=device, n_episodes=self.E, lap_capacity=cap)
-        for e in range(self.E):
-            self.engine.add_lap(e, self.initial_lap)
+        self.engine.add_lap_all(self.initial_lap)  # one upload, transposed into every episode's ring on the device
         if obstacles is not None:
-            obstacles = np.ascontiguousarray(obstacles, dtype=_abi.OBSTACLE_DTYPE)
-            for e in range(self.E):
-                o = _abi.Obstacle.from_buffer_copy(obstacles[e].tobytes())
-                self.engine.set_obstacle(e, o)
+            self.engine.set_obstacles(obstacles)
         self.engine.episodes_begin(x0, self.initial_lap[-1])
         if noise_seed:  # plant noise of utils/base.py:207-211 (off in every reference script)
             self.engine.episodes_set_noise(noise_seed)
@@ -36,11 +32,7 @@ class EpisodeBatch:
 
     def set_obstacles(self, obstacles):
         """Per-lap obstacle plan (e.g. obstacle only on one lap, result/ilqr_test_add_moving_obstacle.py:63-75)."""
-        for e in range(self.E):
-            if obstacles is None:
-                self.engine.set_obstacle(e, None)
-            else:
-                self.engine.set_obstacle(e, _abi.Obstacle.from_buffer_copy(np.ascontiguousarray(obstacles[e]).tobytes()))
+        self.engine.set_obstacles(obstacles)
 
     def run_lap(self, want_traj=False):
         """One lap for every episode.  Returns steps per episode (and the logged states / inputs)."""

@@ -94,7 +94,10 @@ int i2lqr_solve_batch(i2lqr_handle* h, int64_t B, const double* x0, const double
                       const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init, double* uvar, double* xvar,
                       double* lamb_out, int32_t* iters);
 /* Same, all pointers resident on the handle's device; runs on `cuda_stream` (NULL = the handle's stream)
- * and does not synchronise. */
+ * and does not synchronise the host.  ONE HANDLE PER STREAM: a handle owns a single set of device scratch
+ * (parked candidates, long-horizon slab, statistics words), so consecutive calls on the same handle are
+ * serialised on the device even when they are given different streams (each call waits for the previous
+ * call's end event).  Batches that should overlap go through separate handles. */
 int i2lqr_solve_batch_device(i2lqr_handle* h, int64_t B, const double* x0, const double* x_term,
                              const double* lamb_in, const i2lqr_obstacle* obs, int64_t n_obs, const double* uvar_init,
                              double* uvar, double* xvar, double* lamb_out, int32_t* iters, void* cuda_stream);
@@ -106,6 +109,12 @@ int i2lqr_add_lap(i2lqr_handle* h, int episode, const double* x, int T);
 int i2lqr_num_laps(i2lqr_handle* h, int episode, int* n_laps);
 /* `ilqr.obstacle = ...` (iterative_ilqr/result/ilqr_test_add_moving_obstacle.py:73-75); NULL = None. */
 int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs);
+/* Batched forms for many-episode handles (one host-to-device copy instead of one per episode):
+ * the same lap appended to EVERY episode's safe set (what each reference script does with the scripted first lap,
+ * iterative_ilqr/tests/ilqr_test.py:49), and the obstacles of episodes [first, first+n) in one call
+ * (obs == NULL clears them). */
+int i2lqr_add_lap_all(i2lqr_handle* h, const double* x, int T);
+int i2lqr_set_obstacles(i2lqr_handle* h, int first, int n, const i2lqr_obstacle* obs);
 /* Replaces iLqr.select_close_ss (iterative_ilqr/utils/base.py:332-341): 1-norm K-nearest points of stored
  * lap `lap` (absolute lap number, as the reference's `iter` argument) in ascending (distance, index) order.
  * Writes min(K, T) indices and that count. */

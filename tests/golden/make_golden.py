@@ -386,6 +386,7 @@ def make_components():
         Vx, Vxx = np.zeros((B, 4)), np.zeros((B, 4, 4))
         gk, gK = np.zeros((B, 2, N)), np.zeros((B, 2, 4, N))
         xn, un, cn = np.zeros((B, 4, N + 1)), np.zeros((B, 2, N)), np.zeros(B)
+        cc_b, cc_bdd = np.zeros((B, N, 2)), np.zeros((B, N, 2, 2))  # add_control_constraint per stage (ilqr_helper.py:83-103)
         for b in range(B):
             # a trajectory as ilqr() holds it mid-solve: clipped inputs, states rolled out with the model
             u = rng.standard_normal((2, N)) * np.array([[0.8], [0.25]])
@@ -403,15 +404,26 @@ def make_components():
             Bm[b] = sysmod.get_B_matrix(x[3, 1:], N, 1)
             l_u[b], l_uu[b], l_x[b], l_xx[b] = helper.get_cost_derivation(u, dX, param, N, x, obstacle, sysp)
             Vx[b], Vxx[b] = helper.get_cost_final(x, xt, param.matrix_Qterminal, obstacle, param)
+            for k in range(N):
+                bd, bdd = helper.add_control_constraint(u[:, k], param, sysp)
+                cc_b[b, k], cc_bdd[b, k] = np.asarray(bd)[:, 0], np.asarray(bdd)
             gk[b], gK[b] = mod._pristine[0](x, u, xt, dX, float(lamb[b]), N, 1, param, obstacle, sysp)
             xn[b], un[b], cn[b] = mod.forward_pass(x, u, xt, param, 1, N, gk[b], gK[b], sysp)
         has_obs = np.array([1 if b % 5 else 0 for b in range(B)], dtype=np.int32)
         g = name + "/"
         for k, v in dict(N=np.int32(N), x_term=data["x_term"], obs=data["obs"], mode=data["mode"], has_obs=has_obs, lamb=lamb,
                          Q=np.zeros((4, 4)) if Q is None else Q, R=np.zeros((2, 2)) if R is None else R, xvar=xvar, uvar=uvar, A=A, B=Bm,
-                         l_u=l_u, l_uu=l_uu, l_x=l_x, l_xx=l_xx, Vx=Vx, Vxx=Vxx, k=gk, K=gK, xvar_new=xn, uvar_new=un, cost_new=cn).items():  # fmt: skip
+                         l_u=l_u, l_uu=l_uu, l_x=l_x, l_xx=l_xx, cc_b=cc_b, cc_bdd=cc_bdd, Vx=Vx, Vxx=Vxx, k=gk, K=gK, xvar_new=xn, uvar_new=un, cost_new=cn).items():  # fmt: skip
             out[g + k] = v
     out["groups"] = np.array([g[0] for g in groups])
+    # the scripted first lap as KineticBicycle.get_traj logs it (utils/base.py:103-138): states and the input log,
+    # whose first row aliases the array the loop mutates on step 1
+    ego = base.KineticBicycle(False, system_param=sysp)
+    ego.set_state(np.zeros(4))
+    ego.set_timestep(1)
+    with ref.quiet():
+        ego.get_traj()
+    out["traj/xcl"], out["traj/ucl"] = np.array(ego.xcl), np.array(ego.ucl)
     np.savez_compressed(os.path.join(HERE, "components.npz"), **out)
     ref.close()
     print("components done")

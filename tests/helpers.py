@@ -36,6 +36,17 @@ def rel_err(a, ref):
     return np.abs(a - ref).max(axis=ax) / np.maximum(1.0, np.abs(ref).max(axis=ax))
 
 
+def same_discrete_path(out_iters, out_lamb, ref_iters, ref_lamb, what):
+    """Mask of candidates whose discrete path (executed iterations, lambda_out bit for bit) equals the oracle's /
+    reference's.  north_star asks for exact iteration counts and lambda, so the divergence count is printed (pytest -s /
+    the captured-output section) and must be ZERO: a flipped accept / reject would need |J_new - J| within an ulp."""
+    same = (np.asarray(out_iters) == np.asarray(ref_iters)) & (np.asarray(out_lamb) == np.asarray(ref_lamb))
+    n_div = int((~same).sum())
+    print("[parity] %s: discrete path diverged for %d of %d candidates" % (what, n_div, same.size))
+    assert n_div == 0, "%s: discrete path diverged for %d of %d candidates (first: %s)" % (what, n_div, same.size, np.flatnonzero(~same)[:8])
+    return same
+
+
 def step_obstacle(g, s):
     mode = int(g["step/mode"][s])
     if mode < 0:

@@ -24,18 +24,16 @@ from ilqr_iterative_tasks_b200 import engine  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
 
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+def run_check(rank, world, local, max_parity_steps=None):
+    """The check itself, inside an initialised NCCL process group (bench.py calls it for the `split_step` object of
+    its JSON line).  Returns the result dict on every rank; raises AssertionError on any bit difference."""
     g = H.load("steps_k64.npz")
     p = H.step_params(g)
     whole = engine.Engine(p, device=local, n_episodes=1, lap_capacity=128)
     part = engine.Engine(p, device=local, n_episodes=1, lap_capacity=128)
     split = D.SplitStep(part, rank, world, n_episodes=1)
     added, t_whole, t_split, checked = 0, [], [], 0
-    for s in g["solve_ids"]:
+    for s in list(g["solve_ids"])[:max_parity_steps]:
         n_laps = int(g["step/n_laps"][s])
         while added < n_laps:
             whole.add_lap(0, g["lap%d" % added])
@@ -84,12 +82,25 @@ def main():
         t_split.append(t3 - t2)
         checked += 1
     dist.barrier()
+    out = {
+        "check": "split controller step (i2lqr_split_*, lap rows exchanged with ncclAllGather) == single-GPU i2lqr_solve_step, bit for bit, outputs and per-candidate trace",
+        "bit_identical": True, "world_size": world, "steps_checked": checked,
+        "K": int(g["K"]), "L_parity": int(g["L"]), "L_latency": 8, "row_doubles": split8.row, "allgather_bytes_per_rank": int(split8.rows.numel() * 8),
+        "p50_ms_single_gpu": round(1e3 * float(np.median(t_whole)), 3), "p50_ms_split": round(1e3 * float(np.median(t_split)), 3),
+    }  # fmt: skip
+    for e in (whole, part, whole8, part8):
+        e.close()
+    return out
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = run_check(rank, world, local)
     if rank == 0:
-        print(json.dumps({
-            "check": "split controller step == single-GPU step, bit for bit", "world_size": world, "steps_checked": checked,
-            "K": int(g["K"]), "L_parity": int(g["L"]), "L_latency": 8, "row_doubles": split8.row, "allgather_bytes_per_rank": int(split8.rows.numel() * 8),
-            "p50_ms_single_gpu": round(1e3 * float(np.median(t_whole)), 3), "p50_ms_split": round(1e3 * float(np.median(t_split)), 3),
-        }))  # fmt: skip
+        print(json.dumps(out))
         print("OK")
     dist.destroy_process_group()
 

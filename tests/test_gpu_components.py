@@ -92,6 +92,21 @@ def test_backward_and_forward_pass(eng_mod, grp):
     e.close()
 
 
+@pytest.mark.parametrize("grp", GROUPS)
+def test_control_constraint_vs_reference_golden(eng_mod, grp):
+    """add_control_constraint (control/ilqr_helper.py:83-103) against the reference's own outputs (`cc_b`, `cc_bdd`, one
+    call per stage input): the input-barrier gradient / Hessian is what l_u / l_uu are when matrix_R = 0."""
+    g = H.load("components.npz")
+    N = int(g[grp + "/N"])
+    e = eng_mod.Engine(_abi.default_params(num_horizon=N))  # matrix_Q = matrix_R = 0
+    u = g[grp + "/uvar"]
+    B = u.shape[0]
+    l_u, l_uu, _, _ = e.cost_derivatives(u, np.zeros((B, 4, N + 1)), np.zeros((B, 4, N + 1)), None)
+    _close(l_u.transpose(0, 2, 1), g[grp + "/cc_b"])
+    _close(l_uu.transpose(0, 3, 1, 2), g[grp + "/cc_bdd"])
+    e.close()
+
+
 def test_component_error_paths(eng_mod):
     p = _abi.default_params()
     p.precision = 1  # the component entry points exist in FP64 only
@@ -138,11 +153,15 @@ for b in (0, 1, 2, 7):
     close(k, g[grp + "/k"][b]); close(K, g[grp + "/K"][b])
     xn, un, cn = forward_pass(x, u, xt, param, 1, N, g[grp + "/k"][b], g[grp + "/K"][b], sysp)
     close(xn, g[grp + "/xvar_new"][b]); close(un, g[grp + "/uvar_new"][b]); close(cn, g[grp + "/cost_new"][b])
-    bd, bdd = add_control_constraint(u[:, 0], param, sysp)
-    zero = base.iLqrParam(num_ss_points=8, num_ss_iter=1, timestep=1, num_horizon=N)
-    lu0, luu0, _, _ = get_cost_derivation(u, x.copy(), zero, N, x, None, sysp)
-    assert bd.shape == (2, 1) and bdd.shape == (2, 2)
-    close(bd[:, 0], lu0[:, 0]); close(bdd, luu0[:, :, 0])
+    for k in (0, N - 1):
+        bd, bdd = add_control_constraint(u[:, k], param, sysp)
+        assert bd.shape == (2, 1) and bdd.shape == (2, 2)
+        close(bd[:, 0], g[grp + "/cc_b"][b, k]); close(bdd, g[grp + "/cc_bdd"][b, k])  # the reference's own outputs
+# the scripted first lap and its input log (utils/base.py:103-138), first-row aliasing quirk included
+ego = base.KineticBicycle(False, system_param=sysp)
+ego.set_state([0, 0, 0, 0]); ego.set_timestep(1); ego.get_traj()
+assert np.array_equal(ego.ucl, g["traj/ucl"]), (ego.ucl[:3], g["traj/ucl"][:3])
+close(ego.xcl, g["traj/xcl"])
 print("OK")
 """
 

@@ -10,6 +10,9 @@ import pytest
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
+# Closed loops: rounding differences grow along a lap, so the bar is absolute on states of magnitude <= ~120 (1e-8 here
+# is ~1e-10 relative; measured: 6e-10 over the recorded runs).  Discrete outcomes (lap lengths, winners) are exact.
+CLOSED_LOOP_ATOL = 1e-8
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 _SCRIPT = r"""
@@ -81,15 +84,18 @@ def test_dropin_closed_loop_stock_scenario():
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT")][0][6:])
     assert res["lens"] == res["ref_lens"], res
-    assert res["max_abs_err"] < 1e-6, res
+    assert res["max_abs_err"] < CLOSED_LOOP_ATOL, res
     assert res["knn_ok"] and res["l1_lamb_ok"] and res["l1_err"] < 1e-9 * 50, res
     assert res["pickle_ok"], res
 
 
-@pytest.mark.parametrize("name", ["stock", "moving_up"])
+@pytest.mark.parametrize("name", ["stock", "moving_up", "moving_left", "static_big", "k64", "add_static", "add_up", "add_left"])
 def test_episode_batch_matches_reference_closed_loop(name):
     """K4: device-resident closed loop for several identical episodes == the reference's lap lengths and
-    trajectories (closed-loop tolerance)."""
+    trajectories (closed-loop tolerance).  The add_* scenarios are the batched, device-side form of the reference's
+    scenario drivers (result/ilqr_test_add_static_obstacle.py:50-59, result/ilqr_test_add_moving_obstacle.py:63-75):
+    the obstacle appears on lap 5 of a converged run and is removed again on lap 6 -- a per-lap obstacle plan
+    handed to `EpisodeBatch.set_obstacles` between laps."""
     from ilqr_iterative_tasks_b200 import _abi, episodes
 
     g = H.load("steps_%s.npz" % name)
@@ -115,8 +121,8 @@ def test_episode_batch_matches_reference_closed_loop(name):
         assert (eb.status() == 0).all()
         for e in range(E):
             got = lx[e, : len(ref)]
-            assert np.abs(got - ref).max() < 1e-6, (lap, e, np.abs(got - ref).max())
-            assert np.abs(lu[e, : len(ref) - 1] - g["lap_inputs%d" % (lap + 1)]).max() < 1e-6
+            assert np.abs(got - ref).max() < CLOSED_LOOP_ATOL, (lap, e, np.abs(got - ref).max())
+            assert np.abs(lu[e, : len(ref) - 1] - g["lap_inputs%d" % (lap + 1)]).max() < CLOSED_LOOP_ATOL
     eb.close()
 
 
@@ -141,7 +147,7 @@ def test_episode_batch_random_scenarios_vs_oracle():
             lens, lx = got[lap]
             assert lens[e] == len(ref[lap + 1]) - 1, (e, lap, lens[e], len(ref[lap + 1]) - 1)
             err = np.abs(lx[e, : lens[e] + 1] - ref[lap + 1]).max()
-            assert err < 1e-6, (e, lap, err)
+            assert err < CLOSED_LOOP_ATOL, (e, lap, err)
 
 
 def test_episode_noise_is_bounded_and_reproducible():

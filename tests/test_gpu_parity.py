@@ -51,9 +51,7 @@ def test_flat_batch_vs_oracle_sample(eng_mod):
     e = eng_mod.Engine(p)
     out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
     u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
-    same = (out["iters"] == iters) & (out["lamb_out"] == lamb)
-    # a chaotic iteration may flip an accept/reject on a last-bit difference of sin/cos/exp; none expected here
-    assert same.mean() >= 0.999, "discrete path diverged for %d of 4096" % int((~same).sum())
+    same = H.same_discrete_path(out["iters"], out["lamb_out"], iters, lamb, "config-5 sample, 4096 candidates")
     ex = H.rel_err(out["xvar"][same], x[same]).max()
     eu = H.rel_err(out["uvar"][same], u[same]).max()
     assert ex <= H.RTOL and eu <= H.RTOL
@@ -75,8 +73,7 @@ def test_flat_batch_mid_horizons_vs_oracle(eng_mod, N):
     out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
     e.close()
     u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8)
-    same = (out["iters"] == iters) & (out["lamb_out"] == lamb)
-    assert same.mean() >= 0.999, "discrete path diverged for %d of %d" % (int((~same).sum()), B)
+    same = H.same_discrete_path(out["iters"], out["lamb_out"], iters, lamb, "tensor-memory variant, N=%d" % N)
     assert H.rel_err(out["xvar"][same], x[same]).max() <= H.RTOL
     assert H.rel_err(out["uvar"][same], u[same]).max() <= H.RTOL
 
@@ -95,8 +92,7 @@ def test_flat_batch_size_boundaries(eng_mod):
     e = eng_mod.Engine(p)
     for B in (1, 31, 33, 127, 129, 8191, 8192, 8193, 131071, 131072, Bmax):
         out = e.solve_batch(d["x0"][:B], d["x_term"][:B], d["lamb_in"][:B], obs[:B])
-        same = (out["iters"] == iters[:B]) & (out["lamb_out"] == lamb[:B])
-        assert same.mean() >= 0.999, (B, int((~same).sum()))
+        same = H.same_discrete_path(out["iters"], out["lamb_out"], iters[:B], lamb[:B], "batch size %d" % B)
         assert H.rel_err(out["xvar"][same], x[:B][same]).max() <= H.RTOL, B
         assert H.rel_err(out["uvar"][same], u[:B][same]).max() <= H.RTOL, B
         assert e.last_stats()["solves"] == B
@@ -140,8 +136,7 @@ def test_host_pipeline_long_horizon(eng_mod):
         assert np.array_equal(out[k], again[k]), k
     sel = np.random.default_rng(3).choice(B, 4096, replace=False)
     u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"][sel], d["x_term"][sel], d["lamb_in"][sel], obs[sel], nthreads=8)
-    same = (out["iters"][sel] == iters) & (out["lamb_out"][sel] == lamb)
-    assert same.mean() >= 0.999
+    same = H.same_discrete_path(out["iters"][sel], out["lamb_out"][sel], iters, lamb, "host pipeline, N=16")
     assert H.rel_err(out["xvar"][sel][same], x[same]).max() <= H.RTOL
     assert e.last_stats()["solves"] == B
     e.close()
@@ -440,8 +435,7 @@ def test_full_size_properties(eng_mod):
     long_ids = np.flatnonzero(a["iters"] >= 32)[:3000]
     sel = np.unique(np.concatenate([long_ids, np.random.default_rng(2).choice(B, 3000, replace=False)]))
     u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"][sel], d["x_term"][sel], d["lamb_in"][sel], obs[sel], nthreads=8)
-    same = (a["iters"][sel] == iters) & (a["lamb_out"][sel] == lamb)
-    assert same.mean() >= 0.999, "discrete path diverged for %d of %d" % (int((~same).sum()), len(sel))
+    same = H.same_discrete_path(a["iters"][sel], a["lamb_out"][sel], iters, lamb, "2^20-candidate batch, parked-heavy sample")
     assert H.rel_err(a["xvar"][sel][same], x[same]).max() <= H.RTOL
     assert H.rel_err(a["uvar"][sel][same], u[same]).max() <= H.RTOL
     assert (a["iters"][sel] >= 32).sum() >= 2000 and a["iters"].max() == p.max_ilqr_iter

@@ -12,6 +12,7 @@ import pytest
 
 from ilqr_iterative_tasks_b200 import _abi, dist, engine, synth
 from tests import helpers as H
+from tests import host_exchange as X
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -102,13 +103,13 @@ def test_lexicographic_winner_rule():
     inf = np.inf
     # lexicographic lap choice differs from the global minimum
     costs = np.array([[106.0, 205.0, 104.0, inf], [106.0, 206.0, 100.0, 100.0]])
-    assert dist.lexicographic_winner(costs, [4, 4]) == (0, 2)
+    assert X.lexicographic_winner(costs, [4, 4]) == (0, 2)
     # a prefix is smaller; first arg-min within the lap
     costs = np.array([[5.0, 5.0, 1.0, 1.0], [5.0, 5.0, 0.0, 0.0]])
-    assert dist.lexicographic_winner(costs, [4, 2]) == (1, 0)
-    assert dist.lexicographic_winner(np.array([[3.0, 2.0, 2.0]]), [3]) == (0, 1)
+    assert X.lexicographic_winner(costs, [4, 2]) == (1, 0)
+    assert X.lexicographic_winner(np.array([[3.0, 2.0, 2.0]]), [3]) == (0, 1)
     # ties between laps: the first lap wins
-    assert dist.lexicographic_winner(np.array([[1.0, 2.0], [1.0, 2.0]]), [2, 2]) == (0, 0)
+    assert X.lexicographic_winner(np.array([[1.0, 2.0], [1.0, 2.0]]), [2, 2]) == (0, 0)
 
 
 def test_winner_rule_agrees_with_oracle_on_golden_steps():
@@ -121,7 +122,7 @@ def test_winner_rule_agrees_with_oracle_on_golden_steps():
         out = oracle.calc_input(p, laps[: int(g["step/n_laps"][s])], g["step/x"][s], H.step_obstacle(g, s))
         n_act = min(int(g["step/n_laps"][s]), p.num_ss_iter)
         counts = [(out["sel_idx"][2, l] >= 0).sum() for l in range(n_act)]
-        lap, rank = dist.lexicographic_winner(out["cand_cost"][2, :n_act], counts)
+        lap, rank = X.lexicographic_winner(out["cand_cost"][2, :n_act], counts)
         first = max(0, int(g["step/n_laps"][s]) - p.num_ss_iter)
         assert (lap + first, rank) == (out["winner_lap"], out["winner_rank"])
 
@@ -133,6 +134,7 @@ import numpy as np, torch, torch.distributed as td
 from ilqr_iterative_tasks_b200 import dist, _abi
 from oracle import oracle
 from tests import helpers as H
+from tests import host_exchange as X
 td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
 rank = td.get_rank()
 g = H.load("steps_k64.npz")
@@ -141,7 +143,7 @@ s = int(g["solve_ids"][-3])
 laps = [g["lap%d" % i] for i in range(int(g["step/n_laps"][s]))]
 full = oracle.calc_input(p, laps, g["step/x"][s], H.step_obstacle(g, s))
 n_act = min(len(laps), p.num_ss_iter)
-owners = dist.lap_owner(n_act, 2)
+owners = X.lap_owner(n_act, 2)
 # each rank "solves" only the laps it owns (the oracle stands in for the device here), then the exchange
 local = np.full((n_act, p.num_ss_points), np.nan)
 counts = np.zeros(n_act)
@@ -149,8 +151,8 @@ for l in range(n_act):
     if owners[l] == rank:
         local[l] = full["cand_cost"][2, l]
         counts[l] = (full["sel_idx"][2, l] >= 0).sum()
-costs, cnt = dist.gather_lap_costs(local, counts, owners, rank)
-lap, r = dist.lexicographic_winner(costs, cnt)
+costs, cnt = X.gather_lap_costs(local, counts, owners, rank)
+lap, r = X.lexicographic_winner(costs, cnt)
 first = max(0, len(laps) - p.num_ss_iter)
 assert (lap + first, r) == (full["winner_lap"], full["winner_rank"]), (lap, r)
 lo, hi = dist.shard_range(1000, rank, 2)

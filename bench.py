@@ -227,11 +227,14 @@ def latency_probe(device, max_seconds=60.0):
             eng.solve_step(x.reshape(1, 4))
             times.append((time.perf_counter() - t1) * 1e3)
             solves.append(eng.last_stats()["solves"])
+    spec = eng.spec_stats()
     eng.close()
     times = np.array(times[len(states):])  # first pass = warm-up
     return {
         "p50_ms": float(np.percentile(times, 50)), "p90_ms": float(np.percentile(times, 90)), "steps_timed": int(times.size),
         "solves_per_step": float(np.mean(solves)), "stored_laps": len(laps[-8:]),
+        "speculation": {"hit_rate": spec["hit_rate"], "counters": spec,
+                        "note": "one-launch step (spec_step.cuh): candidates served from speculative solves whose lambda_in matched bit for bit"},
         "workload": "BASELINE config 2: one controller step (state in -> u, x_pred, u_pred on host), K=64, L=8, stock scenario",
         "reference_cpu_p50_ms": 9100.0, "reference_note": "Python reference, 1 core, build container (BASELINE.md)",
     }  # fmt: skip

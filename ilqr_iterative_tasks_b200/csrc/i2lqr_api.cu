@@ -14,6 +14,7 @@
 
 #include "../../include/i2lqr.h"
 #include "kernels.cuh"
+#include "spec_step.cuh"
 #include "components.cuh"
 #include "kparams.h"
 
@@ -129,6 +130,13 @@ struct i2lqr_handle {
   DevBuf<int> s_sel_cnt_own;
   DevBuf<int> s_sel_cnt, s_cand_iters, s_wlap, s_wrank, s_shrink, q_cnt;
   DevBuf<double> q_x0;
+  // speculative one-launch controller step (spec_step.cuh)
+  DevBuf<unsigned> sp_state, sp_ctl, sp_hist_cnt;
+  DevBuf<double> sp_lamb, sp_cost, sp_traj;
+  DevBuf<int> sp_iters;
+  DevBuf<unsigned long long> sp_walked, sp_hist_key, sp_set, sp_stats;
+  int sp_cmax = 0, sp_K = 0, sp_S = 0, sp_E = 0, sp_N = 0;
+  unsigned sp_epoch = 0;
   // component entry points (components.cuh): grow-only staging
   DevBuf<double> c_in[6], c_out[4], c_scratch;
   DevBuf<DevObstacle> c_obs;
@@ -549,6 +557,10 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto& e : h->ep_ev)
     if (e) cudaEventDestroy(e);
   h->d_obs0.release();
+  for (auto* b : {&h->sp_state, &h->sp_ctl, &h->sp_hist_cnt}) b->release();
+  for (auto* b : {&h->sp_lamb, &h->sp_cost, &h->sp_traj}) b->release();
+  h->sp_iters.release();
+  for (auto* b : {&h->sp_walked, &h->sp_hist_key, &h->sp_set, &h->sp_stats}) b->release();
   for (auto& b : h->c_in) b.release();
   for (auto& b : h->c_out) b.release();
   h->c_scratch.release();
@@ -1020,20 +1032,14 @@ int launch_chain_step(i2lqr_handle* h, int it, const StepScope& sc, const int* s
   return launch_chain(h, w, st);
 }
 
-int launch_winner_step(i2lqr_handle* h, int it, const StepScope& sc, cudaStream_t st) {
-  const int n_episodes = sc.n_episodes;
-  const int* d_active = sc.active;
+// fields of WinnerArgs that do not depend on the launch
+void fill_winner_args(i2lqr_handle* h, WinnerArgs* out) {
   WinnerArgs wa{};
-  wa.ep_list = sc.ep_list;
-  wa.n_ep = sc.n_ep;
-  wa.n_episodes = n_episodes;
-  wa.it = it;
   wa.L = h->L;
   wa.K = h->K;
   wa.N = h->kp.N;
   wa.lap_count = h->set.lap_count;
   wa.lap_len = h->set.lap_len;
-  wa.active = d_active;
   wa.sel_cnt = h->s_sel_cnt.p;
   wa.sel_idx = h->s_sel_idx.p;
   wa.cand_cost = h->s_cand_cost.p;
@@ -1047,6 +1053,18 @@ int launch_winner_step(i2lqr_handle* h, int it, const StepScope& sc, cudaStream_
   wa.winner_idx = h->s_widx.p;
   wa.winner_cost = h->s_wcost.p;
   wa.shrink = h->s_shrink.p;
+  *out = wa;
+}
+
+int launch_winner_step(i2lqr_handle* h, int it, const StepScope& sc, cudaStream_t st) {
+  const int n_episodes = sc.n_episodes;
+  WinnerArgs wa;
+  fill_winner_args(h, &wa);
+  wa.ep_list = sc.ep_list;
+  wa.n_ep = sc.n_ep;
+  wa.n_episodes = n_episodes;
+  wa.it = it;
+  wa.active = sc.active;
   const int wthreads = 128;
   const size_t wsmem = (size_t)(wthreads / 32) * h->L * h->K * sizeof(double);
   wa.stage_costs = wsmem <= 48 * 1024;
@@ -1066,9 +1084,155 @@ int clear_step_trace(i2lqr_handle* h, cudaStream_t st) {
   return 0;
 }
 
+// ---- speculative one-launch step (spec_step.cuh)
+constexpr int kSpecMaxChains = 64;
+
+bool spec_enabled() {
+  static const bool on = !(getenv("I2LQR_SPEC") && atoi(getenv("I2LQR_SPEC")) == 0);  // tuning / A-B switch
+  return on;
+}
+int spec_set_size() {
+  static const int s = getenv("I2LQR_SPEC_S") ? std::max(1, std::min(kSpecMaxSet, atoi(getenv("I2LQR_SPEC_S")))) : 24;  // tuning switch
+  return s;
+}
+size_t spec_smem_bytes(const i2lqr_handle* h) {
+  const int N = h->kp.N;
+  const size_t solver = (size_t)kSolveThreads * std::max(chain_lane_elems(N, 32), chain_lane_elems(N, kSpecWorkerGroup)) * sizeof(double);
+  const size_t knn = ((size_t)h->Tcap + ((size_t)h->Tcap + 1) / 2) * sizeof(double);
+  return std::max(solver, knn);
+}
+// The one-launch form serves controller steps with few chains (one controller, a handful of episodes, the tail of a
+// batched lap): FP64, chains that fit one warp's shared memory, a table of at most 2^16 speculative entries.
+bool spec_eligible(const i2lqr_handle* h, int n_episodes) {
+  if (!spec_enabled() || h->params.precision != 0) return false;
+  const long long chains = (long long)n_episodes * h->L;
+  if (chains < 1 || chains > kSpecMaxChains || h->K < 2) return false;
+  if (spec_smem_bytes(h) > 100 * 1024) return false;
+  return chains * (h->K - 1) * spec_set_size() <= (1 << 16);
+}
+
+// lambda values reachable from lamb0 by the iteration's own /factor and *factor steps, breadth first (same
+// operations, same doubles): the histogram's seed.  The first launches refine it from what the chains really see.
+void spec_seed_patterns(const i2lqr_params& p, std::vector<unsigned long long>* keys) {
+  std::vector<double> seen{p.lamb}, frontier{p.lamb};
+  while (!frontier.empty() && (int)seen.size() < kSpecHist) {
+    std::vector<double> next;
+    for (double v : frontier)
+      for (double w : {v * p.lamb_factor, v / p.lamb_factor}) {
+        if (!std::isfinite(w) || w == 0.0 || w > p.max_lamb * p.lamb_factor * 1.5) continue;
+        if (std::find(seen.begin(), seen.end(), w) != seen.end()) continue;
+        seen.push_back(w);
+        next.push_back(w);
+      }
+    frontier.swap(next);
+  }
+  keys->assign(kSpecHist, kSpecUnused);
+  for (size_t i = 0; i < seen.size() && i < (size_t)kSpecHist; ++i) memcpy(&(*keys)[i], &seen[i], 8);
+}
+
+int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
+  const int chains = n_episodes * h->L, S = spec_set_size(), K = h->K, N = h->kp.N;
+  const bool first = h->sp_hist_key.p == nullptr;
+  if (first) {
+    CU(h->sp_hist_key.ensure(kSpecHist));
+    CU(h->sp_hist_cnt.ensure(kSpecHist));
+    CU(h->sp_set.ensure(kSpecMaxSet));
+    CU(h->sp_stats.ensure(8));
+    std::vector<unsigned long long> keys;
+    spec_seed_patterns(h->params, &keys);
+    std::vector<unsigned> cnt(kSpecHist, 0u);
+    for (int i = 0; i < kSpecHist; ++i) cnt[i] = keys[i] == kSpecUnused ? 0u : (unsigned)(kSpecHist - i);  // breadth-first order = initial ranking
+    CU(cudaMemcpyAsync(h->sp_hist_key.p, keys.data(), kSpecHist * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->sp_hist_cnt.p, cnt.data(), kSpecHist * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->sp_set.p, keys.data(), kSpecMaxSet * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->sp_stats.p, 0, 8 * 8, st));
+    CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
+  }
+  if (chains > h->sp_cmax || K != h->sp_K || S != h->sp_S || n_episodes > h->sp_E || N != h->sp_N) {
+    const int cmax = std::max(chains, h->sp_cmax), E = std::max(n_episodes, h->sp_E);
+    const size_t entries = (size_t)kOuter * cmax * K * S;
+    CU(h->sp_state.ensure(entries));
+    CU(h->sp_lamb.ensure(entries));
+    CU(h->sp_cost.ensure(entries));
+    CU(h->sp_iters.ensure(entries));
+    CU(h->sp_traj.ensure(entries * (size_t)(6 * N + 4)));
+    const size_t ctl_words = 8 + (size_t)kOuter * cmax + 2 * (size_t)kOuter * E;
+    CU(h->sp_ctl.ensure(ctl_words));
+    CU(h->sp_walked.ensure((size_t)kOuter * cmax));
+    // a new layout invalidates every stamp: clear once (steady-state launches clear nothing)
+    CU(cudaMemsetAsync(h->sp_state.p, 0, h->sp_state.n * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(h->sp_ctl.p, 0, h->sp_ctl.n * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(h->sp_walked.p, 0, h->sp_walked.n * sizeof(unsigned long long), st));
+    h->sp_cmax = cmax;
+    h->sp_E = E;
+    h->sp_K = K;
+    h->sp_S = S;
+    h->sp_N = N;
+  }
+  return 0;
+}
+
+int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
+  if (spec_ensure(h, sc.n_episodes, st)) return 1;
+  const KParams& kp = h->kp;
+  SpecArgs a{};
+  a.n_episodes = sc.n_episodes;
+  a.e_stride = h->sp_E;
+  a.ep_list = sc.ep_list;
+  a.n_ep = sc.n_ep;
+  a.set = h->set;
+  a.x = h->s_x.p;
+  a.ep_obs = h->d_obs.p;
+  a.S = h->sp_S;
+  a.c_max = h->sp_cmax;
+  a.sel_idx = h->s_sel_idx.p;
+  a.sel_cnt = h->s_sel_cnt.p;
+  a.cand_x = h->s_cand_x.p;
+  a.cand_u = h->s_cand_u.p;
+  a.cand_cost = h->s_cand_cost.p;
+  a.cand_lamb = h->s_cand_lamb.p;
+  a.cand_iters = h->s_cand_iters.p;
+  fill_winner_args(h, &a.win);
+  a.item_state = h->sp_state.p;
+  a.item_lamb = h->sp_lamb.p;
+  a.item_cost = h->sp_cost.p;
+  a.item_iters = h->sp_iters.p;
+  a.item_traj = h->sp_traj.p;
+  h->sp_epoch = h->sp_epoch >= (1u << 29) ? 1u : h->sp_epoch + 1u;
+  a.epoch = h->sp_epoch;
+  a.ctl = h->sp_ctl.p;
+  a.ready = h->sp_ctl.p + 8;
+  a.arrived = a.ready + (size_t)kOuter * h->sp_cmax;
+  a.iter_done = a.arrived + (size_t)kOuter * h->sp_E;
+  a.walked = h->sp_walked.p;
+  a.hist_key = h->sp_hist_key.p;
+  a.hist_cnt = h->sp_hist_cnt.p;
+  a.spec_set = h->sp_set.p;
+  a.step_stats = h->ctl.p;
+  a.stats = h->sp_stats.p;
+  const void* kern = kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
+  const size_t smem = spec_smem_bytes(h);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
+  if (per_sm < 1) return fail("speculative step kernel does not fit on an SM");
+  const long long chains = (long long)sc.n_episodes * h->L;
+  const long long workers = std::max<long long>(1, (chains * (h->K - 1) * h->sp_S + 7) / 8);
+  const long long grid = std::min<long long>((long long)per_sm * h->n_sms, chains + workers);
+  if (grid <= chains) return fail("internal: no room for worker warps");
+  static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
+  if (debug) fprintf(stderr, "[i2lqr] spec step: chains %lld S %d grid %lld smem %zu per_sm %d epoch %u\n", chains, h->sp_S, grid, smem, per_sm, a.epoch);
+  void* args[2] = {(void*)&kp, (void*)&a};
+  CU(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kSolveThreads), args, smem, st));
+  h->last_launches += 1;
+  return 0;
+}
+
 // The three outer iterations of calc_input on device-resident state x (E,4); results stay on the device.
 int run_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, bool clear_trace = true) {
   if (sync_obstacles(h)) return 1;
+  if (sc.active == nullptr && spec_eligible(h, sc.n_episodes)) return launch_spec_step(h, sc, st);  // one launch, no memsets
   if (clear_trace && clear_step_trace(h, st)) return 1;
   for (int it = 0; it < kOuter; ++it) {
     if (launch_knn_step(h, it, sc, st)) return 1;
@@ -1544,6 +1708,19 @@ int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int6
   if (launches) *launches = h->last_launches;
   if (ilqr_iterations) *ilqr_iterations = h->last_iters;
   if (solves) *solves = h->last_solves;
+  return 0;
+}
+
+// Cumulative counters of the speculative one-launch controller step (spec_step.cuh) since the handle was created.
+int i2lqr_spec_stats(i2lqr_handle* h, int64_t* counters8) {
+  if (!h || !counters8) return fail("null argument");
+  for (int i = 0; i < 8; ++i) counters8[i] = 0;
+  if (!h->sp_stats.p) return 0;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  unsigned long long v[8];
+  CU(cudaMemcpy(v, h->sp_stats.p, sizeof v, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 8; ++i) counters8[i] = (int64_t)v[i];
   return 0;
 }
 

@@ -745,52 +745,18 @@ struct KnnArgs {
   int* q_cnt;
 };
 
-__global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
-  extern __shared__ double dist_smem[];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  // per warp: Tcap distances, then Tcap ints for the tie path's index array
-  double* dist = dist_smem + (size_t)wib * (a.set.Tcap + (a.set.Tcap + 1) / 2);
-  int* order = reinterpret_cast<int*>(dist + a.set.Tcap);
-  const long long wid = (long long)blockIdx.x * warps_per_block + wib;
-  int e, lrel, slot;
-  double g[4];
-  long long* out;
-  int* out_cnt;
-  if (a.q_x0 != nullptr) {
-    if (wid != 0) return;
-    e = a.q_episode;
-    slot = a.q_lap % a.set.L;
-    lrel = 0;
-    for (int i = 0; i < 4; ++i) g[i] = a.q_x0[i];
-    out = a.q_idx;
-    out_cnt = a.q_cnt;
-  } else {
-    if (wid >= (long long)(a.n_ep != nullptr ? *a.n_ep : a.n_episodes) * a.set.L) return;
-    e = (int)(wid / a.set.L);
-    if (a.ep_list != nullptr) e = a.ep_list[e];
-    lrel = (int)(wid % a.set.L);
-    const int count = a.set.lap_count[e];
-    const int n_act = count < a.set.L ? count : a.set.L;
-    out_cnt = a.sel_cnt + (size_t)e * a.set.L + lrel;
-    if (lrel >= n_act || (a.active != nullptr && !a.active[e])) {
-      if (lane == 0) *out_cnt = 0;
-      return;
-    }
-    const int min_iter = count - a.set.L > 0 ? count - a.set.L : 0;
-    slot = (min_iter + lrel) % a.set.L;
-    for (int i = 0; i < 4; ++i)  // x_guess: utils/base.py:398-401
-      g[i] = a.it == 0 ? a.x[(size_t)e * 4 + i] : a.x_pred[((size_t)e * 4 + i) * (a.N + 1) + a.N];
-    out = a.sel_idx + (((size_t)e * kOuter + a.it) * a.set.L + lrel) * a.K;
-  }
-  const int T = a.set.lap_len[(size_t)e * a.set.L + slot];
-  const double* lap = a.set.lap(e, slot);
-  const size_t Tc = a.set.Tcap;
+// K-nearest selection of one (episode, lap slot) by one warp; `dist` holds Tcap doubles and `order` Tcap ints of
+// (shared) scratch.  Writes the indices in rank order to out[0..K) (-1 beyond the lap's length) and the count.
+__device__ __forceinline__ void knn_warp(const SafeSet& set, int K, int e, int slot, const double (&g)[4], long long* out, int* out_cnt,
+                                         double* dist, int* order, int lane) {
+  const int T = set.lap_len[(size_t)e * set.L + slot];
+  const double* lap = set.lap(e, slot);
+  const size_t Tc = set.Tcap;
   for (int j = lane; j < T; j += 32)
     dist[j] = ((fabs(lap[j] - g[0]) + fabs(lap[Tc + j] - g[1])) + fabs(lap[2 * Tc + j] - g[2])) +
               fabs(lap[3 * Tc + j] - g[3]);
   __syncwarp();
-  const int n = a.K < T ? a.K : T;
+  const int n = K < T ? K : T;
   bool tie = false;
   if (T <= kKnnCountLimit) {
     // Short laps (every lap of the reference's scenarios): rank by counting.  Element j's rank in the order
@@ -809,7 +775,7 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
       }
       const int rank = below + equal_before;
       if (d == d && rank < n) out[rank] = j;  // (a NaN distance never ranks; the arg-min rounds below skip it as well)
-      tie = tie || (equal_all > 1 && below < a.K && below + 1 < T);
+      tie = tie || (equal_all > 1 && below < K && below + 1 < T);
     }
     tie = __any_sync(0xffffffffu, tie);
   } else {
@@ -851,8 +817,49 @@ __global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
   }
   if (lane == 0) {
     *out_cnt = n;
-    for (int r = n; r < a.K; ++r) out[r] = -1;
+    for (int r = n; r < K; ++r) out[r] = -1;
   }
+}
+
+__global__ void knn_kernel(const __grid_constant__ KnnArgs a) {
+  extern __shared__ double dist_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  // per warp: Tcap distances, then Tcap ints for the tie path's index array
+  double* dist = dist_smem + (size_t)wib * (a.set.Tcap + (a.set.Tcap + 1) / 2);
+  int* order = reinterpret_cast<int*>(dist + a.set.Tcap);
+  const long long wid = (long long)blockIdx.x * warps_per_block + wib;
+  int e, lrel, slot;
+  double g[4];
+  long long* out;
+  int* out_cnt;
+  if (a.q_x0 != nullptr) {
+    if (wid != 0) return;
+    e = a.q_episode;
+    slot = a.q_lap % a.set.L;
+    lrel = 0;
+    for (int i = 0; i < 4; ++i) g[i] = a.q_x0[i];
+    out = a.q_idx;
+    out_cnt = a.q_cnt;
+  } else {
+    if (wid >= (long long)(a.n_ep != nullptr ? *a.n_ep : a.n_episodes) * a.set.L) return;
+    e = (int)(wid / a.set.L);
+    if (a.ep_list != nullptr) e = a.ep_list[e];
+    lrel = (int)(wid % a.set.L);
+    const int count = a.set.lap_count[e];
+    const int n_act = count < a.set.L ? count : a.set.L;
+    out_cnt = a.sel_cnt + (size_t)e * a.set.L + lrel;
+    if (lrel >= n_act || (a.active != nullptr && !a.active[e])) {
+      if (lane == 0) *out_cnt = 0;
+      return;
+    }
+    const int min_iter = count - a.set.L > 0 ? count - a.set.L : 0;
+    slot = (min_iter + lrel) % a.set.L;
+    for (int i = 0; i < 4; ++i)  // x_guess: utils/base.py:398-401
+      g[i] = a.it == 0 ? a.x[(size_t)e * 4 + i] : a.x_pred[((size_t)e * 4 + i) * (a.N + 1) + a.N];
+    out = a.sel_idx + (((size_t)e * kOuter + a.it) * a.set.L + lrel) * a.K;
+  }
+  knn_warp(a.set, a.K, e, slot, g, out, out_cnt, dist, order, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -882,26 +889,19 @@ struct WinnerArgs {
   int stage_costs;         // 1: dynamic shared memory holds (warps per block) x L x K doubles
 };
 
-__global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
-  // one warp per episode: lane 0 decides, all lanes copy
-  int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (e >= (a.n_ep != nullptr ? *a.n_ep : a.n_episodes)) return;
-  if (a.ep_list != nullptr) e = a.ep_list[e];
-  if (a.active != nullptr && !a.active[e]) return;
+// Winner of episode e in outer iteration a.it, by one warp; `stage` = L*K doubles of shared scratch or null.
+__device__ __forceinline__ void winner_warp(const WinnerArgs& a, int e, int lane, double* stage) {
   const int count = a.lap_count[e];
   const int n_act = count < a.L ? count : a.L;
   const int min_iter = count - a.L > 0 ? count - a.L : 0;
   int bl = 0, br = 0;
   // The rule below is a chain of dependent reads (a comparison stops at the first differing element), ~1 us each from
   // global memory; when the step's cost table fits, all lanes first copy it to shared memory in one parallel sweep.
-  extern __shared__ double winner_smem[];
   const double* cost = a.cand_cost + ((size_t)e * kOuter + a.it) * a.L * a.K;
-  if (a.stage_costs) {
-    double* mine = winner_smem + (size_t)(threadIdx.x >> 5) * a.L * a.K;
-    for (int i = lane; i < n_act * a.K; i += 32) mine[i] = cost[i];
+  if (stage != nullptr) {
+    for (int i = lane; i < n_act * a.K; i += 32) stage[i] = cost[i];
     __syncwarp();
-    cost = mine;
+    cost = stage;
   }
   if (lane == 0) {
     const int* cnt = a.sel_cnt + (size_t)e * a.L;
@@ -936,6 +936,17 @@ __global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
   for (int i = lane; i < nx; i += 32) a.x_pred[(size_t)e * nx + i] = a.cand_x[cslot * nx + i];
   for (int i = lane; i < nu; i += 32) a.u_pred[(size_t)e * nu + i] = a.cand_u[cslot * nu + i];
   if (lane < 2) a.u[(size_t)e * 2 + lane] = a.cand_u[cslot * nu + (size_t)lane * a.N];
+}
+
+__global__ void winner_kernel(const __grid_constant__ WinnerArgs a) {
+  // one warp per episode: lane 0 decides, all lanes copy
+  int e = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (e >= (a.n_ep != nullptr ? *a.n_ep : a.n_episodes)) return;
+  if (a.ep_list != nullptr) e = a.ep_list[e];
+  if (a.active != nullptr && !a.active[e]) return;
+  extern __shared__ double winner_smem[];
+  winner_warp(a, e, lane, a.stage_costs ? winner_smem + (size_t)(threadIdx.x >> 5) * a.L * a.K : nullptr);
 }
 
 // ------------------------------------------------------------------------------- split controller step

@@ -29,7 +29,7 @@ EXPORTS = [
     "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
     "i2lqr_split_end", "i2lqr_dynamics_batch", "i2lqr_linearize_batch", "i2lqr_cost_derivatives_batch",
     "i2lqr_cost_final_batch", "i2lqr_backward_pass_batch", "i2lqr_forward_pass_batch",
-    "i2lqr_add_lap_all", "i2lqr_set_obstacles",
+    "i2lqr_add_lap_all", "i2lqr_set_obstacles", "i2lqr_spec_stats",
 ]  # fmt: skip
 
 
@@ -324,6 +324,16 @@ class Engine:
         st = np.empty(self.n_episodes, dtype=np.int32)
         _check(lib().i2lqr_episodes_status(self._h, st.ctypes.data_as(_i32p)))
         return st
+
+    def spec_stats(self):
+        """Cumulative counters of the speculative one-launch controller step (include/i2lqr.h, i2lqr_spec_stats)."""
+        v = (C.c_int64 * 8)()
+        _check(lib().i2lqr_spec_stats(self._h, v))
+        names = ("hits", "waited", "self_solved", "misses", "spec_finished", "spec_abandoned", "launches")
+        out = {k: int(v[i]) for i, k in enumerate(names)}
+        served = out["hits"] + out["waited"] + out["self_solved"] + out["misses"]
+        out["hit_rate"] = (out["hits"] + out["waited"]) / served if served else None
+        return out
 
     # -- instrumentation -------------------------------------------------------------------------------
     def last_stats(self):

@@ -219,6 +219,15 @@ int i2lqr_forward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, con
                              const double* k, const double* K, double* xvar_new, double* uvar_new, double* cost_new);
 
 /* ---- instrumentation -------------------------------------------------------------------------------- */
+/* Controller steps with few lambda chains (one controller, a few episodes) run as ONE launch in which idle SMs solve
+ * the chains' candidates ahead of time for the most likely incoming lambda values; the chain takes a precomputed result
+ * only when its lambda matches bit for bit, so results are identical to the sequential chain
+ * (iterative_ilqr/utils/base.py:391-426).  Cumulative counters since i2lqr_create:
+ *   [0] candidates served from a finished speculative solve  [1] served after waiting for one in flight
+ *   [2] in the speculation set but not started: solved in place  [3] lambda not in the set: solved in place
+ *   [4] speculative solves finished  [5] abandoned  [6] one-launch steps  [7] reserved */
+int i2lqr_spec_stats(i2lqr_handle* h, int64_t* counters8);
+
 /* Device time (CUDA events on the stream of the call) of the last compute call, the number of kernels it
  * launched, and the iLQR iterations / solves it executed (device-side counters, for the roofline).  For
  * i2lqr_solve_batch the time spans the whole chunked pipeline (copies included); for the *_device form and

@@ -276,6 +276,11 @@ def test_controller_step_kernel_variants_agree():
         {"I2LQR_CHAIN_LAT": "0"}, {"I2LQR_CHAIN_LAT": "0", "I2LQR_RUNGS": "1"}, {"I2LQR_CHAIN_LAT": "0", "I2LQR_SCRATCH": "1"},
     ]  # fmt: skip
     for env in variants:
+        env["I2LQR_SPEC"] = "0"  # the three-kernel form of the step (one controller would otherwise take the one-launch form)
+    # the speculative one-launch form (spec_step.cuh) with speculation sets of 1 / 8 / 24 (default) / 32 lambda values:
+    # hits, waits and misses fall differently in each, the results may not
+    variants += [{"I2LQR_SPEC_S": "1"}, {"I2LQR_SPEC_S": "8"}, {"I2LQR_SPEC_S": "24"}, {"I2LQR_SPEC_S": "32"}]
+    for env in variants:
         full = dict(os.environ)
         full.update(env)
         out = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT.format(root=root)], capture_output=True, text=True, timeout=600, env=full)
@@ -287,6 +292,31 @@ def test_controller_step_kernel_variants_agree():
     gen = {d for k, d in digests.items() if ("I2LQR_CHAIN_LAT", "0") in k}
     assert len(lat) == 1, digests
     assert len(gen) == 1, digests
+
+
+def test_speculative_step_reports_hits(eng_mod):
+    """The one-launch controller step serves most candidates from speculative solves once its lambda histogram has
+    seen a few steps (K=64 recorded run); counters are consistent with the number of candidates walked."""
+    g = H.load("steps_k64.npz")
+    p = H.step_params(g)
+    e = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+    added, walked = 0, 0
+    for si, s in enumerate(g["solve_ids"]):
+        while added < int(g["step/n_laps"][s]):
+            e.add_lap(0, g["lap%d" % added])
+            added += 1
+        e.set_obstacle(0, H.step_obstacle(g, s))
+        e.solve_step(g["step/x"][s].reshape(1, 4))
+        walked += int((g["solve/c_iters"][si] >= 0).sum())
+    st = e.spec_stats()
+    e.close()
+    print("[spec] %s" % st)
+    if st["launches"] == 0:
+        pytest.skip("speculative step disabled (I2LQR_SPEC=0)")
+    assert st["launches"] == len(g["solve_ids"])
+    n_first = 3 * sum(min(int(g["step/n_laps"][s]), p.num_ss_iter) for s in g["solve_ids"])  # rank-0 candidates: always solved in place
+    assert st["hits"] + st["waited"] + st["self_solved"] + st["misses"] == walked - n_first
+    assert st["hit_rate"] > 0.6, st
 
 
 def test_multi_episode_step_equals_single(eng_mod):

@@ -220,18 +220,21 @@ def latency_probe(device, max_seconds=60.0):
         eng.add_lap(0, lp)
     eng.set_obstacle(0, _abi.Obstacle(31.0, -3.0, 8.0, 6.0, 0.0, 0, 1))
     states = laps[-1][:-6]  # the solve steps of the last lap
-    times, solves = [], []
+    times, solves, dev_ms = [], [], []
     for rep in range(3):
         for x in states:
             t1 = time.perf_counter()
             eng.solve_step(x.reshape(1, 4))
             times.append((time.perf_counter() - t1) * 1e3)
-            solves.append(eng.last_stats()["solves"])
+            st = eng.last_stats()
+            solves.append(st["solves"])
+            dev_ms.append(st["kernel_ms"])
     spec = eng.spec_stats()
     eng.close()
     times = np.array(times[len(states):])  # first pass = warm-up
     return {
         "p50_ms": float(np.percentile(times, 50)), "p90_ms": float(np.percentile(times, 90)), "steps_timed": int(times.size),
+        "device_p50_ms": float(np.percentile(dev_ms[len(states):], 50)), "launches_per_step": int(st["launches"]),
         "solves_per_step": float(np.mean(solves)), "stored_laps": len(laps[-8:]),
         "speculation": {"hit_rate": spec["hit_rate"], "counters": spec,
                         "note": "one-launch step (spec_step.cuh): candidates served from speculative solves whose lambda_in matched bit for bit"},

@@ -206,25 +206,30 @@ __device__ __forceinline__ void chain_task_eval(const KParamsT<R>& p, const Cand
   o[19] = R(0.0);
 }
 
-// The tasks of one lane, two at a time so that their exponentials interleave.
+// The tasks of one lane, two at a time so that their exponentials interleave.  When the group is smaller than the task
+// list (some lane has a second task) EVERY lane runs the two-task body -- a lane without a second task recomputes its
+// first one and drops the result -- so that the lanes of a warp do not split into a two-task and a one-task pass.
 template <bool kQR, int S, typename R>
 __device__ __forceinline__ void chain_terms(const KParamsT<R>& p, const CandT<R>& c, const ChainLane<R, S>& v, const R* cur, int rung) {
   const int N = p.N, n_tasks = N + 1;
+  const bool pairs = n_tasks > v.rungs;  // uniform over the warp
   for (int k0 = rung; k0 < n_tasks; k0 += 2 * v.rungs) {
     const int k1 = k0 + v.rungs;
     const bool two = k1 < n_tasks;
     TaskIn<R> a;
     chain_task_load<S>(p, c, cur, k0, a);
     R oa[kTermWidth];
-    if (two) {  // two tasks side by side
+    if (pairs) {  // two tasks side by side
       TaskIn<R> b;
-      chain_task_load<S>(p, c, cur, k1, b);
+      chain_task_load<S>(p, c, cur, two ? k1 : k0, b);
       R ob[kTermWidth];
       chain_task_eval<kQR>(p, c, a, oa);
       chain_task_eval<kQR>(p, c, b, ob);
-      R* db = v.terms_w(k1);
+      if (two) {
+        R* db = v.terms_w(k1);
 #pragma unroll
-      for (int i = 0; i < kTermWidth - 1; ++i) db[i * S] = ob[i];
+        for (int i = 0; i < kTermWidth - 1; ++i) db[i * S] = ob[i];
+      }
     } else {
       chain_task_eval<kQR>(p, c, a, oa);
     }
@@ -475,6 +480,17 @@ struct GroupSolver {
   const R* cur;        // current trajectory of the group: some lane's trial buffer
   bool dirty;          // the shared terms do not belong to `cur` yet
   bool running;
+#ifdef I2LQR_TRIP_PROFILE
+  long long prof[5] = {0, 0, 0, 0, 0};  // developer build: cycles in terms / riccati / forward / accept, rounds
+#define I2_PROF(i)                  \
+  {                                 \
+    const long long t_ = clock64(); \
+    prof[i] += t_ - tp_;            \
+    tp_ = t_;                       \
+  }
+#else
+#define I2_PROF(i)
+#endif
 
   __device__ __forceinline__ void bind(R* smem, int lane, int N) {
     rung = lane % kGroup;
@@ -502,18 +518,26 @@ struct GroupSolver {
   // One round for the whole warp.  Returns true on the lanes of a group whose candidate ended in this round; its
   // result is then `cur` (trajectory), c.lamb, c.iters, c.J.
   __device__ __forceinline__ bool trip(const KParamsT<R>& p) {
+#ifdef I2LQR_TRIP_PROFILE
+    long long tp_ = clock64();
+    prof[4] += 1;
+#endif
     __syncwarp();
     const bool run = running;
     if (run && dirty) chain_terms<kQR, S>(p, c, v, cur, rung);
     __syncwarp();
+    I2_PROF(0)
     R Jn = R(0.0), Jt = R(0.0);
     if (run && is_rung) {
       R lamb_r = c.lamb;
       for (int r = 0; r < rung; ++r) lamb_r *= p.lamb_factor;  // the value r rejects lead to, same operations
       chain_riccati<kQR, S>(p, v, lamb_r);
+      __syncwarp(__activemask());
+      I2_PROF(1)
       Jn = chain_forward<kQR, S>(p, c, cur, v.gains(), v.trial(wb), Jt);
     }
     __syncwarp();
+    I2_PROF(2)
     const unsigned acc_all = __ballot_sync(kFull, run && is_rung && Jn < c.J);
     const unsigned acc = (acc_all >> gbase_lane) & ((1u << kRungs) - 1u);
     // ---- accept in the reference's order (iterative_ilqr.py:74-84); every lane of the group computes the same
@@ -555,6 +579,7 @@ struct GroupSolver {
       if (c.iters >= p.max_iter) fin = true;
       if (fin) running = false;
     }
+    I2_PROF(3)
     return run && fin;
   }
   // Result in the reference's layout, xvar (4, N+1) and uvar (2, N), written by the lanes of the group together.

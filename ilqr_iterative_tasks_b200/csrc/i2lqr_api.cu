@@ -134,7 +134,7 @@ struct i2lqr_handle {
   DevBuf<unsigned> sp_state, sp_ctl, sp_hist_cnt;
   DevBuf<double> sp_lamb, sp_cost, sp_traj;
   DevBuf<int> sp_iters;
-  DevBuf<unsigned long long> sp_walked, sp_hist_key, sp_set, sp_stats;
+  DevBuf<unsigned long long> sp_walked, sp_hist_key, sp_set, sp_stats, sp_timeline, sp_pub;
   int sp_cmax = 0, sp_K = 0, sp_S = 0, sp_E = 0, sp_N = 0;
   unsigned sp_epoch = 0;
   // component entry points (components.cuh): grow-only staging
@@ -560,7 +560,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto* b : {&h->sp_state, &h->sp_ctl, &h->sp_hist_cnt}) b->release();
   for (auto* b : {&h->sp_lamb, &h->sp_cost, &h->sp_traj}) b->release();
   h->sp_iters.release();
-  for (auto* b : {&h->sp_walked, &h->sp_hist_key, &h->sp_set, &h->sp_stats}) b->release();
+  for (auto* b : {&h->sp_walked, &h->sp_hist_key, &h->sp_set, &h->sp_stats, &h->sp_timeline, &h->sp_pub}) b->release();
   for (auto& b : h->c_in) b.release();
   for (auto& b : h->c_out) b.release();
   h->c_scratch.release();
@@ -1092,7 +1092,7 @@ bool spec_enabled() {
   return on;
 }
 int spec_set_size() {
-  static const int s = getenv("I2LQR_SPEC_S") ? std::max(1, std::min(kSpecMaxSet, atoi(getenv("I2LQR_SPEC_S")))) : 24;  // tuning switch
+  static const int s = getenv("I2LQR_SPEC_S") ? std::max(1, std::min(kSpecMaxSet, atoi(getenv("I2LQR_SPEC_S")))) : 32;  // tuning switch
   return s;
 }
 size_t spec_smem_bytes(const i2lqr_handle* h) {
@@ -1156,9 +1156,11 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     CU(h->sp_cost.ensure(entries));
     CU(h->sp_iters.ensure(entries));
     CU(h->sp_traj.ensure(entries * (size_t)(6 * N + 4)));
-    const size_t ctl_words = 8 + (size_t)kOuter * cmax + 2 * (size_t)kOuter * E;
+    const size_t ctl_words = 8 + 2 * (size_t)kOuter * E;
     CU(h->sp_ctl.ensure(ctl_words));
     CU(h->sp_walked.ensure((size_t)kOuter * cmax));
+    CU(h->sp_pub.ensure((size_t)kOuter * cmax * K * kSpecPubWords));
+    CU(cudaMemsetAsync(h->sp_pub.p, 0, h->sp_pub.n * sizeof(unsigned long long), st));
     // a new layout invalidates every stamp: clear once (steady-state launches clear nothing)
     CU(cudaMemsetAsync(h->sp_state.p, 0, h->sp_state.n * sizeof(unsigned), st));
     CU(cudaMemsetAsync(h->sp_ctl.p, 0, h->sp_ctl.n * sizeof(unsigned), st));
@@ -1198,19 +1200,41 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   a.item_cost = h->sp_cost.p;
   a.item_iters = h->sp_iters.p;
   a.item_traj = h->sp_traj.p;
-  h->sp_epoch = h->sp_epoch >= (1u << 29) ? 1u : h->sp_epoch + 1u;
-  a.epoch = h->sp_epoch;
+  if (h->sp_epoch >= (1u << 29)) {  // the stamps must keep growing: start over from a cleared table
+    CU(cudaMemsetAsync(h->sp_state.p, 0, h->sp_state.n * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(h->sp_pub.p, 0, h->sp_pub.n * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(h->sp_walked.p, 0, h->sp_walked.n * sizeof(unsigned long long), st));
+    h->sp_epoch = 0;
+  }
+  a.epoch = ++h->sp_epoch;
   a.ctl = h->sp_ctl.p;
-  a.ready = h->sp_ctl.p + 8;
-  a.arrived = a.ready + (size_t)kOuter * h->sp_cmax;
+  a.arrived = h->sp_ctl.p + 8;
   a.iter_done = a.arrived + (size_t)kOuter * h->sp_E;
+  a.pub = h->sp_pub.p;
+  {  // candidates per chain never exceed the longest stored lap (the work list of the workers is bounded by it)
+    int longest = 0;
+    for (int e = 0; e < h->E; ++e)
+      for (int l = 0; l < h->L; ++l) longest = std::max(longest, h->h_lap_len[(size_t)e * h->L + l]);
+    a.k_eff = std::max(1, std::min(h->K, longest));
+  }
   a.walked = h->sp_walked.p;
   a.hist_key = h->sp_hist_key.p;
   a.hist_cnt = h->sp_hist_cnt.p;
   a.spec_set = h->sp_set.p;
   a.step_stats = h->ctl.p;
   a.stats = h->sp_stats.p;
+  static const bool want_timeline = getenv("I2LQR_SPEC_TIMELINE") != nullptr;  // developer switch
+  if (want_timeline) {
+    CU(h->sp_timeline.ensure((size_t)kOuter * h->sp_cmax * 8 + 4 * h->sp_state.n + 9 * 1024));
+    CU(cudaMemsetAsync(h->sp_timeline.p, 0, h->sp_timeline.n * 8, st));
+    a.timeline = h->sp_timeline.p;
+    a.item_dbg = h->sp_timeline.p + (size_t)kOuter * h->sp_cmax * 8;
+    a.worker_dbg = a.item_dbg + 4 * h->sp_state.n;  // (the grid never exceeds 1024 blocks)
+  }
+  // (lanes per speculative candidate: 4 and 8 measured the same step latency at the config-2 shape, 16 / 32 are 10-18 % slower:
+  // fewer candidates in flight, more entries the resolver finds not started)
   const void* kern = kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
+  const int per_warp = 32 / kSpecWorkerGroup;
   const size_t smem = spec_smem_bytes(h);
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1218,7 +1242,7 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
   if (per_sm < 1) return fail("speculative step kernel does not fit on an SM");
   const long long chains = (long long)sc.n_episodes * h->L;
-  const long long workers = std::max<long long>(1, (chains * (h->K - 1) * h->sp_S + 7) / 8);
+  const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * h->sp_S + per_warp - 1) / per_warp);
   const long long grid = std::min<long long>((long long)per_sm * h->n_sms, chains + workers);
   if (grid <= chains) return fail("internal: no room for worker warps");
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
@@ -1721,6 +1745,21 @@ int i2lqr_spec_stats(i2lqr_handle* h, int64_t* counters8) {
   unsigned long long v[8];
   CU(cudaMemcpy(v, h->sp_stats.p, sizeof v, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 8; ++i) counters8[i] = (int64_t)v[i];
+  return 0;
+}
+
+// Developer aid (I2LQR_SPEC_TIMELINE=1): per (outer iteration, chain) of the last one-launch step, 8 words -- globaltimer ns at
+// start / K-nearest done / rank-0 candidate done / walk done / released by the winner, ns spent waiting for in-flight entries,
+// (in-place solves << 32 | their iterations), 0.  Returns the number of chains the table is laid out for.
+int i2lqr_spec_timeline(i2lqr_handle* h, uint64_t* words, int64_t capacity_words, int32_t* c_max) {
+  if (!h || !words || !c_max) return fail("null argument");
+  *c_max = 0;
+  if (!h->sp_timeline.p) return 0;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t n = std::min<size_t>((size_t)capacity_words, h->sp_timeline.n);  // (chain table first, then 4 words per table entry)
+  CU(cudaMemcpy(words, h->sp_timeline.p, n * 8, cudaMemcpyDeviceToHost));
+  *c_max = h->sp_cmax;
   return 0;
 }
 

@@ -28,6 +28,7 @@ constexpr int kSpecMaxSet = 32;      // speculation set entries (one per lane of
 constexpr int kSpecHist = 64;        // histogram slots (two per lane)
 constexpr int kSpecRungs = 4;
 constexpr int kSpecWorkerGroup = 4;  // lanes per speculative candidate: 8 candidates per worker warp
+constexpr int kSpecPubWords = 6;
 constexpr unsigned long long kSpecUnused = 0x7ff8dead00000000ull;  // NaN payload: never a lambda
 
 struct SpecArgs {
@@ -51,7 +52,8 @@ struct SpecArgs {
   int* cand_iters;
   WinnerArgs win;              // it / ep_list fields are filled in by the kernel
   // ---- speculation tables: entry ((it * c_max + chain) * K + j) * S + s
-  unsigned* item_state;        // (epoch << 2) | 0 free / 1 claimed / 2 done
+  unsigned* item_state;        // (epoch << 2) | 1 claimed / 2 done; anything below (epoch << 2) is free.  Values only grow (the
+                               // host clears the table when the epoch wraps), so a claim is ONE atomicMax with no prior read
   double* item_lamb;           // lambda_out
   double* item_cost;           // relaxed cost
   int* item_iters;
@@ -59,7 +61,10 @@ struct SpecArgs {
   unsigned epoch;              // launch number, stamps every flag: nothing is cleared between launches
   // ---- control words (zero at allocation, restored by the last block to leave)
   unsigned* ctl;               // [0] ticket [1] blocks left [2] chains finished [3] all done (epoch) [4..6] queue heads
-  unsigned* ready;             // (3, c_max)  epoch once the chain's K-nearest of that outer iteration is published
+  unsigned long long* pub;     // (3, c_max, K, 6) what a worker needs to start candidate j, published by the chain's resolver after its
+                               //   K-nearest: [0] (epoch << 32) | safe-set index (0xffffffff: the lap has no candidate j), written LAST
+                               //   (release) so that it doubles as the "record is there" flag; [1..4] terminal point; [5] Qfun
+  int k_eff;                   // host's upper bound of candidates per chain (min(K, longest active lap)): bounds the work list
   unsigned long long* walked;  // (3, c_max)  (epoch << 32) | candidates the resolver has passed
   unsigned* arrived;           // (3, E)      resolvers of the episode that finished the outer iteration
   unsigned* iter_done;         // (3, E)      epoch once the episode's winner of that outer iteration is published
@@ -67,6 +72,9 @@ struct SpecArgs {
   unsigned long long* hist_key;  // (kSpecHist) bit patterns
   unsigned* hist_cnt;            // (kSpecHist)
   unsigned long long* spec_set;  // (kSpecMaxSet) the S most frequent patterns, frozen for the launch
+  unsigned long long* item_dbg;    // optional (developer): per table entry [start ns, end ns, rounds, iterations]
+  unsigned long long* worker_dbg;  // optional (developer): per block [rounds with a live candidate, cycles picking entries, cycles in rounds, cycles publishing]
+  unsigned long long* timeline;    // optional (developer): per (it, chain) 8 words of globaltimer ns / counters, see i2lqr_spec_timeline
   unsigned long long* step_stats;  // [0] += iLQR iterations, [1] += candidate solves of the step (the reference's path only)
   unsigned long long* stats;       // cumulative: [0] hits [1] waited for [2] self-solved (in the set, not started) [3] misses
                                    // [4] speculative solves finished [5] abandoned [6] launches
@@ -81,6 +89,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+// polls of flags that guard no data (step over? chain past this candidate?): relaxed, no L1 invalidation
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -112,7 +136,7 @@ __device__ __forceinline__ SpecLap spec_lap(const SpecArgs& a, int ep, int lrel)
   return l;
 }
 
-template <bool kQR>
+template <bool kQR, int kWG = kSpecWorkerGroup>
 __global__ void __launch_bounds__(kSolveThreads, 1)
 spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ SpecArgs a) {
   extern __shared__ double smem[];
@@ -142,6 +166,8 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
     const SpecLap lp = spec_lap(a, ep, lrel < n_act ? lrel : 0);
     unsigned long long hkey0 = a.hist_key[lane], hkey1 = a.hist_key[lane + 32];
     for (int it = 0; it < kOuter; ++it) {
+      unsigned long long tl[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // start, knn done, rank 0 done, walk done, released | wait ns, in-place solves, their iterations
+      if (a.timeline != nullptr) tl[0] = global_ns();
       const double scale = it == 0 ? 1.0 : (it == 1 ? 10.0 : 100.0);  // 10**it, utils/base.py:428-435
       const size_t trow = (((size_t)ep * kOuter + it) * L + lrel) * K;
       int cnt = 0;
@@ -170,10 +196,23 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
       __threadfence();
       __syncwarp();
       unsigned long long* walked = a.walked + (size_t)it * a.c_max + chain;
-      if (lane == 0) {
-        st_release_u64(walked, (unsigned long long)epoch << 32);
-        st_release_u32(a.ready + (size_t)it * a.c_max + chain, epoch);
+      if (lane == 0) st_release_u64(walked, (unsigned long long)epoch << 32);
+      {  // publish the candidates to the workers: terminal point and cost-to-go first, the stamped index word last
+        unsigned long long* pub = a.pub + ((size_t)it * a.c_max + chain) * K * kSpecPubWords;
+        for (int r = lane; r < cnt; r += 32) {
+          const long long js = a.sel_idx[trow + r];
+          double* rec = reinterpret_cast<double*>(pub + (size_t)r * kSpecPubWords);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rec[1 + i] = lp.lap[(size_t)i * a.set.Tcap + js];
+          rec[5] = (double)(lp.T - 1 - js);
+        }
+        __threadfence();
+        __syncwarp();
+        for (int r = lane; r < K; r += 32)
+          st_release_u64(pub + (size_t)r * kSpecPubWords,
+                         ((unsigned long long)epoch << 32) | (r < cnt ? (unsigned long long)(unsigned)a.sel_idx[trow + r] : 0xffffffffull));
       }
+      if (a.timeline != nullptr) tl[1] = global_ns();
       // ---- walk the chain in rank order, lambda carried (utils/base.py:393,403-455)
       double lamb = p.lamb0;
       int br = 0;
@@ -220,15 +259,17 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
             for (;;) {
               const unsigned stw = ld_acquire_u32(a.item_state + idx);
               if ((stw >> 2) != epoch) {  // nobody has started it: take it out of the workers' reach and solve it here
-                if (atomicCAS(a.item_state + idx, stw, (epoch << 2) | 1u) == stw) {
+                if (atomicMax(a.item_state + idx, (epoch << 2) | 1u) < (epoch << 2)) {  // (states only grow: see item_state)
                   st_self += 1;
                   break;
                 }
               } else if ((stw & 3u) == 2u) {
                 how = 1;
                 if (spins) st_wait += 1; else st_hit += 1;
+                if (spins && a.timeline != nullptr) tl[5] += global_ns() - tl[7];
                 break;
               } else {
+                if (spins == 0 && a.timeline != nullptr) tl[7] = global_ns();
                 ++spins;
                 __nanosleep(40);
               }
@@ -268,6 +309,7 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
           cost = relax_cost(p, xN, gs.c.xt, qfun, scale);
           lamb_out = gs.c.lamb;
           iters = gs.c.iters;
+          if (j > 0) tl[6] += (1ull << 32) | (unsigned)iters;
           if (j == 0 || cost < best_cost) {
             br = j;
             best_cost = cost;
@@ -283,8 +325,10 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
           st_solves += 1;
         }
         lamb = lamb_out;
+        if (j == 0 && a.timeline != nullptr) tl[2] = global_ns();
       }
       (void)br;
+      if (a.timeline != nullptr) tl[3] = global_ns();
       if (lane == 0) st_release_u64(walked, ((unsigned long long)epoch << 32) | 0xffffffffull);  // everything left is stale
       // ---- K3: the episode's last resolver to get here applies the winner rule (utils/base.py:462-478)
       __threadfence();
@@ -308,6 +352,11 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
         __syncwarp();
       }
       __threadfence();
+      if (a.timeline != nullptr && lane == 0) {
+        tl[4] = global_ns();
+        tl[7] = 0;
+        for (int i = 0; i < 8; ++i) a.timeline[((size_t)it * a.c_max + chain) * 8 + i] = tl[i];
+      }
     }
     // ---- end of the step for this chain
     unsigned fin = 0;
@@ -339,98 +388,183 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
     }
   } else {
     // =============================================================== worker: speculative candidates, 8 per warp
-    constexpr int G = kSpecWorkerGroup;
+    // Lane group g of all workers owns the table entries q = g, g + n_groups, g + 2 n_groups, ... of every outer
+    // iteration, in the j-major order q = ((j - 1) * n_chains + chain) * S + s, so that the candidates a resolver reaches
+    // first are started first.  The groups of a warp run their candidates in lock step, so whatever one group does
+    // between candidates is paid by all eight: picking the next entry is therefore fully pipelined.  While a candidate
+    // runs, its group fetches the NEXT entry's published record in two asynchronous stages (stamped index word, then
+    // terminal point / cost-to-go / resolver progress), each consumed a round after it was issued; when the candidate
+    // ends the next one starts from registers, claimed by one atomicMax whose answer is read after the start-up
+    // arithmetic.  No round waits for a global-memory round trip.
+    constexpr int G = kWG;
     GroupSolver<double, kQR, kSpecRungs, G, S32> gs;
     gs.bind(smem, lane, N);
     const int rung = gs.rung;
-    const unsigned gmask = ((1u << G) - 1u) << gs.gbase_lane;
+    const unsigned gmask = (G >= 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << gs.gbase_lane;
     auto bcast = [&](auto v) { return __shfl_sync(gmask, v, gs.gbase_lane); };
-    enum { W_NEED, W_READY, W_RUN, W_DONE };
-    int state = W_NEED, it = 0;
-    int j = 0, chain = 0, s = 0, ep = 0, lrel = 0;
+    enum { W_NEED, W_RUN, W_DONE };
+    const unsigned long long n_groups = (unsigned long long)(gridDim.x - n_chains) * (32 / G);
+    const unsigned long long gid = (unsigned long long)(ticket - n_chains) * (32 / G) + (lane / G);
+    const int k_eff = a.k_eff < K ? a.k_eff : K;
+    const unsigned long long per_it = (unsigned long long)n_chains * (k_eff > 1 ? k_eff - 1 : 0) * S;
+    int state = per_it == 0 ? W_DONE : W_NEED;
+    // running candidate
+    int it = 0, j = 0, chain = 0;
     size_t idx = 0;
     double qfun = 0.0;
-    const unsigned long long per_it = (unsigned long long)n_chains * (K - 1) * S;
-    if (per_it == 0) state = W_DONE;
+    // next entry of this group's list, being prefetched: 0 nothing issued, 1 index word in flight, 2 record in flight / here
+    int pf_stage = 0, pf_it = 0, pf_j = 0, pf_chain = 0, pf_s = 0;
+    unsigned long long pf_q = gid, pf_word = 0, pf_walked = 0;
+    size_t pf_idx = 0;
+    double pf_xt[4] = {0.0, 0.0, 0.0, 0.0}, pf_qfun = 0.0;
+    bool list_done = per_it == 0;
+    int bound_ep = -1;
+    // claim of the running candidate whose answer has not been looked at yet; finished entry whose "done" flag is still to be set
+    bool claim_pending = false, flag_pending = false;
+    unsigned claim_prev = 0;
+    size_t flag_idx = 0;
+    unsigned over = 0;  // polled one round ahead: the load's latency hides under the round
+    long long dbg_rounds = 0, dbg_pick = 0, dbg_trip = 0, dbg_pub = 0, dbg_t = 0;
     for (;;) {
       // ---- leave when the step is over (abandoning whatever is still in flight) or when nothing is left to try
-      unsigned over = 0;
-      if (lane == 0) over = ld_acquire_u32(a.ctl + 3) == epoch;
       if (__shfl_sync(kFull, over, 0)) break;
+      if (lane == 0) over = ld_relaxed_u32(a.ctl + 3) == epoch;
       if (__all_sync(kFull, state == W_DONE)) break;
-      if (state == W_NEED) {  // next entry of the j-major queue of outer iteration `it`
-        unsigned long long q = 0;
-        if (rung == 0) q = atomicAdd(a.ctl + 4 + it, 1u);
-        q = bcast(q);
-        if (q >= per_it) {
-          if (++it == kOuter) state = W_DONE;
-        } else {
-          s = (int)(q % S);
-          chain = (int)((q / S) % n_chains);
-          j = 1 + (int)(q / ((unsigned long long)S * n_chains));
-          lrel = chain % L;
-          ep = a.ep_list != nullptr ? a.ep_list[chain / L] : chain / L;
-          idx = (((size_t)it * a.c_max + chain) * K + j) * S + s;
-          state = W_READY;
+      if (a.worker_dbg != nullptr) dbg_t = clock64();
+      // ---- (z) left over from the previous round.  A finished entry's "done" flag is set one round after its data was
+      // written (unless its resolver was already waiting for it): by then the stores have drained and the fence that must
+      // precede the flag costs next to nothing, where a fence right behind the stores stalls all eight candidates of the warp.
+      if (flag_pending) {
+        __threadfence();
+        __syncwarp(gmask);
+        if (rung == 0) st_release_u32(a.item_state + flag_idx, (epoch << 2) | 2u);
+        flag_pending = false;
+      }
+      if (claim_pending && state == W_RUN) {  // the claim's answer, a round after it was asked for
+        claim_pending = false;
+        if (bcast(claim_prev) >= (epoch << 2)) {  // somebody (the resolver, usually) already had this entry
+          gs.running = false;
+          state = W_NEED;
         }
       }
-      if (state == W_READY) {  // non-blocking: wait for the chain's K-nearest, drop entries nobody will ask for
-        unsigned rdy = 0;
-        unsigned long long wk = 0;
-        if (rung == 0) {
-          rdy = ld_acquire_u32(a.ready + (size_t)it * a.c_max + chain);
-          wk = ld_acquire_u64(a.walked + (size_t)it * a.c_max + chain);
-        }
-        rdy = bcast(rdy);
-        wk = bcast(wk);
-        if (rdy == epoch) {
-          const int cnt = __ldcg(a.sel_cnt + (size_t)ep * L + lrel);
-          const bool stale = (wk >> 32) == epoch && (unsigned)(wk & 0xffffffffull) > (unsigned)j;
-          const bool unused = a.spec_set[s] == kSpecUnused;  // fewer than S lambda values known so far
-          unsigned got = 0;
-          if (j < cnt && !stale && !unused && rung == 0) {
-            const unsigned stw = ld_acquire_u32(a.item_state + idx);
-            if ((stw >> 2) != epoch) got = atomicCAS(a.item_state + idx, stw, (epoch << 2) | 1u) == stw;
-          }
-          got = bcast(got);
-          if (got) {
-            const SpecLap lp = spec_lap(a, ep, lrel);
-            const long long jsel = __ldcg(a.sel_idx + (((size_t)ep * kOuter + it) * L + lrel) * K + j);
-            spec_bind_episode(p, a, ep, gs);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) gs.c.xt[i] = lp.lap[(size_t)i * a.set.Tcap + jsel];
-            gs.c.lamb = __longlong_as_double((long long)a.spec_set[s]);
-            qfun = (double)(lp.T - 1 - jsel);
-            gs.start(p);
-            state = W_RUN;
+      // ---- (a) what was fetched during the previous round
+      if (pf_stage == 1) {
+        const unsigned long long w = bcast(pf_word);
+        if ((w >> 32) == epoch) {
+          pf_word = w;
+          if ((unsigned)(w & 0xffffffffull) == 0xffffffffu || a.spec_set[pf_s] == kSpecUnused) {
+            pf_stage = 0;  // the lap has no candidate j, or no lambda behind this slot: next entry
+            pf_q += n_groups;
           } else {
-            state = W_NEED;
+            const double* rec = reinterpret_cast<const double*>(a.pub + (((size_t)pf_it * a.c_max + pf_chain) * K + pf_j) * kSpecPubWords);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pf_xt[i] = __ldcg(rec + 1 + i);
+            pf_qfun = __ldcg(rec + 5);
+            if (rung == 0) pf_walked = ld_relaxed_u64(a.walked + (size_t)pf_it * a.c_max + pf_chain);
+            pf_stage = 2;
           }
+        } else {
+          pf_stage = 0;  // not published yet (the resolver is still selecting): ask again
         }
       }
+      // ---- (b) start the prefetched candidate
+      if (state == W_NEED && pf_stage == 2) {
+        const unsigned long long wk = bcast(pf_walked);
+        const bool stale = (wk >> 32) == epoch && (unsigned)(wk & 0xffffffffull) > (unsigned)pf_j;
+        if (!stale) {
+          it = pf_it;
+          j = pf_j;
+          chain = pf_chain;
+          idx = pf_idx;
+          qfun = pf_qfun;
+          if (rung == 0) claim_prev = atomicMax(a.item_state + idx, (epoch << 2) | 1u);  // the claim; its answer is read a round later
+          claim_pending = true;
+          const int ep = a.ep_list != nullptr ? a.ep_list[chain / L] : chain / L;
+          if (ep != bound_ep) {
+            spec_bind_episode(p, a, ep, gs);
+            bound_ep = ep;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gs.c.xt[i] = pf_xt[i];
+          gs.c.lamb = __longlong_as_double((long long)a.spec_set[pf_s]);
+          gs.start(p);
+          state = W_RUN;
+          if (a.item_dbg != nullptr && rung == 0) {
+            a.item_dbg[idx * 4 + 0] = global_ns();
+            a.item_dbg[idx * 4 + 2] = 0;
+          }
+        }
+        pf_stage = 0;
+        pf_q += n_groups;
+      }
+      // ---- (c) issue the next fetch: the stamped index word of this group's next entry
+      if (pf_stage == 0 && !list_done) {
+        if (pf_q >= per_it) {  // this group's share of the outer iteration is done
+          pf_q = gid;
+          if (++pf_it == kOuter || pf_q >= per_it) list_done = true;
+        }
+        if (!list_done) {
+          pf_s = (int)(pf_q % S);
+          pf_chain = (int)((pf_q / S) % n_chains);
+          pf_j = 1 + (int)(pf_q / ((unsigned long long)S * n_chains));
+          pf_idx = (((size_t)pf_it * a.c_max + pf_chain) * K + pf_j) * S + pf_s;
+          if (rung == 0) pf_word = ld_acquire_u64(a.pub + (((size_t)pf_it * a.c_max + pf_chain) * K + pf_j) * kSpecPubWords);
+          pf_stage = 1;
+        }
+      }
+      if (state == W_NEED && list_done && pf_stage == 0 && !flag_pending) state = W_DONE;
       const bool any_run = __any_sync(kFull, state == W_RUN);
       if (!any_run) {
-        __nanosleep(100);
+        __nanosleep(60);
         continue;
       }
       // ---- one round of every live candidate of the warp
       unsigned long long wk = 0;
-      if (state == W_RUN && rung == 0) wk = ld_acquire_u64(a.walked + (size_t)it * a.c_max + chain);  // consumed after the round
+      if (state == W_RUN && rung == 0) wk = ld_relaxed_u64(a.walked + (size_t)it * a.c_max + chain);  // consumed after the round
+      if (a.worker_dbg != nullptr) {
+        const long long t = clock64();
+        dbg_pick += t - dbg_t;
+        dbg_t = t;
+      }
       const bool fin = gs.trip(p);
+      if (a.worker_dbg != nullptr) {
+        const long long t = clock64();
+        dbg_trip += t - dbg_t;
+        dbg_t = t;
+        dbg_rounds += 1;
+      }
+      if (a.item_dbg != nullptr && rung == 0 && state == W_RUN) a.item_dbg[idx * 4 + 2] += 1;
       if (fin) {
-        double* tr = a.item_traj + idx * n_traj;
-        gs.store(tr, tr + 4 * (N + 1));
-        if (rung == 0) {
-          double xN[4];
-          gs.terminal_state(xN);
-          a.item_cost[idx] = relax_cost(p, xN, gs.c.xt, qfun, it == 0 ? 1.0 : (it == 1 ? 10.0 : 100.0));
-          a.item_lamb[idx] = gs.c.lamb;
-          a.item_iters[idx] = gs.c.iters;
-          st_spec += 1;
+        bool mine = true;
+        if (claim_pending) {  // a candidate that ended in its first round
+          claim_pending = false;
+          mine = bcast(claim_prev) < (epoch << 2);
         }
-        __threadfence();
-        __syncwarp(gmask);
-        if (rung == 0) st_release_u32(a.item_state + idx, (epoch << 2) | 2u);
+        if (mine) {
+          if (a.item_dbg != nullptr && rung == 0) {
+            a.item_dbg[idx * 4 + 1] = global_ns();
+            a.item_dbg[idx * 4 + 3] = (unsigned long long)gs.c.iters;
+          }
+          double* tr = a.item_traj + idx * n_traj;
+          gs.store(tr, tr + 4 * (N + 1));
+          if (rung == 0) {
+            double xN[4];
+            gs.terminal_state(xN);
+            a.item_cost[idx] = relax_cost(p, xN, gs.c.xt, qfun, it == 0 ? 1.0 : (it == 1 ? 10.0 : 100.0));
+            a.item_lamb[idx] = gs.c.lamb;
+            a.item_iters[idx] = gs.c.iters;
+            st_spec += 1;
+          }
+          wk = bcast(wk);
+          if ((wk >> 32) == epoch && (unsigned)(wk & 0xffffffffull) == (unsigned)j) {  // its resolver is waiting for it: now
+            __threadfence();
+            __syncwarp(gmask);
+            if (rung == 0) st_release_u32(a.item_state + idx, (epoch << 2) | 2u);
+          } else {
+            flag_pending = true;
+            flag_idx = idx;
+          }
+        }
         state = W_NEED;
       } else if (state == W_RUN) {
         wk = bcast(wk);
@@ -441,6 +575,18 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
         }
       }
       __syncwarp();
+      if (a.worker_dbg != nullptr) dbg_pub += clock64() - dbg_t;
+    }
+    if (a.worker_dbg != nullptr && lane == 0) {
+      unsigned long long* d = a.worker_dbg + (size_t)blockIdx.x * 4;
+      d[0] = (unsigned long long)dbg_rounds;
+      d[1] = (unsigned long long)dbg_pick;
+      d[2] = (unsigned long long)dbg_trip;
+      d[3] = (unsigned long long)dbg_pub;
+#ifdef I2LQR_TRIP_PROFILE
+      unsigned long long* e = a.worker_dbg + 4096 + (size_t)blockIdx.x * 5;
+      for (int i = 0; i < 5; ++i) e[i] = (unsigned long long)gs.prof[i];
+#endif
     }
   }
   // ---- statistics, then the last block to leave restores the counters for the next launch

@@ -29,7 +29,7 @@ EXPORTS = [
     "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
     "i2lqr_split_end", "i2lqr_dynamics_batch", "i2lqr_linearize_batch", "i2lqr_cost_derivatives_batch",
     "i2lqr_cost_final_batch", "i2lqr_backward_pass_batch", "i2lqr_forward_pass_batch",
-    "i2lqr_add_lap_all", "i2lqr_set_obstacles", "i2lqr_spec_stats",
+    "i2lqr_add_lap_all", "i2lqr_set_obstacles", "i2lqr_spec_stats", "i2lqr_spec_timeline",
 ]  # fmt: skip
 
 
@@ -72,6 +72,8 @@ def measure_fp64_peak(device=0, reps=5):
 
 class Engine:
     """One GPU, one stream, `n_episodes` independent safe sets (see i2lqr_create)."""
+
+    spec_set_size = int(os.environ.get("I2LQR_SPEC_S", "32"))  # mirrors the library's tuning switch (developer tools only)
 
     def __init__(self, params=None, device=0, n_episodes=0, lap_capacity=0):
         self.params = params if params is not None else _abi.default_params()
@@ -334,6 +336,20 @@ class Engine:
         served = out["hits"] + out["waited"] + out["self_solved"] + out["misses"]
         out["hit_rate"] = (out["hits"] + out["waited"]) / served if served else None
         return out
+
+    def spec_timeline(self, max_chains=64):
+        """(3, c_max, 8) uint64 table of the last one-launch step (needs I2LQR_SPEC_TIMELINE=1), or None."""
+        K, S = self.params.num_ss_points, 32
+        buf = np.zeros(3 * max_chains * 8 + 4 * 3 * max_chains * K * S + 9216, dtype=np.uint64)
+        cm = C.c_int32()
+        _check(lib().i2lqr_spec_timeline(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_int64(buf.size), C.byref(cm)))
+        if not cm.value:
+            return None
+        n_items = 4 * 3 * cm.value * K * self.spec_set_size
+        self.spec_item_debug = buf[3 * cm.value * 8 : 3 * cm.value * 8 + n_items]  # (entries, 4): start ns, end ns, rounds, iterations
+        self.spec_worker_debug = buf[3 * cm.value * 8 + n_items : 3 * cm.value * 8 + n_items + 4096].reshape(1024, 4)
+        self.spec_trip_profile = buf[3 * cm.value * 8 + n_items + 4096 : 3 * cm.value * 8 + n_items + 9216].reshape(1024, 5)  # I2LQR_TRIP_PROFILE builds
+        return buf[: 3 * cm.value * 8].reshape(3, cm.value, 8)
 
     # -- instrumentation -------------------------------------------------------------------------------
     def last_stats(self):

@@ -227,6 +227,9 @@ int i2lqr_forward_pass_batch(i2lqr_handle* h, int64_t B, const double* xvar, con
  *   [2] in the speculation set but not started: solved in place  [3] lambda not in the set: solved in place
  *   [4] speculative solves finished  [5] abandoned  [6] one-launch steps  [7] reserved */
 int i2lqr_spec_stats(i2lqr_handle* h, int64_t* counters8);
+/* Developer aid (environment I2LQR_SPEC_TIMELINE=1): where the last one-launch step spent its time, 8 words per (outer
+ * iteration, chain) -- see csrc/i2lqr_api.cu.  *c_max = chains per outer iteration in the table (0: not recorded). */
+int i2lqr_spec_timeline(i2lqr_handle* h, uint64_t* words, int64_t capacity_words, int32_t* c_max);
 
 /* Device time (CUDA events on the stream of the call) of the last compute call, the number of kernels it
  * launched, and the iLQR iterations / solves it executed (device-side counters, for the roofline).  For

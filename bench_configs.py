@@ -109,52 +109,92 @@ def episodes_cfg(device=0, E=512, laps=3):
 
 
 def horizon_sweep(device=0):
+    """BASELINE config 4a.  Per horizon: (1) the kernel on device-resident batches large enough that the 150-iteration
+    stragglers do not dominate (CUDA events; algorithmic FP64 fraction AND, for the streaming placement of N > 25, the
+    scratch traffic against the measured HBM copy bandwidth); (2) the same solve through the host-pointer call with a
+    65536-candidate batch (copies inside); (3) the optional FP32 build's tolerance gate."""
+    import torch
+
     rows = []
     peak = engine.measure_fp64_peak(device)
-    for N, B in ((6, 1 << 18), (10, 1 << 18), (25, 1 << 17), (50, 1 << 17), (100, 1 << 16), (200, 1 << 16)):  # enough candidates to fill the GPU at every horizon
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = None
+    dev = torch.device("cuda", device)
+    for N, B in ((6, 1 << 20), (10, 1 << 20), (25, 1 << 20), (50, 1 << 20), (100, 1 << 19), (200, 1 << 19)):
         d = synth.flat_candidates(B, N, seed=synth.SEED + N)
         p = _abi.default_params(num_horizon=N)
         obs = _abi.obstacle_array(d["obs"], d["mode"])
         e = engine.Engine(p, device=device)
-        import torch
+        g = {k: torch.from_numpy(np.ascontiguousarray(d[k])).to(dev) for k in ("x0", "x_term", "lamb_in")}
+        g_obs = torch.from_numpy(obs.view(np.uint8).reshape(B, -1).copy()).to(dev)
+        out = (torch.empty((B, 2, N), dtype=torch.float64, device=dev), torch.empty((B, 4, N + 1), dtype=torch.float64, device=dev),
+               torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.int32, device=dev))  # fmt: skip
+        stream = torch.cuda.Stream(dev)
+        best = None
+        for rep in range(3):
+            e.solve_batch_device(B, g["x0"].data_ptr(), g["x_term"].data_ptr(), g["lamb_in"].data_ptr(), g_obs.data_ptr(), B,
+                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), stream=stream.cuda_stream)
+            st = e.sync_stats(stream.cuda_stream)
+            if rep and (best is None or st["kernel_ms"] < best["kernel_ms"]):
+                best = st
+        tf = best["ilqr_iterations"] * flops_per_iteration(N) / (best["kernel_ms"] * 1e-3) / 1e12
+        finite = bool(torch.isfinite(out[1]).all())
+        row = {
+            "N": N, "device_resident": {
+                "B": B, "kernel_ms": best["kernel_ms"], "launches": best["launches"], "solves_per_s": B / (best["kernel_ms"] * 1e-3),
+                "iters_per_solve": best["ilqr_iterations"] / B, "algorithmic_tflops": tf, "frac_of_fp64_peak": tf / peak, "finite": finite,
+            },
+        }  # fmt: skip
+        if N > 25:  # streaming placement: ~65 doubles of scratch traffic per stage and iteration (ncu: profiles/r02_stream_n50_summary.txt)
+            gbs = best["ilqr_iterations"] * N * 65 * 8 / (best["kernel_ms"] * 1e-3) / 1e9
+            row["device_resident"].update({"scratch_traffic_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak if hbm_peak else None,
+                                           "placement": "global memory streamed through a shared-memory ring with cp.async.bulk"})  # fmt: skip
+        else:
+            row["device_resident"]["placement"] = "trajectory in shared memory, gains in tensor memory"
+        del g, g_obs, out
+        torch.cuda.empty_cache()
+        # ---- host-pointer call, 65536 candidates, pinned buffers (pageable memory would serialise and dominate the timing)
+        Bh = 1 << 16
 
-        def pin(a):  # pinned host buffers: pageable memory would serialise and dominate the timing
+        def pin(a):
             return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
-        d = {k: pin(v) for k, v in d.items()}
-        obs = np.frombuffer(pin(obs.view(np.uint8)), dtype=_abi.OBSTACLE_DTYPE)
-        bufs = {"uvar": pin(np.empty((B, 2, N))), "xvar": pin(np.empty((B, 4, N + 1))), "lamb_out": pin(np.empty(B)), "iters": pin(np.empty(B, dtype=np.int32))}
-        e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, out=bufs)
+        dh = {k: pin(v[:Bh]) for k, v in d.items()}
+        obs_h = np.frombuffer(pin(obs[:Bh].view(np.uint8)), dtype=_abi.OBSTACLE_DTYPE)
+        bufs = {"uvar": pin(np.empty((Bh, 2, N))), "xvar": pin(np.empty((Bh, 4, N + 1))), "lamb_out": pin(np.empty(Bh)), "iters": pin(np.empty(Bh, dtype=np.int32))}
+        e.solve_batch(dh["x0"], dh["x_term"], dh["lamb_in"], obs_h, out=bufs)
         t0 = time.perf_counter()
-        out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, out=bufs)
+        o64 = e.solve_batch(dh["x0"], dh["x_term"], dh["lamb_in"], obs_h, out=bufs)
         wall = time.perf_counter() - t0
-        out = {k: v.copy() for k, v in out.items()}  # kept for the FP32 comparison below (outside the timed call)
-        st = e.last_stats()
+        o64 = {k: v.copy() for k, v in o64.items()}
         e.close()
-        tf = st["ilqr_iterations"] * flops_per_iteration(N) / (st["kernel_ms"] * 1e-3) / 1e12
-        # optional FP32 build: tolerance gate against the FP64 result of the same inputs
+        row["host_call"] = {"B": Bh, "wall_ms": wall * 1e3, "solves_per_s": Bh / wall,
+                            "bytes_moved": int(Bh * (bytes_in_per_solve() + 48 * N + 44))}  # fmt: skip
+        # ---- optional FP32 build: tolerance gate against the FP64 result of the same inputs
         e32 = engine.Engine(_abi.default_params(num_horizon=N, precision=1), device=device)
-        o32 = e32.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs)
+        o32 = e32.solve_batch(dh["x0"], dh["x_term"], dh["lamb_in"], obs_h)
         t0 = time.perf_counter()
-        e32.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, out=bufs)  # same pinned output buffers as the FP64 call
+        e32.solve_batch(dh["x0"], dh["x_term"], dh["lamb_in"], obs_h, out=bufs)
         wall32 = time.perf_counter() - t0
         e32.close()
         with np.errstate(divide="ignore"):
-            same = (o32["iters"] == out["iters"]) & (np.round(np.log10(o32["lamb_out"])) == np.round(np.log10(out["lamb_out"])))
+            same = (o32["iters"] == o64["iters"]) & (np.round(np.log10(o32["lamb_out"])) == np.round(np.log10(o64["lamb_out"])))
         ax = tuple(range(1, 3))
         err = np.maximum(
-            np.abs(o32["xvar"] - out["xvar"]).max(axis=ax) / np.maximum(1, np.abs(out["xvar"]).max(axis=ax)),
-            np.abs(o32["uvar"] - out["uvar"]).max(axis=ax) / np.maximum(1, np.abs(out["uvar"]).max(axis=ax)),
+            np.abs(o32["xvar"] - o64["xvar"]).max(axis=ax) / np.maximum(1, np.abs(o64["xvar"]).max(axis=ax)),
+            np.abs(o32["uvar"] - o64["uvar"]).max(axis=ax) / np.maximum(1, np.abs(o64["uvar"]).max(axis=ax)),
         )
-        rows.append({
-            "N": N, "B": B, "wall_ms": wall * 1e3, "pipeline_ms": st["kernel_ms"], "solves_per_s": B / wall,
-            "iters_per_solve": st["ilqr_iterations"] / B, "algorithmic_tflops": tf, "frac_of_fp64_peak": tf / peak,
-            "finite": bool(np.isfinite(out["xvar"]).all()),
-            "fp32": {"wall_ms": wall32 * 1e3, "same_discrete_path": float(same.mean()),
-                     "within_1e-4_of_fp64_where_path_matches": float((err[same] <= 1e-4).mean()),
-                     "median_rel_err": float(np.median(err[same]))},
-        })  # fmt: skip
-    return {"config": "BASELINE config 4a: horizon sweep, host-pointer API (copies inside the timed call)", "fp64_peak_tflops": peak, "rows": rows}
+        row["fp32"] = {"wall_ms": wall32 * 1e3, "same_discrete_path": float(same.mean()),
+                       "within_1e-4_of_fp64_where_path_matches": float((err[same] <= 1e-4).mean()), "median_rel_err": float(np.median(err[same]))}  # fmt: skip
+        rows.append(row)
+    return {"config": "BASELINE config 4a: horizon sweep of the flat candidate solve (obstacle barrier on), FP64 vs FP32 gate",
+            "fp64_peak_tflops": peak, "hbm_peak_gbs": hbm_peak, "rows": rows}
+
+
+def bytes_in_per_solve():
+    return 32 + 32 + 8 + 48
 
 
 if __name__ == "__main__":

@@ -181,7 +181,12 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur <= kSmemLimit ? 2 : 1);
   const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon && h->params.precision == 0;
   if (tmem_ok && w.n_items >= 8192) scratch = 3;
+  // long horizons (flat batches, FP64): the working set is streamed through shared memory with bulk asynchronous copies
+  const bool stream_ok = w.mode == 0 && h->params.precision == 0;
+  static const int stream_from = getenv("I2LQR_STREAM_FROM") ? atoi(getenv("I2LQR_STREAM_FROM")) : 26;  // tuning switch: first horizon that streams
+  if (stream_ok && kp.N >= stream_from && w.n_items >= 2048) scratch = 4;
   if (force >= 0) scratch = force;
+  if (scratch >= 4 && !stream_ok) scratch = 2;
   if (scratch == 3 && !tmem_ok) scratch = 0;
   if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
   if (scratch == 2 && smem_cur > kSmemLimit) scratch = 1;
@@ -218,11 +223,14 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   } else {
     k64 = w.mode == 0 ? pick64(std::integral_constant<int, 0>()) : pick64(std::integral_constant<int, 1>());
     if (scratch == 3) k64 = solve_kernel<double, false, 3, 0, kTmemThreads>;
+    if (scratch == 4) k64 = kp.has_qr ? solve_kernel<double, true, 4, 0, kSolveThreads> : solve_kernel<double, false, 4, 0, kSolveThreads>;
+    if (scratch == 5) k64 = kp.has_qr ? solve_kernel<double, true, 5, 0, kSolveThreads> : solve_kernel<double, false, 5, 0, kSolveThreads>;
   }
   const void* kern = fp32 ? (const void*)k32 : (const void*)k64;
   int per_sm = 0;
   size_t smem = scratch == 0 ? smem_full * rsz / sizeof(double)
                              : (scratch == 2 ? smem_cur : (scratch == 3 ? (size_t)kTmemThreads * 8 * kp.N * sizeof(double) : 0));
+  if (scratch >= 4) smem = stream_smem_bytes(scratch == 4 ? kStreamRing : 4);
   // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
   static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
   if (smem > 0 && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
@@ -238,6 +246,13 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
     per_sm = std::max(1, std::min<int>(per_sm, (int)((kSmemLimit - 1024) / (smem + 1024))));
   }
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
+  if (scratch >= 4) {
+    static const int stream_blocks = getenv("I2LQR_STREAM_BLOCKS") ? atoi(getenv("I2LQR_STREAM_BLOCKS")) : 0;  // tuning switch: warps per SM
+    if (stream_blocks > 0) grid = std::min<long long>(grid, (long long)stream_blocks * h->n_sms);
+    CU(h->gscratch[pipe].ensure((size_t)grid * stream_warp_doubles(kp.N)));
+    w.gscratch = h->gscratch[pipe].p;
+    w.gstride = 0;
+  }
   if (scratch == 1 || scratch == 2) {
     const size_t per_lane = scratch == 1 ? 18 * kp.N : 10 * kp.N;
     CU(h->gscratch[pipe].ensure((size_t)grid * threads * per_lane));  // sized in doubles: enough for either precision

@@ -66,8 +66,27 @@ struct DevObstacle {  // mirrors i2lqr_obstacle (include/i2lqr.h)
 //   HybridScratch current trajectory in shared memory, gains in the global slab: 384 instead of 864 bytes of
 //                 shared memory per lane at N=6, i.e. 12 instead of 8 resident warps per SM.
 // Scalar-addressed gains region shared by the memory-backed scratch types.
+// Stage-loop protocol shared by all scratch types.  The backward pass, the forward pass and the accept copy walk
+// the stages strictly in order; a scratch that STREAMS its slots through shared memory (StreamScratch) fetches
+// ahead in begin / done and blocks in wait, for the others these are empty.  ldcs(k, i) is element i of the current
+// trajectory's slot k as seen INSIDE those loops (a ring slot when streaming); ldc / stc address the backing store
+// directly and are what the code outside the loops uses (candidate start, result, parking).
+template <class Derived>
+struct StageLoopDefaults {
+  static constexpr bool kStream = false;
+  __device__ __forceinline__ void bwd_begin(int) const {}
+  __device__ __forceinline__ void bwd_wait(int) const {}
+  __device__ __forceinline__ void bwd_done(int) const {}
+  __device__ __forceinline__ void fwd_begin(int) const {}
+  __device__ __forceinline__ void fwd_wait(int) const {}
+  __device__ __forceinline__ void fwd_done(int) const {}
+  __device__ __forceinline__ void cpy_begin(int) const {}
+  __device__ __forceinline__ void cpy_wait(int) const {}
+  __device__ __forceinline__ void cpy_done(int) const {}
+  __device__ __forceinline__ auto ldcs(int k, int i) const { return static_cast<const Derived*>(this)->ldc(k * 8 + i); }
+};
 template <class Derived, typename R>
-struct GainsByElement {
+struct GainsByElement : StageLoopDefaults<Derived> {
   static constexpr bool kAligned = false;
   static constexpr bool kPrefetchCur = false;  // current-trajectory loads are cheap (shared memory)
   __device__ __forceinline__ void stg10(int k, const R (&v)[10]) const {
@@ -148,7 +167,7 @@ struct HybridScratch : GainsByElement<HybridScratch<R, kStride>, R> {
 // 20 columns (10 doubles) per stage.  tcgen05.ld / tcgen05.st are warp-collective (.sync.aligned), which is
 // why ilqr_iteration is executed convergently by all 32 lanes.
 template <int kStride>
-struct TmemScratch {
+struct TmemScratch : StageLoopDefaults<TmemScratch<kStride>> {
   using real = double;
   static constexpr bool kAligned = true;
   static constexpr bool kPrefetchCur = false;
@@ -212,6 +231,168 @@ struct TmemScratch {
   __device__ __forceinline__ void fence_gains() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 #endif
+
+// StreamScratch (long horizons): a lane's 18 N doubles live in global memory, laid out per WARP as
+//   CUR [N][8][32 lanes]   current trajectory slots        NEW [N][10][32 lanes]   gains / trial trajectory slots
+// so that one stage of one region is a contiguous 2 KB / 2.5 KB block.  All three stage loops walk the stages in
+// order, so the warp streams them through a shared-memory ring of kRing slots with bulk asynchronous copies
+// (cp.async.bulk global -> shared, completion on an mbarrier per slot: the TMA engine moves the data, one lane
+// issues): the loads of the next kRing - 1 stages are in flight while a stage computes, and the loop bodies read
+// shared memory.  Results (gains, trial, accepted trajectory) go straight to global memory with coalesced stores,
+// 256 B per element per warp.  The kernel is then bound by memory bandwidth (~57 N doubles per iteration and
+// candidate against 927 N flops) instead of by dependent L2 / HBM round trips per stage.
+template <int kRing>
+struct StreamScratch : StageLoopDefaults<StreamScratch<kRing>> {
+  using real = double;
+  static constexpr bool kAligned = true;  // mbarrier waits and bulk copies are warp-wide: every lane runs the iteration
+  static constexpr bool kPrefetchCur = false;
+  static constexpr bool kStream = true;
+  static constexpr int kSlot = 18 * 32;   // doubles per ring slot: CUR part [8][32], then NEW part [10][32]
+  static_assert((kRing & (kRing - 1)) == 0 && kRing >= 4, "ring size: a power of two, at least 4");
+  double* ring;    // shared
+  uint32_t bars;   // shared address of kRing mbarriers
+  double* gcur;    // global
+  double* gnew;    // global
+  int lane, N;
+  mutable unsigned phase;  // expected parity per slot (the scratch is handed around as a const reference)
+#ifdef __CUDACC__
+  __device__ __forceinline__ void bind_stream(double* ring_smem, double* gwarp, int lane_, int N_) {
+    ring = ring_smem;
+    bars = (uint32_t)__cvta_generic_to_shared(ring_smem + (size_t)kRing * kSlot);
+    gcur = gwarp;
+    gnew = gwarp + (size_t)N_ * 8 * 32;
+    lane = lane_;
+    N = N_;
+    phase = 0;
+    if (lane == 0) {
+      for (int i = 0; i < kRing; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * i) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // ---- backing store, direct
+  __device__ __forceinline__ double ldc(int e) const { return gcur[(size_t)e * 32 + lane]; }
+  __device__ __forceinline__ void stc(int e, double v) const { gcur[(size_t)e * 32 + lane] = v; }
+  __device__ __forceinline__ void stg10(int k, const double (&v)[10]) const {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) gnew[((size_t)k * 10 + i) * 32 + lane] = v[i];
+  }
+  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gnew[((size_t)k * 10 + i) * 32 + lane] = v[i];
+  }
+  __device__ __forceinline__ void fence_gains() const {}
+  // The finished trajectory of lane `j` in the reference's layout, xvar (4, N+1) and uvar (2, N), written by the WHOLE warp
+  // (lane l takes stages l, l + 32, ...): a lane copying its own 6 N values is a chain of 6 N dependent global loads, each
+  // followed by a store, during which the other 31 candidates of the warp stand still (measured: a third of the kernel).
+  __device__ __forceinline__ void store_lane(int j, const double (&x0)[4], double* xv, double* uv) const {
+    for (int k = lane; k < N; k += 32) {
+      const double* slot = gcur + (size_t)k * 8 * 32 + j;
+      if (uv != nullptr) {
+        uv[k] = slot[0];
+        uv[N + k] = slot[32];
+      }
+      if (xv != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i * (N + 1) + k + 1] = slot[(2 + i) * 32];
+      }
+    }
+    if (lane == 0 && xv != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i * (N + 1)] = x0[i];
+    }
+  }
+  // ---- ring
+  __device__ __forceinline__ double ldcs(int k, int i) const { return ring[(k & (kRing - 1)) * kSlot + i * 32 + lane]; }
+  __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (8 + i) * 32 + lane];
+  }
+  __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (8 + i) * 32 + lane];
+  }
+  // what to fetch of a stage: 1 = CUR slot, 2 = NEW slot (10 elements), 4 = the trial part of the NEW slot (8 elements)
+  __device__ __forceinline__ void issue(int k, int what) const {
+    if (lane != 0) return;
+    const int slot = k & (kRing - 1);
+    const uint32_t bar = bars + 8 * slot;
+    const uint32_t bytes = ((what & 1) ? 2048u : 0u) + ((what & 2) ? 2560u : 0u) + ((what & 4) ? 2048u : 0u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)slot * kSlot);
+    if (what & 1)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(gcur + (size_t)k * 8 * 32), "r"(2048u), "r"(bar)
+                   : "memory");
+    if (what & 6)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2048u),
+                   "l"(gnew + (size_t)k * 10 * 32), "r"((what & 2) ? 2560u : 2048u), "r"(bar)
+                   : "memory");
+  }
+  __device__ __forceinline__ void wait(int k) const {
+    const int slot = k & (kRing - 1);
+    const uint32_t bar = bars + 8 * slot, par = (phase >> slot) & 1u;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(par)
+        : "memory");
+    phase ^= 1u << slot;
+  }
+  // Everything the warp wrote to global memory with ordinary stores (candidate start, gains, trial, accepted slots)
+  // must be visible to the bulk copies (async proxy) that read it back, and nobody may still be reading a ring slot
+  // that the next pass refills.
+  __device__ __forceinline__ void pass_fence() const {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncwarp();
+  }
+  // backward: stages N-1 ... 0, stage k reads CUR slots k and k-1
+  __device__ __forceinline__ void bwd_begin(int) const {
+    pass_fence();
+    for (int k = N - 1; k >= 0 && k > N - 1 - kRing; --k) issue(k, 1);
+    wait(N - 1);
+  }
+  __device__ __forceinline__ void bwd_wait(int k) const {
+    if (k > 0) wait(k - 1);
+  }
+  __device__ __forceinline__ void bwd_done(int k) const {
+    __syncwarp();
+    if (k - kRing >= 0) issue(k - kRing, 1);
+  }
+  // forward: stages 0 ... N-1, stage k reads CUR slots k-1, k and NEW slots k, k+1
+  __device__ __forceinline__ void fwd_begin(int) const {
+    pass_fence();
+    for (int k = 0; k < N && k < kRing; ++k) issue(k, 3);
+    wait(0);
+  }
+  __device__ __forceinline__ void fwd_wait(int k) const {
+    if (k + 1 < N) wait(k + 1);
+  }
+  __device__ __forceinline__ void fwd_done(int k) const {
+    __syncwarp();
+    if (k >= 1 && k - 1 + kRing < N) issue(k - 1 + kRing, 3);
+  }
+  // accept copy: stages 0 ... N-1, stage k reads the trial part of NEW slots k (already in registers) and k+1
+  __device__ __forceinline__ void cpy_begin(int) const {
+    pass_fence();
+    for (int k = 0; k < N && k < kRing; ++k) issue(k, 4);
+    wait(0);
+  }
+  __device__ __forceinline__ void cpy_wait(int k) const {
+    if (k + 1 < N) wait(k + 1);
+  }
+  __device__ __forceinline__ void cpy_done(int k) const {
+    __syncwarp();
+    if (k + kRing < N) issue(k + kRing, 4);
+  }
+#endif
+};
 // Scratch layout for horizon N (18 N doubles per candidate):
 //   cur slot k (8):  [0..1] u_k   [2..5] x_{k+1}   [6] cos(theta_{k+1})  [7] sin(theta_{k+1})
 //   new slot k (10): gains [0..1] k_k, [2..9] K_k (row-major 2x4) after the backward pass; the forward pass
@@ -355,9 +536,10 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   const R dt = p.dt;
   // ---- value function at the horizon end: get_cost_final (ilqr_helper.py:106-150)
+  s.bwd_begin(N);
   R xN[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) xN[i] = s.ldc(I2_CUR(N - 1) + 2 + i);
+  for (int i = 0; i < 4; ++i) xN[i] = s.ldcs(N - 1, 2 + i);
   R Vx0, Vx1, Vx2, Vx3;
   {
     R e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
@@ -379,20 +561,20 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
   }
   // operands of one stage: u_k, v_{k+1}, cos / sin theta_{k+1} from slot k, x_k from slot k-1 (x_0 for k = 0)
   auto load_stage = [&](int k, R (&o)[9]) {
-    o[0] = s.ldc(I2_CUR(k) + 0);
-    o[1] = s.ldc(I2_CUR(k) + 1);
-    o[2] = s.ldc(I2_CUR(k) + 4);
-    o[3] = s.ldc(I2_CUR(k) + 6);
-    o[4] = s.ldc(I2_CUR(k) + 7);
+    o[0] = s.ldcs(k, 0);
+    o[1] = s.ldcs(k, 1);
+    o[2] = s.ldcs(k, 4);
+    o[3] = s.ldcs(k, 6);
+    o[4] = s.ldcs(k, 7);
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[5 + i] = c.x0[i];
     } else {
-      o[5] = s.ldc(I2_CUR(k - 1) + 2);
-      o[6] = s.ldc(I2_CUR(k - 1) + 3);
+      o[5] = s.ldcs(k - 1, 2);
+      o[6] = s.ldcs(k - 1, 3);
       if (kQR) {
-        o[7] = s.ldc(I2_CUR(k - 1) + 4);
-        o[8] = s.ldc(I2_CUR(k - 1) + 5);
+        o[7] = s.ldcs(k - 1, 4);
+        o[8] = s.ldcs(k - 1, 5);
       } else {
         o[7] = o[8] = R(0.0);
       }
@@ -403,6 +585,7 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
 #pragma unroll(kN > 0 ? kN : 1)  // (two stages per trip measured 11 % slower here: 720-instruction body)
   for (int k = N - 1; k >= 0; --k) {
     // ---- trajectory at stage k
+    s.bwd_wait(k);
     R op[9];
     if (Scratch::kPrefetchCur) {
 #pragma unroll
@@ -510,6 +693,7 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
       const R gv[10] = {k0, k1, K00, K01, K02, K03, K10, K11, K12, K13};
       s.stg10(k, gv);
     }
+    s.bwd_done(k);
     // ---- value function update with the unregularised Quu: iterative_ilqr.py:128-129
     const R P00 = fma(K10, Quu10, K00 * Quu00), P01 = fma(K10, Quu11, K00 * Quu01);
     const R P10 = fma(K11, Quu10, K01 * Quu00), P11 = fma(K11, Quu11, K01 * Quu01);
@@ -542,11 +726,13 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
   R cs = c.c0, sn = c.s0;
   R Jn = R(0.0), Jt = R(0.0);
   R g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
+  s.fwd_begin(N);
   s.ldg10(0, g);
 #pragma unroll
   for (int i = 0; i < 10; ++i) gn[i] = g[i];
 #pragma unroll(kN > 0 ? kN : 2)  // two stages per trip: the one-stage-ahead operand registers need no rotation moves
   for (int k = 0; k < N; ++k) {
+    s.fwd_wait(k);
     s.ldg10(k + 1 < N ? k + 1 : k, gn);  // clamped, not conditional: the prefetch must never leave the lane's strip
     R xo[4];
     if (k == 0) {
@@ -554,9 +740,9 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
       for (int i = 0; i < 4; ++i) xo[i] = c.x0[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xo[i] = s.ldc(I2_CUR(k - 1) + 2 + i);
+      for (int i = 0; i < 4; ++i) xo[i] = s.ldcs(k - 1, 2 + i);
     }
-    const R uo0 = s.ldc(I2_CUR(k) + 0), uo1 = s.ldc(I2_CUR(k) + 1);
+    const R uo0 = s.ldcs(k, 0), uo1 = s.ldcs(k, 1);
     const R d0 = x[0] - xo[0], d1 = x[1] - xo[1], d2 = x[2] - xo[2], d3 = x[3] - xo[3];
     // u + k + K (x - xo) with the sign-flipped gains of backward_pass
     R ua = (uo0 - g[0]) - fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
@@ -580,6 +766,7 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) g[i] = gn[i];
+    s.fwd_done(k);
   }
   const R T = terminal_cost(p, c, x);
   Jtarget = Jt + T;
@@ -616,14 +803,17 @@ __device__ __forceinline__ bool ilqr_iteration(const KParamsT<R>& p, CandT<R>& c
   s.fence_gains();
   const int N = kN > 0 ? kN : p.N;
   const bool accept = live && Jn < c.J;
-  if (Scratch::kAligned || accept) {
+  // (a streaming scratch moves whole warp-wide slots: the copy is skipped only when no lane of the warp accepted)
+  if (Scratch::kStream ? __any_sync(0xffffffffu, accept) : (Scratch::kAligned || accept)) {
     // trial -> current; the trial of stage k+1 is loaded while stage k is stored
     R t[8], tn[8];
+    s.cpy_begin(N);
     s.ldg8(0, t);
 #pragma unroll
     for (int i = 0; i < 8; ++i) tn[i] = t[i];
 #pragma unroll 2
     for (int k = 0; k < N; ++k) {
+      s.cpy_wait(k);
       s.ldg8(k + 1 < N ? k + 1 : k, tn);  // clamped prefetch (see forward_pass)
       if (accept) {
 #pragma unroll
@@ -631,6 +821,7 @@ __device__ __forceinline__ bool ilqr_iteration(const KParamsT<R>& p, CandT<R>& c
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = tn[i];
+      s.cpy_done(k);
     }
   }
   if (!live) return false;

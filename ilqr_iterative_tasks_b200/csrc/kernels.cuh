@@ -93,13 +93,19 @@ constexpr int kTmemMaxHorizon = 25;  // 20 32-bit TMEM columns per stage: 128 co
 __host__ __device__ __forceinline__ int tmem_columns(int N) { return 20 * N <= 128 ? 128 : (20 * N <= 256 ? 256 : 512); }
 
 // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab),
-//           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8)
+//           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8),
+//           4 = global memory streamed through a shared-memory ring by bulk asynchronous copies (long horizons)
+constexpr int kStreamRing = 8;  // ring slots per warp (4.5 KB each): the loads of the next 6-7 stages are in flight
 template <typename R, int kScratch, int kThreads>
 struct ScratchSelect {
   using type = typename std::conditional<kScratch == 0, SmemScratch<R, kThreads>,
                typename std::conditional<kScratch == 1, GlobalScratch<R>,
-               typename std::conditional<kScratch == 2, HybridScratch<R, kThreads>, TmemScratch<kThreads>>::type>::type>::type;
-};
+               typename std::conditional<kScratch == 2, HybridScratch<R, kThreads>,
+               typename std::conditional<kScratch == 3, TmemScratch<kThreads>,
+               typename std::conditional<kScratch == 4, StreamScratch<kStreamRing>, StreamScratch<4>>::type>::type>::type>::type>::type;
+};  // (kScratch 5 = the streaming placement with a 4-slot ring: half the shared memory per warp, twice the warps per SM)
+__host__ __device__ __forceinline__ size_t stream_smem_bytes(int ring = kStreamRing) { return (size_t)ring * 18 * 32 * sizeof(double) + ring * 8; }
+__host__ __device__ __forceinline__ size_t stream_warp_doubles(int N) { return (size_t)N * 18 * 32; }
 
 // R = double is the product path (results within 1e-9 of the reference); R = float is the optional FP32
 // build of BASELINE config 4 (inputs / outputs stay double, everything in between is single precision).
@@ -124,6 +130,9 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     s.bind_tmem(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
     for (int e = 0; e < 8 * p.N; ++e) s.stc(e, R(0.0));  // lanes without a live candidate iterate on zeros
+  } else if constexpr (kScratch >= 4) {
+    s.bind_stream(smem_raw, w.gscratch + (size_t)blockIdx.x * stream_warp_doubles(p.N), threadIdx.x & 31, p.N);
+    for (int e = 0; e < 18 * p.N; ++e) s.gcur[(size_t)e * 32 + (threadIdx.x & 31)] = 0.0;  // lanes without a live candidate iterate on zeros
   } else {
     s.bind(smem + threadIdx.x, reinterpret_cast<R*>(w.gscratch) + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
   }
@@ -164,7 +173,24 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
       trip = trip + 1 == kServiceTrips ? 0 : trip + 1;
       if (service) {
         // (z) lanes flagged in the previous trips: results out, or park
-        if (state == ST_FIN) {
+        if constexpr (ScratchT::kStream) {  // long horizons: the warp writes each finished lane's trajectory together
+          __syncwarp();
+          unsigned fm = __ballot_sync(0xffffffffu, state == ST_FIN);
+          while (fm) {
+            const int j = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const long long it_j = __shfl_sync(0xffffffffu, item, j);
+            double x0j[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x0j[i] = __shfl_sync(0xffffffffu, (double)c.x0[i], j);
+            s.store_lane(j, x0j, w.xvar ? w.xvar + it_j * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + it_j * 2 * N : nullptr);
+          }
+          if (state == ST_FIN) {
+            if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
+            if (w.iters) w.iters[item] = c.iters;
+            state = ST_NEED;
+          }
+        } else if (state == ST_FIN) {
           store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
           if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
           if (w.iters) w.iters[item] = c.iters;

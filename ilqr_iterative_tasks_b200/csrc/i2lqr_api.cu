@@ -649,7 +649,11 @@ int launch_flat(i2lqr_handle* h, int64_t lo, int64_t n, const double* x0, const 
   // Iteration slicing (see solve_kernel): big batches run as four passes -- candidates still unfinished after
   // 32 / 64 / 96 iterations are parked and resumed, packed into full warps, by the next pass.
   static const int cap0 = getenv("I2LQR_ITER_CAP") ? atoi(getenv("I2LQR_ITER_CAP")) : 32;  // tuning switch; 0 = off
-  if (cap0 <= 0 || n < kSliceMinBatch) return launch_solve(h, w, st, pipe);
+  // (the streaming placement of long horizons runs as one pass: a resume pass costs up to 32 iterations x N stages of
+  // latency whatever the number of parked candidates -- N = 200, 2^20 candidates: 251 ms in one pass, 280 ms in four)
+  static const int stream_from_ = getenv("I2LQR_STREAM_FROM") ? atoi(getenv("I2LQR_STREAM_FROM")) : 26;
+  const bool streams = h->params.precision == 0 && h->kp.N >= stream_from_ && !(getenv("I2LQR_SCRATCH") && atoi(getenv("I2LQR_SCRATCH")) < 4);
+  if (cap0 <= 0 || n < kSliceMinBatch || streams) return launch_solve(h, w, st, pipe);
   const long long capacity = std::max<long long>(65536, n / 4);
   const size_t words = (size_t)(8 * N + 4);
   for (int b = 0; b < 2; ++b) {

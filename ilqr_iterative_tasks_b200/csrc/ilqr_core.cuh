@@ -232,22 +232,26 @@ struct TmemScratch : StageLoopDefaults<TmemScratch<kStride>> {
 };
 #endif
 
-// StreamScratch (long horizons): a lane's 18 N doubles live in global memory, laid out per WARP as
-//   CUR [N][8][32 lanes]   current trajectory slots        NEW [N][10][32 lanes]   gains / trial trajectory slots
-// so that one stage of one region is a contiguous 2 KB / 2.5 KB block.  All three stage loops walk the stages in
+// StreamScratch (long horizons): a lane's working set lives in global memory, laid out per WARP as
+//   CUR [N][6][32 lanes]   current trajectory slots        NEW [N][10][32 lanes]   gains / trial trajectory slots
+// so that one stage of one region is a contiguous 1.5 KB / 2.5 KB block.  All three stage loops walk the stages in
 // order, so the warp streams them through a shared-memory ring of kRing slots with bulk asynchronous copies
 // (cp.async.bulk global -> shared, completion on an mbarrier per slot: the TMA engine moves the data, one lane
-// issues): the loads of the next kRing - 1 stages are in flight while a stage computes, and the loop bodies read
+// issues): the loads of the next kRing - 2 stages are in flight while a stage computes, and the loop bodies read
 // shared memory.  Results (gains, trial, accepted trajectory) go straight to global memory with coalesced stores,
-// 256 B per element per warp.  The kernel is then bound by memory bandwidth (~57 N doubles per iteration and
-// candidate against 927 N flops) instead of by dependent L2 / HBM round trips per stage.
+// 256 B per element per warp.  The kernel is then bound by HBM bandwidth (measured at N = 50: 4.8 TB/s of DRAM
+// traffic) instead of by dependent L2 / HBM round trips per stage -- so the slots carry no cos / sin of the heading
+// (6 doubles: u_k, x_{k+1}): the backward pass recomputes them with the same routine from the same heading, bit for
+// bit what the other placements store, and a sixth of the traffic is gone.
 template <int kRing>
 struct StreamScratch : StageLoopDefaults<StreamScratch<kRing>> {
   using real = double;
   static constexpr bool kAligned = true;  // mbarrier waits and bulk copies are warp-wide: every lane runs the iteration
   static constexpr bool kPrefetchCur = false;
   static constexpr bool kStream = true;
-  static constexpr int kSlot = 18 * 32;   // doubles per ring slot: CUR part [8][32], then NEW part [10][32]
+  static constexpr int kCur = 6;                  // doubles per current-trajectory / trial slot
+  static constexpr int kSlot = (kCur + 10) * 32;  // doubles per ring slot: CUR part [6][32], then NEW part [10][32]
+  static constexpr unsigned kCurBytes = kCur * 32 * 8, kNewBytes = 10 * 32 * 8;
   static_assert((kRing & (kRing - 1)) == 0 && kRing >= 4, "ring size: a power of two, at least 4");
   double* ring;    // shared
   uint32_t bars;   // shared address of kRing mbarriers
@@ -260,7 +264,7 @@ struct StreamScratch : StageLoopDefaults<StreamScratch<kRing>> {
     ring = ring_smem;
     bars = (uint32_t)__cvta_generic_to_shared(ring_smem + (size_t)kRing * kSlot);
     gcur = gwarp;
-    gnew = gwarp + (size_t)N_ * 8 * 32;
+    gnew = gwarp + (size_t)N_ * kCur * 32;
     lane = lane_;
     N = N_;
     phase = 0;
@@ -270,31 +274,56 @@ struct StreamScratch : StageLoopDefaults<StreamScratch<kRing>> {
     }
     __syncwarp();
   }
-  // ---- backing store, direct
-  __device__ __forceinline__ double ldc(int e) const { return gcur[(size_t)e * 32 + lane]; }
-  __device__ __forceinline__ void stc(int e, double v) const { gcur[(size_t)e * 32 + lane] = v; }
+  // ---- backing store, direct.  e = 8 k + i as everywhere else; i = 6, 7 (cos / sin of the heading) are not stored.
+  __device__ __forceinline__ double ldc(int e) const {
+    const int k = e >> 3, i = e & 7;
+    if (i < kCur) return gcur[((size_t)k * kCur + i) * 32 + lane];
+    double sn, cs;
+    sincos_fast(gcur[((size_t)k * kCur + 5) * 32 + lane], &sn, &cs);
+    return i == 6 ? cs : sn;
+  }
+  __device__ __forceinline__ void stc(int e, double v) const {
+    const int k = e >> 3, i = e & 7;
+    if (i < kCur) gcur[((size_t)k * kCur + i) * 32 + lane] = v;
+  }
   __device__ __forceinline__ void stg10(int k, const double (&v)[10]) const {
 #pragma unroll
     for (int i = 0; i < 10; ++i) gnew[((size_t)k * 10 + i) * 32 + lane] = v[i];
   }
   __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) gnew[((size_t)k * 10 + i) * 32 + lane] = v[i];
+    for (int i = 0; i < kCur; ++i) gnew[((size_t)k * 10 + i) * 32 + lane] = v[i];
   }
   __device__ __forceinline__ void fence_gains() const {}
   // The finished trajectory of lane `j` in the reference's layout, xvar (4, N+1) and uvar (2, N), written by the WHOLE warp
   // (lane l takes stages l, l + 32, ...): a lane copying its own 6 N values is a chain of 6 N dependent global loads, each
   // followed by a store, during which the other 31 candidates of the warp stand still (measured: a third of the kernel).
-  __device__ __forceinline__ void store_lane(int j, const double (&x0)[4], double* xv, double* uv) const {
-    for (int k = lane; k < N; k += 32) {
-      const double* slot = gcur + (size_t)k * 8 * 32 + j;
+  __device__ __forceinline__ void store_lane(int j, const double (&x0)[4], double* __restrict__ xv, double* __restrict__ uv) const {
+    for (int k0 = lane; k0 < N; k0 += 64) {  // two stages per lane and trip: twelve loads in flight before the first store
+      const int k1 = k0 + 32;
+      const bool two = k1 < N;
+      const double* s0 = gcur + (size_t)k0 * kCur * 32 + j;
+      const double* s1 = gcur + (size_t)(two ? k1 : k0) * kCur * 32 + j;
+      double a[kCur], b[kCur];
+#pragma unroll
+      for (int i = 0; i < kCur; ++i) {
+        a[i] = __ldcg(s0 + i * 32);
+        b[i] = __ldcg(s1 + i * 32);
+      }
       if (uv != nullptr) {
-        uv[k] = slot[0];
-        uv[N + k] = slot[32];
+        uv[k0] = a[0];
+        uv[N + k0] = a[1];
+        if (two) {
+          uv[k1] = b[0];
+          uv[N + k1] = b[1];
+        }
       }
       if (xv != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i * (N + 1) + k + 1] = slot[(2 + i) * 32];
+        for (int i = 0; i < 4; ++i) {
+          xv[i * (N + 1) + k0 + 1] = a[2 + i];
+          if (two) xv[i * (N + 1) + k1 + 1] = b[2 + i];
+        }
       }
     }
     if (lane == 0 && xv != nullptr) {
@@ -303,30 +332,31 @@ struct StreamScratch : StageLoopDefaults<StreamScratch<kRing>> {
     }
   }
   // ---- ring
-  __device__ __forceinline__ double ldcs(int k, int i) const { return ring[(k & (kRing - 1)) * kSlot + i * 32 + lane]; }
+  __device__ __forceinline__ double ldcs(int k, int i) const { return ring[(k & (kRing - 1)) * kSlot + i * 32 + lane]; }  // i < 6
   __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (8 + i) * 32 + lane];
+    for (int i = 0; i < 10; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (kCur + i) * 32 + lane];
   }
   __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (8 + i) * 32 + lane];
+    for (int i = 0; i < kCur; ++i) v[i] = ring[(k & (kRing - 1)) * kSlot + (kCur + i) * 32 + lane];
+    v[6] = v[7] = 0.0;
   }
-  // what to fetch of a stage: 1 = CUR slot, 2 = NEW slot (10 elements), 4 = the trial part of the NEW slot (8 elements)
+  // what to fetch of a stage: 1 = CUR slot, 2 = NEW slot (10 elements), 4 = the trial part of the NEW slot (6 elements)
   __device__ __forceinline__ void issue(int k, int what) const {
     if (lane != 0) return;
     const int slot = k & (kRing - 1);
     const uint32_t bar = bars + 8 * slot;
-    const uint32_t bytes = ((what & 1) ? 2048u : 0u) + ((what & 2) ? 2560u : 0u) + ((what & 4) ? 2048u : 0u);
+    const uint32_t bytes = ((what & 1) ? kCurBytes : 0u) + ((what & 2) ? kNewBytes : 0u) + ((what & 4) ? kCurBytes : 0u);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (size_t)slot * kSlot);
     if (what & 1)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                   "l"(gcur + (size_t)k * 8 * 32), "r"(2048u), "r"(bar)
+                   "l"(gcur + (size_t)k * kCur * 32), "r"(kCurBytes), "r"(bar)
                    : "memory");
     if (what & 6)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + 2048u),
-                   "l"(gnew + (size_t)k * 10 * 32), "r"((what & 2) ? 2560u : 2048u), "r"(bar)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + kCurBytes),
+                   "l"(gnew + (size_t)k * 10 * 32), "r"((what & 2) ? kNewBytes : kCurBytes), "r"(bar)
                    : "memory");
   }
   __device__ __forceinline__ void wait(int k) const {
@@ -564,8 +594,12 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
     o[0] = s.ldcs(k, 0);
     o[1] = s.ldcs(k, 1);
     o[2] = s.ldcs(k, 4);
-    o[3] = s.ldcs(k, 6);
-    o[4] = s.ldcs(k, 7);
+    if constexpr (Scratch::kStream) {  // (the streamed slots carry no cos / sin: same routine, same heading, same bits)
+      sincos_fast(R(s.ldcs(k, 5)), &o[4], &o[3]);
+    } else {
+      o[3] = s.ldcs(k, 6);
+      o[4] = s.ldcs(k, 7);
+    }
     if (k == 0) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[5 + i] = c.x0[i];

@@ -95,7 +95,7 @@ __host__ __device__ __forceinline__ int tmem_columns(int N) { return 20 * N <= 1
 // kScratch: 0 = shared memory, 1 = global slab, 2 = hybrid (trajectory in shared memory, gains in the slab),
 //           3 = trajectory in shared memory, gains in tensor memory (12 resident warps per SM instead of 8),
 //           4 = global memory streamed through a shared-memory ring by bulk asynchronous copies (long horizons)
-constexpr int kStreamRing = 8;  // ring slots per warp (4.5 KB each): the loads of the next 6-7 stages are in flight
+constexpr int kStreamRing = 8;  // ring slots per warp (4 KB each): the loads of the next 6-7 stages are in flight
 template <typename R, int kScratch, int kThreads>
 struct ScratchSelect {
   using type = typename std::conditional<kScratch == 0, SmemScratch<R, kThreads>,
@@ -104,13 +104,13 @@ struct ScratchSelect {
                typename std::conditional<kScratch == 3, TmemScratch<kThreads>,
                typename std::conditional<kScratch == 4, StreamScratch<kStreamRing>, StreamScratch<4>>::type>::type>::type>::type>::type;
 };  // (kScratch 5 = the streaming placement with a 4-slot ring: half the shared memory per warp, twice the warps per SM)
-__host__ __device__ __forceinline__ size_t stream_smem_bytes(int ring = kStreamRing) { return (size_t)ring * 18 * 32 * sizeof(double) + ring * 8; }
-__host__ __device__ __forceinline__ size_t stream_warp_doubles(int N) { return (size_t)N * 18 * 32; }
+__host__ __device__ __forceinline__ size_t stream_smem_bytes(int ring = kStreamRing) { return (size_t)ring * 16 * 32 * sizeof(double) + ring * 8; }
+__host__ __device__ __forceinline__ size_t stream_warp_doubles(int N) { return (size_t)N * 16 * 32; }
 
 // R = double is the product path (results within 1e-9 of the reference); R = float is the optional FP32
 // build of BASELINE config 4 (inputs / outputs stay double, everything in between is single precision).
 template <typename R, bool kQR, int kScratch, int kMode, int kThreads>
-__global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : (kScratch == 5 ? 12 : 1))
 solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
   extern __shared__ double smem_raw[];
   R* smem = reinterpret_cast<R*>(smem_raw);
@@ -132,7 +132,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     for (int e = 0; e < 8 * p.N; ++e) s.stc(e, R(0.0));  // lanes without a live candidate iterate on zeros
   } else if constexpr (kScratch >= 4) {
     s.bind_stream(smem_raw, w.gscratch + (size_t)blockIdx.x * stream_warp_doubles(p.N), threadIdx.x & 31, p.N);
-    for (int e = 0; e < 18 * p.N; ++e) s.gcur[(size_t)e * 32 + (threadIdx.x & 31)] = 0.0;  // lanes without a live candidate iterate on zeros
+    for (int e = 0; e < 16 * p.N; ++e) s.gcur[(size_t)e * 32 + (threadIdx.x & 31)] = 0.0;  // lanes without a live candidate iterate on zeros
   } else {
     s.bind(smem + threadIdx.x, reinterpret_cast<R*>(w.gscratch) + (size_t)blockIdx.x * blockDim.x + threadIdx.x, w.gstride, p.N);
   }

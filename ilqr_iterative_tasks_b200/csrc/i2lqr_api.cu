@@ -1104,7 +1104,11 @@ int clear_step_trace(i2lqr_handle* h, cudaStream_t st) {
 }
 
 // ---- speculative one-launch step (spec_step.cuh)
-constexpr int kSpecMaxChains = 64;
+int spec_max_chains() {
+  static const int n = getenv("I2LQR_SPEC_MAXCHAINS") ? std::max(1, atoi(getenv("I2LQR_SPEC_MAXCHAINS"))) : 256;  // tuning switch
+  return n;
+}
+constexpr long long kSpecMaxEntries = 1ll << 19;  // table entries (344 B each at N = 6)
 
 bool spec_enabled() {
   static const bool on = !(getenv("I2LQR_SPEC") && atoi(getenv("I2LQR_SPEC")) == 0);  // tuning / A-B switch
@@ -1125,9 +1129,9 @@ size_t spec_smem_bytes(const i2lqr_handle* h) {
 bool spec_eligible(const i2lqr_handle* h, int n_episodes) {
   if (!spec_enabled() || h->params.precision != 0) return false;
   const long long chains = (long long)n_episodes * h->L;
-  if (chains < 1 || chains > kSpecMaxChains || h->K < 2) return false;
+  if (chains < 1 || chains > spec_max_chains() || h->K < 2) return false;
   if (spec_smem_bytes(h) > 100 * 1024) return false;
-  return chains * (h->K - 1) * spec_set_size() <= (1 << 16);
+  return (long long)kOuter * chains * h->K * kSpecMaxSet <= kSpecMaxEntries;
 }
 
 // lambda values reachable from lamb0 by the iteration's own /factor and *factor steps, breadth first (same
@@ -1150,7 +1154,7 @@ void spec_seed_patterns(const i2lqr_params& p, std::vector<unsigned long long>* 
 }
 
 int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
-  const int chains = n_episodes * h->L, S = spec_set_size(), K = h->K, N = h->kp.N;
+  const int chains = n_episodes * h->L, S = kSpecMaxSet, K = h->K, N = h->kp.N;  // tables hold the largest set; a launch may use fewer
   const bool first = h->sp_hist_key.p == nullptr;
   if (first) {
     CU(h->sp_hist_key.ensure(kSpecHist));
@@ -1204,7 +1208,6 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   a.set = h->set;
   a.x = h->s_x.p;
   a.ep_obs = h->d_obs.p;
-  a.S = h->sp_S;
   a.c_max = h->sp_cmax;
   a.sel_idx = h->s_sel_idx.p;
   a.sel_cnt = h->s_sel_cnt.p;
@@ -1261,11 +1264,18 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
   if (per_sm < 1) return fail("speculative step kernel does not fit on an SM");
   const long long chains = (long long)sc.n_episodes * h->L;
-  const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * h->sp_S + per_warp - 1) / per_warp);
-  const long long grid = std::min<long long>((long long)per_sm * h->n_sms, chains + workers);
-  if (grid <= chains) return fail("internal: no room for worker warps");
+  const long long resident = (long long)per_sm * h->n_sms;
+  if (resident <= chains) return fail("internal: no room for worker warps");
+  // speculation set size: all of it while one wave of worker groups covers the table, halved down to 4 when the chains are many
+  // (entries the workers cannot reach in time are solved in place by the resolvers: correct, just no faster than the chain itself)
+  int S = spec_set_size();
+  const long long group_slots = (resident - chains) * per_warp;
+  while (S > 4 && chains * std::max(1, a.k_eff - 1) * S > 2 * group_slots) S /= 2;
+  a.S = S;
+  const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * S + per_warp - 1) / per_warp);
+  const long long grid = std::min<long long>(resident, chains + workers);
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
-  if (debug) fprintf(stderr, "[i2lqr] spec step: chains %lld S %d grid %lld smem %zu per_sm %d epoch %u\n", chains, h->sp_S, grid, smem, per_sm, a.epoch);
+  if (debug) fprintf(stderr, "[i2lqr] spec step: chains %lld S %d grid %lld smem %zu per_sm %d epoch %u\n", chains, a.S, grid, smem, per_sm, a.epoch);
   void* args[2] = {(void*)&kp, (void*)&a};
   CU(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kSolveThreads), args, smem, st));
   h->last_launches += 1;
@@ -1701,6 +1711,17 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
   const int tb = 128, gb = (E + tb - 1) / tb;
   volatile int* hw = h->h_nrun;
   int issued = 0;
+  static const bool ep_timing = getenv("I2LQR_EP_TIMING") != nullptr;  // developer switch: per-step device times on stderr
+  std::vector<cudaEvent_t> tev;
+  std::vector<int> tupper;
+  auto tmark = [&]() {
+    if (!ep_timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  tmark();
   static const int lookahead = getenv("I2LQR_EP_LOOKAHEAD") ? atoi(getenv("I2LQR_EP_LOOKAHEAD")) : 4;  // tuning switch
   for (int i = 0; i < S; ++i) {
     // at most `lookahead` steps in flight: a deeper queue would size many steps from the same stale counts
@@ -1720,8 +1741,21 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
     CU(cudaEventRecord(h->ep_ev[i % i2lqr_handle::kEpEvents], st));
     h->last_launches += 3;
     ++issued;
+    tupper.push_back(n_upper);
+    tmark();
   }
   (void)issued;
+  if (ep_timing) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[i2lqr] lap %d: per step (size bound : ms):", h->ep_lap_index);
+    for (size_t i = 0; i + 1 < tev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      fprintf(stderr, " %d:%.2f", tupper[i], ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   episode_finish_kernel<<<(unsigned)(((long long)E * 32 + tb - 1) / tb), tb, 0, st>>>(es, h->set, E, N, h->ep_laplen.p);
   CU(cudaGetLastError());
   h->last_launches += 1;

@@ -164,6 +164,7 @@ __device__ __forceinline__ void chain_task_eval(const KParamsT<R>& p, const Cand
   }
   R g0, g1, l00, l01, l11;
   obstacle_barrier(p, c, t.x[0], t.x[1], terminal ? p.N_param : t.k, g0, g1, l00, l01, l11);
+  if (c.n_ex > 0) obstacle_barrier_extra(p, c, t.x[0], t.x[1], terminal ? p.N_param : t.k, g0, g1, l00, l01, l11);
   R lx2 = R(0.0), lx3 = R(0.0);
   if (kQR) {
     const R d0 = t.x[0] - p.xtarget[0], d1 = t.x[1] - p.xtarget[1], d2 = t.x[2] - p.xtarget[2], d3 = t.x[3] - p.xtarget[3];

@@ -123,6 +123,12 @@ struct i2lqr_handle {
   std::vector<DevObstacle> h_obs;
   DevBuf<DevObstacle> d_obs;
   bool obs_dirty = true;
+  // obstacle lists (extension): up to kMaxExtraObstacles further ellipses per episode
+  std::vector<DevObstacle> h_obs_extra;
+  std::vector<int> h_n_extra;
+  DevBuf<DevObstacle> d_obs_extra, d_obs_extra0;
+  DevBuf<int> d_n_extra;
+  int extras_in_use = 0;  // episodes with a list longer than one
   // controller-step workspace
   DevBuf<double> s_x, s_u, s_xpred, s_upred, s_cand_x, s_cand_u, s_cand_cost, s_cand_lamb, s_wcost;
   DevBuf<long long> s_sel_idx, s_widx, q_idx;
@@ -337,6 +343,8 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   long long grid = std::max<long long>(1, (lanes + kSolveThreads - 1) / kSolveThreads);
   CU(h->ctl.ensure(kCtlWords));
   w.counter = nullptr;
+  if (!lat_form && w.ep_n_extra != nullptr)
+    return fail("obstacle lists need a horizon whose controller-step working set fits shared memory (num_horizon %d is too long)", kp.N);
   if (lat_form) {
     // latency form: never launch more warps than are resident at once -- with more chains than lane groups the groups
     // fetch further chains from a counter as they finish (a second wave of whole warps would double the time)
@@ -405,6 +413,12 @@ int sync_obstacles(i2lqr_handle* h) {
   if (!h->obs_dirty) return 0;
   CU(h->d_obs.ensure(h->E));
   CU(cudaMemcpyAsync(h->d_obs.p, h->h_obs.data(), sizeof(DevObstacle) * h->E, cudaMemcpyHostToDevice, h->stream));
+  if (h->extras_in_use > 0 || h->d_n_extra.p != nullptr) {
+    CU(h->d_obs_extra.ensure((size_t)h->E * kMaxExtraObstacles));
+    CU(h->d_n_extra.ensure(h->E));
+    CU(cudaMemcpyAsync(h->d_obs_extra.p, h->h_obs_extra.data(), sizeof(DevObstacle) * h->E * kMaxExtraObstacles, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_n_extra.p, h->h_n_extra.data(), sizeof(int) * h->E, cudaMemcpyHostToDevice, h->stream));
+  }
   h->obs_dirty = false;
   return 0;
 }
@@ -477,6 +491,8 @@ int create_resources(i2lqr_handle* h, const i2lqr_params* p, int n_episodes, int
     h->h_lap_count.assign(h->E, 0);
     DevObstacle none{};
     h->h_obs.assign(h->E, none);
+    h->h_obs_extra.assign((size_t)h->E * kMaxExtraObstacles, none);
+    h->h_n_extra.assign(h->E, 0);
   }
   CU(cudaStreamSynchronize(h->stream));
   return 0;
@@ -572,6 +588,9 @@ int i2lqr_destroy(i2lqr_handle* h) {
   for (auto& e : h->ep_ev)
     if (e) cudaEventDestroy(e);
   h->d_obs0.release();
+  h->d_obs_extra.release();
+  h->d_obs_extra0.release();
+  h->d_n_extra.release();
   for (auto* b : {&h->sp_state, &h->sp_ctl, &h->sp_hist_cnt}) b->release();
   for (auto* b : {&h->sp_lamb, &h->sp_cost, &h->sp_traj}) b->release();
   h->sp_iters.release();
@@ -905,6 +924,10 @@ int i2lqr_set_obstacles(i2lqr_handle* h, int first, int n, const i2lqr_obstacle*
       if (!o.present) o = DevObstacle{};
     }
     h->h_obs[first + i] = o;
+    if (h->h_n_extra[first + i] > 0) {
+      h->h_n_extra[first + i] = 0;
+      h->extras_in_use -= 1;
+    }
   }
   h->obs_dirty = true;
   return 0;
@@ -926,6 +949,32 @@ int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs) 
       return fail("obstacle with spd != 0 needs moving_option 1 or 2 (control/ilqr_helper.py:34-43)");
   }
   h->h_obs[episode] = o;
+  if (h->h_n_extra[episode] > 0) {  // a single obstacle replaces a list
+    h->h_n_extra[episode] = 0;
+    h->extras_in_use -= 1;
+  }
+  h->obs_dirty = true;
+  return 0;
+}
+
+int i2lqr_set_obstacle_list(i2lqr_handle* h, int episode, const i2lqr_obstacle* list, int n) {
+  if (check_episode(h, episode)) return 1;
+  if (n < 0 || n > 1 + kMaxExtraObstacles) return fail("an obstacle list holds 0..%d obstacles", 1 + kMaxExtraObstacles);
+  if (n > 0 && !list) return fail("null obstacle list");
+  if (n > 1 && h->params.precision != 0) return fail("obstacle lists are FP64 only");
+  if (i2lqr_set_obstacle(h, episode, n > 0 ? list : nullptr)) return 1;  // validates and stores the first, clears an older list
+  for (int m = 1; m < n; ++m) {
+    DevObstacle o{};
+    memcpy(&o, list + m, sizeof o);
+    if (o.present && (o.moving_option < 0 || o.moving_option > 2)) return fail("moving_option must be 0, 1 or 2");
+    if (o.present && o.moving_option == 0 && o.spd != 0.0)
+      return fail("obstacle with spd != 0 needs moving_option 1 or 2 (control/ilqr_helper.py:34-43)");
+    h->h_obs_extra[(size_t)episode * kMaxExtraObstacles + (m - 1)] = o;
+  }
+  if (n > 1) {
+    h->h_n_extra[episode] = n - 1;
+    h->extras_in_use += 1;
+  }
   h->obs_dirty = true;
   return 0;
 }
@@ -1040,6 +1089,10 @@ int launch_chain_step(i2lqr_handle* h, int it, const StepScope& sc, const int* s
   w.set = h->set;
   w.x = h->s_x.p;
   w.ep_obs = h->d_obs.p;
+  if (h->extras_in_use > 0) {
+    w.ep_obs_extra = h->d_obs_extra.p;
+    w.ep_n_extra = h->d_n_extra.p;
+  }
   w.active = d_active;
   w.sel_idx = h->s_sel_idx.p;
   w.sel_cnt = sel_cnt;
@@ -1208,6 +1261,10 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   a.set = h->set;
   a.x = h->s_x.p;
   a.ep_obs = h->d_obs.p;
+  if (h->extras_in_use > 0) {
+    a.ep_obs_extra = h->d_obs_extra.p;
+    a.ep_n_extra = h->d_n_extra.p;
+  }
   a.c_max = h->sp_cmax;
   a.sel_idx = h->s_sel_idx.p;
   a.sel_cnt = h->s_sel_cnt.p;
@@ -1636,6 +1693,11 @@ EpisodeState episode_state(i2lqr_handle* h) {
   s.S = h->params.max_sim_steps;
   s.obs = h->d_obs.p;
   s.obs0 = h->d_obs0.p;
+  if (h->extras_in_use > 0) {
+    s.obs_extra = h->d_obs_extra.p;
+    s.obs_extra0 = h->d_obs_extra0.p;
+    s.n_extra = h->d_n_extra.p;
+  }
   s.goal = h->ep_goal.p;
   s.n_running = h->ep_nrun.p;
   return s;
@@ -1693,6 +1755,10 @@ int i2lqr_episodes_run_lap(i2lqr_handle* h, int32_t* lap_len, double* lap_x, dou
   if (sync_obstacles(h)) return 1;
   CU(h->d_obs0.ensure(E));
   CU(cudaMemcpyAsync(h->d_obs0.p, h->d_obs.p, sizeof(DevObstacle) * E, cudaMemcpyDeviceToDevice, st));
+  if (h->extras_in_use > 0) {
+    CU(h->d_obs_extra0.ensure((size_t)E * kMaxExtraObstacles));
+    CU(cudaMemcpyAsync(h->d_obs_extra0.p, h->d_obs_extra.p, sizeof(DevObstacle) * E * kMaxExtraObstacles, cudaMemcpyDeviceToDevice, st));
+  }
   EpisodeState es = episode_state(h);
   // row 0 of every lap log = the state the lap starts from
   CU(cudaMemcpy2DAsync(h->ep_lapx.p, (size_t)(S + 1) * 4 * sizeof(double), h->s_x.p, 4 * sizeof(double), 4 * sizeof(double), E,

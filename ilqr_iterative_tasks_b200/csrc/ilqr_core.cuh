@@ -442,7 +442,11 @@ struct CandT {
   // `obstacle is None` is encoded as zero scales and zero P so that the same straight-line code runs.
   R ox, oy, oP0, oP1, osx, osy, og, oh;
   int iters;
+  // further obstacles of the episode (extension, controller-step kernels only: SURVEY.md 8 f2); their barrier terms add
+  const DevObstacle* ex;
+  int n_ex;
 };
+constexpr int kMaxExtraObstacles = 3;  // an episode's obstacle list holds up to 1 + 3 ellipses
 using Cand = CandT<double>;
 
 template <typename R>
@@ -480,6 +484,32 @@ __device__ __forceinline__ void obstacle_barrier(const KParamsT<R>& p, const Can
   h00 = c2 * (hd0 * hd0);
   h01 = c2 * (hd0 * hd1);
   h11 = c2 * (hd1 * hd1);
+}
+
+// The same barrier for the further obstacles of an episode's list, ADDED to the primary's terms: the reference's cost
+// loop takes one Obstacle (ilqr_helper.py:16-24,32-51); a list is priced as the sum of its members' barriers, each
+// evaluated exactly as the single one (same association, 1 / w^2 by division as load_obstacle does).
+template <typename R>
+__device__ __forceinline__ void obstacle_barrier_extra(const KParamsT<R>& p, const CandT<R>& c, R px, R py, int step, R& g0, R& g1, R& h00,
+                                                       R& h01, R& h11) {
+  for (int m = 0; m < c.n_ex; ++m) {
+    const DevObstacle o = c.ex[m];
+    if (!o.present) continue;
+    const R st = R(step);
+    const R osx = R(o.moving_option == 2 ? o.spd : 0.0), osy = R(o.moving_option == 1 ? o.spd : 0.0);
+    const R P0 = R(1.0 / (o.width * o.width)), P1 = R(1.0 / (o.height * o.height));
+    const R cx = R(o.x) - st * osx, cy = R(o.y) + st * osy;
+    const R d0 = px - cx, d1 = py - cy;
+    const R h = p.one_margin - ((d0 * P0) * d0 + (d1 * P1) * d1);
+    const R hd0 = (-R(2.0) * P0) * d0, hd1 = (-R(2.0) * P1) * d1;
+    const R e = exp_fast_lo(p.oq2 * h);
+    const R c1 = p.og * e, c2 = p.oh * e;
+    g0 += c1 * hd0;
+    g1 += c1 * hd1;
+    h00 += c2 * (hd0 * hd0);
+    h01 += c2 * (hd0 * hd1);
+    h11 += c2 * (hd1 * hd1);
+  }
 }
 
 // Regularised inverse of the 2x2 Quu (iterative_ilqr.py:118-123): eigen-decompose, clamp negative
@@ -922,6 +952,8 @@ __device__ __forceinline__ void load_obstacle(const KParamsT<R>& p, CandT<R>& c,
   } else {
     c.ox = c.oy = c.oP0 = c.oP1 = c.osx = c.osy = c.og = c.oh = R(0.0);
   }
+  c.ex = nullptr;
+  c.n_ex = 0;
 }
 
 }  // namespace i2lqr

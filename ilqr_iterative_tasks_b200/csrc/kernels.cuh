@@ -62,6 +62,8 @@ struct Work {
   SafeSet set;
   const double* x;             // (E,4) current states
   const DevObstacle* ep_obs;   // (E)
+  const DevObstacle* ep_obs_extra;  // (E, kMaxExtraObstacles) further obstacles per episode, or null
+  const int* ep_n_extra;       // (E) how many of them are in use
   const int* active;           // (E) or null: episodes that solve this step
   const int* ep_list;          // compacted list of the episodes that solve this step, or null (= all n_items / L episodes)
   const int* n_ep;             // device: entries of ep_list
@@ -573,6 +575,10 @@ chain_lat_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ 
       lap = w.set.lap(ep, slot);
       c.lamb = p.lamb0;  // utils/base.py:393
       load_obstacle(p, c, w.ep_obs + ep);
+      if (w.ep_n_extra != nullptr) {
+        c.ex = w.ep_obs_extra + (size_t)ep * kMaxExtraObstacles;
+        c.n_ex = w.ep_n_extra[ep];
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) c.x0[i] = R(w.x[(size_t)ep * 4 + i]);
       sincos_fast(c.x0[3], &c.s0, &c.c0);
@@ -1075,6 +1081,9 @@ struct EpisodeState {
   int S;
   DevObstacle* obs;     // current obstacle per episode (moves)
   const DevObstacle* obs0;
+  DevObstacle* obs_extra;         // (E, kMaxExtraObstacles) or null
+  const DevObstacle* obs_extra0;
+  const int* n_extra;
   const double* goal;   // (4)
   int* n_running;       // episodes whose lap is still running
 };
@@ -1187,6 +1196,14 @@ __global__ void episode_post_kernel(EpisodeState s, const __grid_constant__ KPar
     if (o->moving_option == 1) o->y += o->spd * p.dt;
     if (o->moving_option == 2) o->x -= o->spd * p.dt;
   }
+  if (s.n_extra != nullptr) {
+    for (int m = 0; m < s.n_extra[e]; ++m) {
+      DevObstacle* q = s.obs_extra + (size_t)e * kMaxExtraObstacles + m;
+      if (!q->present) continue;
+      if (q->moving_option == 1) q->y += q->spd * p.dt;
+      if (q->moving_option == 2) q->x -= q->spd * p.dt;
+    }
+  }
   const double d0 = x0 - s.goal[0], d1 = x1 - s.goal[1], d2 = x2 - s.goal[2], d3 = x3 - s.goal[3];
   const bool reached = sqrt(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) <= goal_tol;
   if (reached || sim_i == s.S - 1) {
@@ -1228,6 +1245,8 @@ __global__ void episode_finish_kernel(EpisodeState s, SafeSet set, int E, int N_
     s.horizon[e] = N_param;
     s.pb[e] = 0;
     s.obs[e] = s.obs0[e];
+    if (s.n_extra != nullptr)
+      for (int m = 0; m < kMaxExtraObstacles; ++m) s.obs_extra[(size_t)e * kMaxExtraObstacles + m] = s.obs_extra0[(size_t)e * kMaxExtraObstacles + m];
     for (int i = 0; i < 4; ++i) s.x[(size_t)e * 4 + i] = 0.0;
   }
 }

@@ -39,6 +39,8 @@ struct SpecArgs {
   SafeSet set;
   const double* x;             // (E,4)
   const DevObstacle* ep_obs;   // (E)
+  const DevObstacle* ep_obs_extra;  // (E, kMaxExtraObstacles) or null
+  const int* ep_n_extra;       // (E)
   int S;                       // speculation set size in use, <= kSpecMaxSet
   int c_max;                   // chains the tables are laid out for (>= n_episodes * L)
   int e_stride;                // episodes the per-episode control words are laid out for (>= n_episodes)
@@ -117,6 +119,10 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 template <class Solver>
 __device__ __forceinline__ void spec_bind_episode(const KParams& p, const SpecArgs& a, int ep, Solver& gs) {
   load_obstacle(p, gs.c, a.ep_obs + ep);
+  if (a.ep_n_extra != nullptr) {
+    gs.c.ex = a.ep_obs_extra + (size_t)ep * kMaxExtraObstacles;
+    gs.c.n_ex = a.ep_n_extra[ep];
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) gs.c.x0[i] = a.x[(size_t)ep * 4 + i];
   sincos_fast(gs.c.x0[3], &gs.c.s0, &gs.c.c0);

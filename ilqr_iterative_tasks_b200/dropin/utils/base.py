@@ -18,7 +18,8 @@ What runs where
 
 Observable differences: the inner-loop prints ("k neighbors", "Convergence achieved") are dropped; the plotting
 methods are no-ops; the LMPC-only attributes of `iLqr` (`ss_point_selected_id`, `x_sol`, `u_sol`, `cost_improve`,
-`old_cost`, `old_iter`) are not kept; `max_outloop_iter < 3` raises ValueError (the reference would then do fewer
+`old_cost`, `old_iter`) are not kept; `ilqr.obstacle` may also be a list of up to four `Obstacle`s (extension: their barrier
+terms add); `max_outloop_iter < 3` raises ValueError (the reference would then do fewer
 refinements and never shrink the horizon).  K-nearest
 ties (the stock initial lap ends in identical rows) come out in the order numpy.argsort's scalar introsort leaves
 them -- what the reference's pinned numpy==1.19.5 does; a NumPy >= 1.25 on an AVX2 / AVX-512 host sorts float64
@@ -362,7 +363,10 @@ class iLqr(ControlBase):
                 # (:384,:472-478); the device step is exactly those three outer iterations
                 raise ValueError("max_outloop_iter < 3 is not supported: the controller step runs the reference's three outer iterations")
             eng = self._sync_engine()
-            eng.set_obstacle(0, _abi.obstacle_struct(self.obstacle) if self.obstacle is not None else None)
+            if isinstance(self.obstacle, (list, tuple)):  # extension: several obstacles, their barrier terms add (i2lqr_set_obstacle_list)
+                eng.set_obstacle_list(0, [_abi.obstacle_struct(o) for o in self.obstacle])
+            else:
+                eng.set_obstacle(0, _abi.obstacle_struct(self.obstacle) if self.obstacle is not None else None)
             self.x_guess = self.x
             out = eng.solve_step(np.asarray(self.x, dtype=np.float64).reshape(1, 4))
             self.u_pred = out["u_pred"][0]
@@ -407,13 +411,14 @@ class Simulator:
         for i in range(steps):
             ego.forward_one_step()
             obstacle = ego.ctrl_policy.obstacle
-            if obstacle is not None:
-                obstacle.update_obstacle()
+            obstacles = list(obstacle) if isinstance(obstacle, (list, tuple)) else ([obstacle] if obstacle is not None else [])
+            for o in obstacles:
+                o.update_obstacle()
             reached = np.linalg.norm(ego.x - self.initial_traj[-1, :]) <= 0.8
             if reached or i == steps - 1:
                 ego.update_memory_post_iter()
-                if obstacle is not None:
-                    obstacle.reset_obstacle()
+                for o in obstacles:
+                    o.reset_obstacle()
                 print("iteration: {}".format(iter) + (" finished" if reached else " not finished"))
                 break
 

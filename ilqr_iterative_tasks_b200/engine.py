@@ -29,7 +29,7 @@ EXPORTS = [
     "i2lqr_measure_fp64_peak", "i2lqr_split_row_doubles", "i2lqr_split_begin", "i2lqr_split_solve", "i2lqr_split_merge",
     "i2lqr_split_end", "i2lqr_dynamics_batch", "i2lqr_linearize_batch", "i2lqr_cost_derivatives_batch",
     "i2lqr_cost_final_batch", "i2lqr_backward_pass_batch", "i2lqr_forward_pass_batch",
-    "i2lqr_add_lap_all", "i2lqr_set_obstacles", "i2lqr_spec_stats", "i2lqr_spec_timeline",
+    "i2lqr_add_lap_all", "i2lqr_set_obstacles", "i2lqr_spec_stats", "i2lqr_spec_timeline", "i2lqr_set_obstacle_list",
 ]  # fmt: skip
 
 
@@ -179,6 +179,19 @@ class Engine:
     def set_obstacle(self, episode, obstacle):
         ptr = None if obstacle is None else C.byref(obstacle)
         _check(lib().i2lqr_set_obstacle(self._h, C.c_int(episode), ptr))
+
+    def set_obstacle_list(self, episode, obstacles):
+        """Extension: up to four obstacles for one episode (their barrier terms add); a sequence of `Obstacle` structs or a
+        structured array."""
+        if obstacles is None or len(obstacles) == 0:
+            _check(lib().i2lqr_set_obstacle_list(self._h, C.c_int(episode), None, C.c_int(0)))
+            return
+        if isinstance(obstacles[0], Obstacle):
+            arr = (Obstacle * len(obstacles))(*obstacles)
+            _check(lib().i2lqr_set_obstacle_list(self._h, C.c_int(episode), arr, C.c_int(len(obstacles))))
+        else:
+            arr = np.ascontiguousarray(obstacles, dtype=_abi.OBSTACLE_DTYPE)
+            _check(lib().i2lqr_set_obstacle_list(self._h, C.c_int(episode), C.c_void_p(arr.ctypes.data), C.c_int(arr.shape[0])))
 
     def select_knn(self, episode, lap, x0, K):
         x0 = _f64(x0, (4,))

@@ -109,6 +109,11 @@ int i2lqr_add_lap(i2lqr_handle* h, int episode, const double* x, int T);
 int i2lqr_num_laps(i2lqr_handle* h, int episode, int* n_laps);
 /* `ilqr.obstacle = ...` (iterative_ilqr/result/ilqr_test_add_moving_obstacle.py:73-75); NULL = None. */
 int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs);
+/* EXTENSION: several obstacles per episode.  The reference's cost loop takes ONE Obstacle
+ * (iterative_ilqr/control/ilqr_helper.py:16-24,32-51); a list of n <= 4 is priced as the SUM of its members' barriers, each
+ * evaluated exactly as the single one.  list[0] is what i2lqr_set_obstacle would store; n = 0 or 1 is the reference's
+ * behaviour.  Controller steps and batched episodes only (FP64, horizons whose step working set fits shared memory). */
+int i2lqr_set_obstacle_list(i2lqr_handle* h, int episode, const i2lqr_obstacle* list, int n);
 /* Batched forms for many-episode handles (one host-to-device copy instead of one per episode):
  * the same lap appended to EVERY episode's safe set (what each reference script does with the scripted first lap,
  * iterative_ilqr/tests/ilqr_test.py:49), and the obstacles of episodes [first, first+n) in one call

@@ -51,8 +51,26 @@ static double quad_form(const double* v, const double* M, int n) {
 
 /* control/ilqr_helper.py:59-64 applied to the obstacle ellipse (:32-51 stage, :118-149 terminal).
  * step = horizon index k for a stage, ilqr_param.num_horizon for the terminal call.  Adds into lx, lxx. */
+static void obstacle_barrier_one(const i2lqr_params* p, const i2lqr_obstacle* o, const double* xk, int step, double* lx,
+                                 double* lxx);
+
+/* EXTENSION (obstacle lists, include/i2lqr.h i2lqr_set_obstacle_list): further obstacles of the calling thread's solve.  The
+ * reference prices one Obstacle; a list is priced as the sum of its members' barriers, each evaluated by the reference's formula. */
+static __thread const i2lqr_obstacle* g_extra = 0;
+static __thread int g_n_extra = 0;
+void orc_set_extra_obstacles(const i2lqr_obstacle* list, int n) {
+  g_extra = list;
+  g_n_extra = n;
+}
+
 static void obstacle_barrier(const i2lqr_params* p, const i2lqr_obstacle* o, const double* xk, int step, double* lx,
                              double* lxx) {
+  obstacle_barrier_one(p, o, xk, step, lx, lxx);
+  for (int m = 0; m < g_n_extra; ++m) obstacle_barrier_one(p, g_extra + m, xk, step, lx, lxx);
+}
+
+static void obstacle_barrier_one(const i2lqr_params* p, const i2lqr_obstacle* o, const double* xk, int step, double* lx,
+                                 double* lxx) {
   if (!o || !o->present) return;
   double cx = o->x, cy = o->y;
   if (o->moving_option == 1) cy = o->y + step * o->spd;

@@ -136,6 +136,20 @@ def kinetic_bicycle(x, u, dt):
     return out
 
 
+def set_extra_obstacles(obstacles):
+    """EXTENSION (obstacle lists): further obstacles whose barriers are added to every following `ilqr` / `calc_input` /
+    `backward_pass` call of this thread; None or [] switches back to the reference's single obstacle.  Returns the ctypes
+    array, which the caller must keep alive while it is set."""
+    from ilqr_iterative_tasks_b200 import _abi
+
+    if not obstacles:
+        lib().orc_set_extra_obstacles(None, C.c_int(0))
+        return None
+    arr = (_abi.Obstacle * len(obstacles))(*obstacles)
+    lib().orc_set_extra_obstacles(arr, C.c_int(len(obstacles)))
+    return arr
+
+
 def calc_input(params, laps, x, obstacle=None):
     """Solve branch of calc_input for one controller; laps = list of (T,4) arrays (all stored laps)."""
     N, K, L = params.num_horizon, params.num_ss_points, params.num_ss_iter

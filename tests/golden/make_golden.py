@@ -429,7 +429,64 @@ def make_components():
     print("components done")
 
 
+def make_multi_obstacle():
+    """EXTENSION goldens (obstacle lists, include/i2lqr.h i2lqr_set_obstacle_list).  The reference's cost functions take one
+    Obstacle; a list is priced as the sum of its members' barrier terms.  That composition is done HERE, outside the
+    reference, by wrapping the two cost functions `backward_pass` calls (control/iterative_ilqr.py:101-107): each
+    member's contribution is the reference's own output for that obstacle minus its output for `None`.  The wrapped
+    functions then drive the reference's unmodified `ilqr()`.  matrix_Q = matrix_R = 0 (the default), so the stage terms
+    add exactly; the terminal gradient carries the rounding of one subtraction per member (< 1 ulp)."""
+    ref = Reference(stable_argsort=False)
+    mod = ref.ilqr_mod
+    orig_cd, orig_cf = mod.get_cost_derivation, mod.get_cost_final
+
+    def cost_derivation(ctrl_U, dX, ilqr_param, num_horizon, xvar, obstacle, sys_param):
+        if not isinstance(obstacle, list):
+            return orig_cd(ctrl_U, dX, ilqr_param, num_horizon, xvar, obstacle, sys_param)
+        base = [np.array(a, dtype=np.float64) for a in orig_cd(ctrl_U, dX, ilqr_param, num_horizon, xvar, None, sys_param)]
+        l_x, l_xx = base[2].copy(), base[3].copy()
+        for o in obstacle:
+            r = orig_cd(ctrl_U, dX, ilqr_param, num_horizon, xvar, o, sys_param)
+            l_x = l_x + (np.asarray(r[2]) - base[2])
+            l_xx = l_xx + (np.asarray(r[3]) - base[3])
+        return base[0], base[1], l_x, l_xx
+
+    def cost_final(x, x_terminal, matrix_Qterminal, obstacle, ilqr_param):
+        if not isinstance(obstacle, list):
+            return orig_cf(x, x_terminal, matrix_Qterminal, obstacle, ilqr_param)
+        b0, b1 = [np.array(a, dtype=np.float64) for a in orig_cf(x, x_terminal, matrix_Qterminal, None, ilqr_param)]
+        Vx, Vxx = b0.copy(), b1.copy()
+        for o in obstacle:
+            r = orig_cf(x, x_terminal, matrix_Qterminal, o, ilqr_param)
+            Vx = Vx + (np.asarray(r[0]) - b0)
+            Vxx = Vxx + (np.asarray(r[1]) - b1)
+        return Vx, Vxx
+
+    mod.get_cost_derivation, mod.get_cost_final = cost_derivation, cost_final
+    try:
+        N, B, M = 6, 64, 3
+        data = synth.flat_candidates(B, num_horizon=N, seed=synth.SEED + 41)
+        rng = np.random.default_rng(synth.SEED + 42)
+        data["lamb_in"] = rng.choice(np.array([1.0, 1.0, 1.0, 1e-1, 10.0, 1e2]), size=B)
+        param = _param(ref, N)
+        members = np.stack([(np.arange(B) + s) % B for s in (0, 7, 13)], axis=1)  # candidate b faces obstacles b, b+7, b+13
+        n_list = 1 + (np.arange(B) % M)  # lists of one, two and three obstacles
+        uvar, xvar = np.zeros((B, 2, N)), np.zeros((B, 4, N + 1))
+        lamb_out, iters = np.zeros(B), np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            obstacles = [ref.make_obstacle(data["obs"][m], data["mode"][m]) for m in members[b, : n_list[b]]]
+            u, x, lo, it = ref.call_ilqr(param, N, data["x0"][b], data["x_term"][b], obstacles, float(data["lamb_in"][b]))
+            uvar[b], xvar[b], lamb_out[b], iters[b] = u, x, lo, it
+    finally:
+        mod.get_cost_derivation, mod.get_cost_final = orig_cd, orig_cf
+    np.savez_compressed(os.path.join(HERE, "multi_obstacle.npz"), N=np.int32(N), x0=data["x0"], x_term=data["x_term"], lamb_in=data["lamb_in"],
+                        obs=data["obs"], mode=data["mode"], members=members, n_list=n_list, uvar=uvar, xvar=xvar, lamb_out=lamb_out, iters=iters)  # fmt: skip
+    ref.close()
+    print("multi_obstacle done: iters mean %.2f max %d" % (iters.mean(), iters.max()))
+
+
 TARGETS = {
+    "multi_obstacle": make_multi_obstacle,
     "flat": make_flat,
     "knn": make_knn,
     "steps_stock": make_steps_stock,

@@ -58,7 +58,7 @@ def step_params(g):
     return _abi.default_params(num_horizon=int(g["N"]), num_ss_points=int(g["K"]), num_ss_iter=int(g["L"]))
 
 
-def oracle_closed_loop(params, x0, obs_row, mode, initial_lap, n_laps):
+def oracle_closed_loop(params, x0, obs_row, mode, initial_lap, n_laps, extra=None):
     """Closed loop of one episode driven by the CPU oracle: the reference's Simulator.sim
     (iterative_ilqr/utils/base.py:708-726), forward_one_step (:157-213), obstacle motion (:50-64), the
     controller's playback branch (:377-382) and the lap post-processing of
@@ -71,6 +71,9 @@ def oracle_closed_loop(params, x0, obs_row, mode, initial_lap, n_laps):
     x = np.asarray(x0, dtype=np.float64).copy()
     for _ in range(n_laps):
         obs = None if obs_row is None else _abi.Obstacle(*[float(v) for v in obs_row], int(mode), 1)
+        # EXTENSION (obstacle lists): further obstacles as (row, mode) pairs; they move and reset like the first one
+        more = [_abi.Obstacle(*[float(v) for v in r], int(m), 1) for r, m in (extra or [])]
+        keep = oracle.set_extra_obstacles(more)
         horizon, u_old = N, None
         states = [x.copy()]
         for i in range(S):
@@ -86,15 +89,19 @@ def oracle_closed_loop(params, x0, obs_row, mode, initial_lap, n_laps):
                     horizon -= 1
             x = oracle.kinetic_bicycle(x, u, dt)
             states.append(x.copy())
-            if obs is not None:
-                if obs.moving_option == 1:
-                    obs.y += obs.spd * dt
-                if obs.moving_option == 2:
-                    obs.x -= obs.spd * dt
+            for o in ([obs] if obs is not None else []) + more:
+                if o.moving_option == 1:
+                    o.y += o.spd * dt
+                if o.moving_option == 2:
+                    o.x -= o.spd * dt
+            if keep is not None:
+                for i, o in enumerate(more):  # the oracle reads the ctypes copy
+                    keep[i].x, keep[i].y = o.x, o.y
             if np.linalg.norm(x - goal) <= params.goal_tol:
                 break
         lap = np.array(states)
         lap[-1] = goal
         laps.append(lap)
         x = np.zeros(4)
+        oracle.set_extra_obstacles(None)
     return laps

@@ -150,6 +150,36 @@ def test_episode_batch_random_scenarios_vs_oracle():
             assert err < CLOSED_LOOP_ATOL, (e, lap, err)
 
 
+def test_episode_batch_obstacle_lists_vs_oracle():
+    """EXTENSION (obstacle lists) in the batched closed loop: every episode faces two or three obstacles (static and moving
+    ones: the members move and reset with the lap like the first), compared with an oracle-driven closed loop."""
+    from ilqr_iterative_tasks_b200 import _abi, episodes, synth
+
+    E, n_laps = 12, 2
+    sc = synth.episode_scenarios(E + 8)
+    p = _abi.default_params(num_ss_points=8, num_ss_iter=2)
+    lap0, _ = synth.initial_lap()
+    eb = episodes.EpisodeBatch(p, sc["x0"][:E], initial_lap=lap0)
+    lists = []
+    for e in range(E):
+        rows = [(sc["obs"][e + d], int(sc["mode"][e + d])) for d in range(2 + e % 2)]
+        lists.append(rows)
+        eb.engine.set_obstacle_list(e, [_abi.Obstacle(*[float(v) for v in r], m, 1) for r, m in rows])
+    got = []
+    for _ in range(n_laps):
+        lens, lx, _ = eb.run_lap(want_traj=True)
+        got.append((lens.copy(), lx.copy()))
+    eb.close()
+    for e in range(E):
+        (r0, m0), more = lists[e][0], lists[e][1:]
+        ref = H.oracle_closed_loop(p, sc["x0"][e], r0, m0, lap0, n_laps, extra=more)
+        for lap in range(n_laps):
+            lens, lx = got[lap]
+            assert lens[e] == len(ref[lap + 1]) - 1, (e, lap, lens[e], len(ref[lap + 1]) - 1)
+            err = np.abs(lx[e, : lens[e] + 1] - ref[lap + 1]).max()
+            assert err < CLOSED_LOOP_ATOL, (e, lap, err)
+
+
 def test_episode_noise_is_bounded_and_reproducible():
     """Plant noise (utils/base.py:207-211) from the device-side counter RNG: same seed -> identical laps,
     another seed -> different laps, and every step's deviation from the noise-free model stays within the

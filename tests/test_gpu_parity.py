@@ -319,6 +319,54 @@ def test_speculative_step_reports_hits(eng_mod):
     assert st["hit_rate"] > 0.6, st
 
 
+def test_obstacle_list_step_vs_oracle(eng_mod):
+    """EXTENSION (obstacle lists): controller steps with one, two and three obstacles per episode against the
+    oracle (whose member-sum is pinned to the composed reference by tests/test_oracle.py).  A one-element list must equal
+    the single-obstacle call bit for bit, and an obstacle far from the path must not change a step."""
+    from ilqr_iterative_tasks_b200 import _abi
+    from oracle import oracle
+
+    g = H.load("steps_stock.npz")
+    p = H.step_params(g)
+    laps = [g["lap0"], g["lap1"]]
+    O = _abi.Obstacle
+    near = [O(31.0, -3.0, 8.0, 6.0, 0.0, 0, 1), O(60.0, 2.5, 6.0, 3.0, 0.0, 0, 1), O(18.0, 4.0, 5.0, 2.5, 0.3, 1, 1), O(80.0, -2.0, 9.0, 4.0, 0.2, 2, 1)]
+    e = eng_mod.Engine(p, n_episodes=1, lap_capacity=128)
+    for lp in laps:
+        e.add_lap(0, lp)
+    states = [g["lap1"][i] + np.array([0.2, -0.1, 0.05, 0.01]) for i in (2, 9, 17, 30, 44)]
+    for n in (1, 2, 3, 4):
+        e.set_obstacle_list(0, near[:n])
+        keep = oracle.set_extra_obstacles(near[1:n])
+        try:
+            for x in states:
+                out = e.solve_step(x.reshape(1, 4))
+                tr = e.step_trace(1)
+                ref = oracle.calc_input(p, laps, x, near[0])
+                assert np.array_equal(tr["cand_iters"][0], ref["cand_iters"]), n
+                assert np.array_equal(np.nan_to_num(tr["cand_lamb"][0], nan=-1.0), np.nan_to_num(ref["cand_lamb"], nan=-1.0)), n
+                assert int(out["winner_idx"][0]) == ref["winner_idx"] and int(out["winner_lap"][0]) == ref["winner_lap"]
+                assert np.abs(out["x_pred"][0] - ref["x_pred"]).max() <= H.RTOL * max(1.0, np.abs(ref["x_pred"]).max())
+                assert np.abs(out["u_pred"][0] - ref["u_pred"]).max() <= H.RTOL * 2
+        finally:
+            oracle.set_extra_obstacles(None)
+        del keep
+    # a list of one == the reference's single obstacle; a far-away second obstacle changes nothing
+    x = states[1].reshape(1, 4)
+    e.set_obstacle(0, near[0])
+    single = e.solve_step(x)
+    e.set_obstacle_list(0, near[:1])
+    one = e.solve_step(x)
+    e.set_obstacle_list(0, [near[0], O(5000.0, 5000.0, 3.0, 3.0, 0.0, 0, 1)])
+    far = e.solve_step(x)
+    for k in single:
+        assert np.array_equal(single[k], one[k]), k
+        assert np.array_equal(single[k], far[k]), k
+    with pytest.raises(RuntimeError):
+        e.set_obstacle_list(0, near + near[:1])  # five
+    e.close()
+
+
 def test_multi_episode_step_equals_single(eng_mod):
     """E episodes in one call == E single-episode calls (the batch axis must not couple episodes)."""
     g = H.load("steps_stock.npz")

@@ -182,3 +182,22 @@ def test_backward_forward_pass_match_reference(grp):
         assert H.rel_err(xn[None], g[grp + "/xvar_new"][b][None])[0] <= 1e-12, (grp, b)
         assert H.rel_err(un[None], g[grp + "/uvar_new"][b][None])[0] <= 1e-12, (grp, b)
         assert abs(c - g[grp + "/cost_new"][b]) <= 1e-12 * max(1.0, abs(g[grp + "/cost_new"][b])), (grp, b)
+
+
+def test_obstacle_list_matches_composed_reference():
+    """EXTENSION (obstacle lists): the oracle's sum of member barriers against `multi_obstacle.npz` -- the reference's own
+    `ilqr()` driven by cost functions that add up the reference's single-obstacle outputs (make_golden.py multi_obstacle)."""
+    g = H.load("multi_obstacle.npz")
+    p = _abi.default_params(num_horizon=int(g["N"]))
+    for b in range(len(g["x0"])):
+        members = g["members"][b, : g["n_list"][b]]
+        obs = [_abi.Obstacle(*[float(v) for v in g["obs"][m]], int(g["mode"][m]), 1) for m in members]
+        keep = oracle.set_extra_obstacles(obs[1:])
+        try:
+            u, x, lamb, iters = oracle.ilqr(p, g["x0"][b], g["x_term"][b], float(g["lamb_in"][b]), obs[0])
+        finally:
+            oracle.set_extra_obstacles(None)
+        del keep
+        assert iters == g["iters"][b] and lamb == g["lamb_out"][b], b
+        assert np.abs(x - g["xvar"][b]).max() <= 4e-12 * max(1.0, np.abs(g["xvar"][b]).max()), b
+        assert np.abs(u - g["uvar"][b]).max() <= 4e-12 * max(1.0, np.abs(g["uvar"][b]).max()), b

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -143,6 +144,10 @@ struct i2lqr_handle {
   DevBuf<unsigned long long> sp_walked, sp_hist_key, sp_set, sp_stats, sp_timeline, sp_pub;
   int sp_cmax = 0, sp_K = 0, sp_S = 0, sp_E = 0, sp_N = 0;
   unsigned sp_epoch = 0;
+  unsigned long long* sp_host = nullptr;      // mapped pinned: results of small steps, written by the kernel (spec_step.cuh host_out)
+  unsigned long long* sp_host_dev = nullptr;  // its device alias
+  size_t sp_host_words = 0;
+  bool stats_lazy = false;  // last_ms of the no-copy step is read from the events on demand
   // component entry points (components.cuh): grow-only staging
   DevBuf<double> c_in[6], c_out[4], c_scratch;
   DevBuf<DevObstacle> c_obs;
@@ -377,6 +382,7 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
 
 int begin_stats(i2lqr_handle* h, cudaStream_t st) {
   h->last_launches = 0;
+  h->stats_lazy = false;
   CU(h->ctl.ensure(kCtlWords));
   CU(zero_words(h->ctl.p, 2, st));
   CU(cudaEventRecord(h->ev0, st));
@@ -601,6 +607,7 @@ int i2lqr_destroy(i2lqr_handle* h) {
   h->c_obs.release();
   if (h->h_nrun) cudaFreeHost(h->h_nrun);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->sp_host) cudaFreeHost(h->sp_host);
   if (h->stage) cudaFreeHost(h->stage);
   h->ctl.release();
   h->b_obs.release();
@@ -948,12 +955,16 @@ int i2lqr_set_obstacle(i2lqr_handle* h, int episode, const i2lqr_obstacle* obs) 
     if (o.present && o.moving_option == 0 && o.spd != 0.0)
       return fail("obstacle with spd != 0 needs moving_option 1 or 2 (control/ilqr_helper.py:34-43)");
   }
-  h->h_obs[episode] = o;
   if (h->h_n_extra[episode] > 0) {  // a single obstacle replaces a list
     h->h_n_extra[episode] = 0;
     h->extras_in_use -= 1;
+    h->obs_dirty = true;
   }
-  h->obs_dirty = true;
+  // (the drop-in controller passes its obstacle before every step: upload only what changed)
+  if (memcmp(&h->h_obs[episode], &o, sizeof o) != 0) {
+    h->h_obs[episode] = o;
+    h->obs_dirty = true;
+  }
   return 0;
 }
 
@@ -1213,7 +1224,7 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     CU(h->sp_hist_key.ensure(kSpecHist));
     CU(h->sp_hist_cnt.ensure(kSpecHist));
     CU(h->sp_set.ensure(kSpecMaxSet));
-    CU(h->sp_stats.ensure(8));
+    CU(h->sp_stats.ensure(16));  // [0..7] cumulative counters, [8..9] iterations / solves of a no-copy step (reset by the kernel)
     std::vector<unsigned long long> keys;
     spec_seed_patterns(h->params, &keys);
     std::vector<unsigned> cnt(kSpecHist, 0u);
@@ -1221,7 +1232,7 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     CU(cudaMemcpyAsync(h->sp_hist_key.p, keys.data(), kSpecHist * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->sp_hist_cnt.p, cnt.data(), kSpecHist * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->sp_set.p, keys.data(), kSpecMaxSet * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(h->sp_stats.p, 0, 8 * 8, st));
+    CU(cudaMemsetAsync(h->sp_stats.p, 0, 16 * 8, st));
     CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
   }
   if (chains > h->sp_cmax || K != h->sp_K || S != h->sp_S || n_episodes > h->sp_E || N != h->sp_N) {
@@ -1250,7 +1261,7 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
   return 0;
 }
 
-int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
+int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, const double* x_inline = nullptr, bool host_out = false) {
   if (spec_ensure(h, sc.n_episodes, st)) return 1;
   const KParams& kp = h->kp;
   SpecArgs a{};
@@ -1260,6 +1271,14 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   a.n_ep = sc.n_ep;
   a.set = h->set;
   a.x = h->s_x.p;
+  if (x_inline != nullptr) {
+    a.n_inline = sc.n_episodes;
+    memcpy(a.x_inline, x_inline, sizeof(double) * 4 * sc.n_episodes);
+  }
+  if (host_out) {
+    a.host_out = h->sp_host_dev;
+    a.step_stats = h->sp_stats.p + 8;
+  }
   a.ep_obs = h->d_obs.p;
   if (h->extras_in_use > 0) {
     a.ep_obs_extra = h->d_obs_extra.p;
@@ -1300,7 +1319,7 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st) {
   a.hist_key = h->sp_hist_key.p;
   a.hist_cnt = h->sp_hist_cnt.p;
   a.spec_set = h->sp_set.p;
-  a.step_stats = h->ctl.p;
+  if (!host_out) a.step_stats = h->ctl.p;
   a.stats = h->sp_stats.p;
   static const bool want_timeline = getenv("I2LQR_SPEC_TIMELINE") != nullptr;  // developer switch
   if (want_timeline) {
@@ -1382,6 +1401,61 @@ int download_step_results(i2lqr_handle* h, int n_episodes, double* u, double* x_
 }
 }  // namespace
 
+namespace {
+// The no-copy form of a small controller step: the state travels in the launch parameters, the kernel writes the results
+// into mapped host memory and raises a flag the host spins on.  One launch, no copy, no stream synchronisation; the
+// kernel's tail (workers leaving, counters restored) overlaps the caller's next host work, and the next launch queues
+// behind it on the stream.
+int solve_step_nocopy(i2lqr_handle* h, int n_episodes, const double* x, double* u, double* x_pred, double* u_pred,
+                      int32_t* winner_lap, int32_t* winner_rank, int64_t* winner_idx, double* winner_cost, int32_t* shrink) {
+  cudaStream_t st = h->stream;
+  const int N = h->kp.N;
+  const size_t words = 3 + (size_t)kSpecInlineEpisodes * spec_host_words(N);
+  if (h->sp_host_words < words) {
+    if (h->sp_host) CU(cudaFreeHost(h->sp_host));
+    h->sp_host = nullptr;
+    CU(cudaHostAlloc((void**)&h->sp_host, words * sizeof(unsigned long long), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&h->sp_host_dev, h->sp_host, 0));
+    memset(h->sp_host, 0, words * sizeof(unsigned long long));
+    h->sp_host_words = words;
+  }
+  if (sync_obstacles(h)) return 1;
+  h->last_launches = 0;
+  CU(cudaEventRecord(h->ev0, st));
+  if (launch_spec_step(h, StepScope{n_episodes}, st, x, true)) return 1;
+  CU(cudaEventRecord(h->ev1, st));
+  volatile unsigned long long* ho = h->sp_host;
+  const unsigned long long want = h->sp_epoch;
+  for (unsigned long long spins = 0; ho[0] != want; ++spins) {
+    if ((spins & 0xfffff) == 0xfffff) {  // ~ every few ms: make sure the kernel is still alive
+      const cudaError_t q = cudaStreamQuery(st);
+      if (q != cudaErrorNotReady && ho[0] != want) {
+        if (q != cudaSuccess) return fail("controller step failed: %s", cudaGetErrorString(q));
+        return fail("controller step finished without publishing its result");
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  h->last_iters = (long long)ho[1];
+  h->last_solves = (long long)ho[2];
+  h->stats_lazy = true;
+  const int nx = 4 * (N + 1), nu = 2 * N;
+  for (int e = 0; e < n_episodes; ++e) {
+    const double* r = reinterpret_cast<const double*>(h->sp_host + 3 + (size_t)e * spec_host_words(N));
+    const long long* rl = reinterpret_cast<const long long*>(r + 2 + nx + nu + 1);
+    if (u) memcpy(u + (size_t)e * 2, r, 2 * sizeof(double));
+    if (x_pred) memcpy(x_pred + (size_t)e * nx, r + 2, nx * sizeof(double));
+    if (u_pred) memcpy(u_pred + (size_t)e * nu, r + 2 + nx, nu * sizeof(double));
+    if (winner_cost) winner_cost[e] = r[2 + nx + nu];
+    if (winner_idx) winner_idx[e] = rl[0];
+    if (winner_lap) winner_lap[e] = (int32_t)(rl[1] & 0xffffffffll);
+    if (winner_rank) winner_rank[e] = (int32_t)(rl[1] >> 32);
+    if (shrink) shrink[e] = (int32_t)rl[2];
+  }
+  return 0;
+}
+}  // namespace
+
 int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u, double* x_pred, double* u_pred,
                      int32_t* winner_lap, int32_t* winner_rank, int64_t* winner_idx, double* winner_cost,
                      int32_t* shrink) {
@@ -1393,6 +1467,11 @@ int i2lqr_solve_step(i2lqr_handle* h, int n_episodes, const double* x, double* u
   CU(cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   if (ensure_step_workspace(h)) return 1;
+  static const bool no_nocopy = getenv("I2LQR_STEP_COPY") != nullptr;  // A-B switch: force the staged-copy form
+  static const bool want_timeline = getenv("I2LQR_SPEC_TIMELINE") != nullptr;
+  if (!no_nocopy && !want_timeline && n_episodes <= kSpecInlineEpisodes && spec_eligible(h, n_episodes))
+    return solve_step_nocopy(h, n_episodes, x, u, x_pred, u_pred, winner_lap, winner_rank, winner_idx, winner_cost, shrink);
+  h->stats_lazy = false;
   const size_t n_in = (size_t)n_episodes * 4 * sizeof(double);
   if (stage_reserve(h, n_in + step_result_bytes(h, n_episodes))) return 1;
   memcpy(h->stage, x, n_in);
@@ -1847,6 +1926,14 @@ int i2lqr_episodes_status(i2lqr_handle* h, int32_t* status) {
 
 int i2lqr_last_stats(i2lqr_handle* h, double* kernel_ms, int64_t* launches, int64_t* ilqr_iterations, int64_t* solves) {
   if (!h) return fail("null handle");
+  if (h->stats_lazy) {  // the no-copy step returned before its kernel's tail: read the device time now
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->stats_lazy = false;
+  }
   if (kernel_ms) *kernel_ms = h->last_ms;
   if (launches) *launches = h->last_launches;
   if (ilqr_iterations) *ilqr_iterations = h->last_iters;

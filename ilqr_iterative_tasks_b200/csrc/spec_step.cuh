@@ -29,6 +29,9 @@ constexpr int kSpecHist = 64;        // histogram slots (two per lane)
 constexpr int kSpecRungs = 4;
 constexpr int kSpecWorkerGroup = 4;  // lanes per speculative candidate: 8 candidates per worker warp
 constexpr int kSpecPubWords = 6;
+constexpr int kSpecInlineEpisodes = 8;  // steps of up to this many episodes need no copy at all: state in the launch parameters, results by zero-copy stores
+// per episode in host_out: u (2), x_pred (4 (N+1)), u_pred (2 N), winner cost | winner index | lap, rank | shrink
+__host__ __device__ __forceinline__ int spec_host_words(int N) { return 2 + 4 * (N + 1) + 2 * N + 1 + 1 + 1 + 1; }
 constexpr unsigned long long kSpecUnused = 0x7ff8dead00000000ull;  // NaN payload: never a lambda
 
 struct SpecArgs {
@@ -38,6 +41,10 @@ struct SpecArgs {
   const int* n_ep;             // device: entries of ep_list
   SafeSet set;
   const double* x;             // (E,4)
+  int n_inline;                // > 0: the states of episodes 0 .. n_inline-1 travel in the launch parameters (x_inline) instead
+  double x_inline[4 * kSpecInlineEpisodes];
+  unsigned long long* host_out;  // mapped pinned host memory or null: results of a small step written straight to the host
+                                 // ([0] flag = epoch, written last; [1] iterations [2] solves; then per episode kSpecHostWords(N) words)
   const DevObstacle* ep_obs;   // (E)
   const DevObstacle* ep_obs_extra;  // (E, kMaxExtraObstacles) or null
   const int* ep_n_extra;       // (E)
@@ -115,6 +122,9 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ double spec_x(const SpecArgs& a, int ep, int i) {
+  return a.n_inline > 0 ? a.x_inline[ep * 4 + i] : a.x[(size_t)ep * 4 + i];
+}
 // Binds a solver's candidate to episode `ep` (state, obstacle); the terminal point and lambda follow per candidate.
 template <class Solver>
 __device__ __forceinline__ void spec_bind_episode(const KParams& p, const SpecArgs& a, int ep, Solver& gs) {
@@ -124,7 +134,7 @@ __device__ __forceinline__ void spec_bind_episode(const KParams& p, const SpecAr
     gs.c.n_ex = a.ep_n_extra[ep];
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) gs.c.x0[i] = a.x[(size_t)ep * 4 + i];
+  for (int i = 0; i < 4; ++i) gs.c.x0[i] = spec_x(a, ep, i);
   sincos_fast(gs.c.x0[3], &gs.c.s0, &gs.c.c0);
 }
 
@@ -181,7 +191,7 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
         double g[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)  // (x_pred was written by another warp, possibly on another SM: read it from L2)
-          g[i] = it == 0 ? a.x[(size_t)ep * 4 + i] : __ldcg(a.win.x_pred + ((size_t)ep * 4 + i) * (N + 1) + N);
+          g[i] = it == 0 ? spec_x(a, ep, i) : __ldcg(a.win.x_pred + ((size_t)ep * 4 + i) * (N + 1) + N);
         double* dist = smem;
         int* order = reinterpret_cast<int*>(dist + a.set.Tcap);
         const int count2 = a.set.lap_count[ep];
@@ -351,6 +361,22 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
         winner_warp(wa, ep, lane, (size_t)L * K * sizeof(double) <= 16 * 1024 ? smem : nullptr);
         __threadfence();
         __syncwarp();
+        if (it == kOuter - 1 && a.host_out != nullptr) {  // the step's result for this episode, straight into host memory
+          double* ho = reinterpret_cast<double*>(a.host_out + 3 + (size_t)pos * spec_host_words(N));
+          const int nx = 4 * (N + 1), nu = 2 * N;
+          if (lane < 2) ho[lane] = a.win.u[(size_t)ep * 2 + lane];
+          for (int i = lane; i < nx; i += 32) ho[2 + i] = a.win.x_pred[(size_t)ep * nx + i];
+          for (int i = lane; i < nu; i += 32) ho[2 + nx + i] = a.win.u_pred[(size_t)ep * nu + i];
+          if (lane == 0) {
+            ho[2 + nx + nu] = a.win.winner_cost[ep];
+            long long* hl = reinterpret_cast<long long*>(ho + 2 + nx + nu + 1);
+            hl[0] = a.win.winner_idx[ep];
+            hl[1] = ((long long)(unsigned)a.win.winner_rank[ep] << 32) | (unsigned)a.win.winner_lap[ep];
+            hl[2] = (long long)a.win.shrink[ep];
+          }
+          __threadfence_system();
+          __syncwarp();
+        }
         if (lane == 0) st_release_u32(done_flag, epoch);
       } else {
         if (lane == 0)
@@ -364,10 +390,27 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
         for (int i = 0; i < 8; ++i) a.timeline[((size_t)it * a.c_max + chain) * 8 + i] = tl[i];
       }
     }
-    // ---- end of the step for this chain
+    // ---- end of the step for this chain: its share of the step's counters first, so that the last chain sees the totals
+    if (lane == 0) {
+      if (st_iters) atomicAdd(a.step_stats + 0, st_iters);
+      if (st_solves) atomicAdd(a.step_stats + 1, st_solves);
+      __threadfence();
+    }
+    st_iters = st_solves = 0;
     unsigned fin = 0;
     if (lane == 0) fin = atomicAdd(a.ctl + 2, 1u);
     fin = __shfl_sync(kFull, fin, 0);
+    if ((int)fin == n_chains - 1 && a.host_out != nullptr && lane == 0) {
+      __threadfence();
+      volatile unsigned long long* ho = a.host_out;
+      ho[1] = atomicAdd(a.step_stats + 0, 0ull);
+      ho[2] = atomicAdd(a.step_stats + 1, 0ull);
+      a.step_stats[0] = 0;  // (the no-copy form of the step has no separate reset launch)
+      a.step_stats[1] = 0;
+      __threadfence_system();
+      ho[0] = (unsigned long long)epoch;  // the host is spinning on this word
+      __threadfence_system();
+    }
     if ((int)fin == n_chains - 1) {
       // last chain of the step: freeze the next launch's speculation set = the S most counted histogram entries
       __threadfence();

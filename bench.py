@@ -441,6 +441,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     fp64_peak = engine.measure_fp64_peak(local, reps=5)
+    # clocks / throttle reasons are sampled from the warm-up on (nvidia-smi needs ~100 ms to deliver its first sample and the timed
+    # region of the default run is 27 ms), through the timed region and the >= 2 s `sustained` repetition of the same loop
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # W warm-up steps, and at least one on every handle: a handle allocates its device buffers on first use, which must
     # not happen inside the timed region (it did once, with 4 handles and W = 3: 31 ms per step instead of 2.6)
     for k in range(max(args.warmup, n_pipe)):
@@ -455,9 +460,6 @@ def run_ours(args):
     streams[0].synchronize()
     isolated_ms = iso[0].elapsed_time(iso[1]) / 3
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(streams[0])
     for st in streams[1:]:
@@ -474,14 +476,10 @@ def run_ours(args):
     total_ms = ev0.elapsed_time(ev1)
     step_ms = [total_ms / args.steps]
     st = eng.sync_stats(streams[0].cuda_stream)
-    clocks = sampler.stop() if rank == 0 else None
     # ---- sustained: the same rotation for >= args.sustain_s seconds (hundreds of steps), clocks / power sampled alongside
     sustained = None
     if args.sustain_s > 0:
         n_sus = max(args.steps, int(args.sustain_s * 1e3 / max(step_ms[0], 1e-3)) + 1)
-        sus_sampler = ClockSampler(local)
-        if rank == 0:
-            sus_sampler.start()
         ev0.record(streams[0])
         for st_ in streams[1:]:
             st_.wait_event(ev0)
@@ -499,8 +497,10 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(tsus, op=dist.ReduceOp.MAX)
         sustained = {"steps": n_sus, "seconds": float(tsus[0]) * 1e-3, "ms_per_step": float(tsus[0]) / n_sus,
-                     "value": B * world * n_sus / (float(tsus[0]) * 1e-3), "unit": UNIT,
-                     "clocks": sus_sampler.stop() if rank == 0 else None}  # fmt: skip
+                     "value": B * world * n_sus / (float(tsus[0]) * 1e-3), "unit": UNIT}  # fmt: skip
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + sustained repetition of the same loop"
     iters_total = st["ilqr_iterations"]  # per step (identical every step)
     kernel_ms = isolated_ms
     launches_per_step = st["launches"]

@@ -465,6 +465,7 @@ __device__ __forceinline__ R chain_forward(const KParamsT<R>& p, const CandT<R>&
   return Jn + T;
 }
 
+#ifdef __CUDACC__
 // One candidate solve by a group of kGroup adjacent lanes (the first kRungs of them are the speculative lambda
 // rungs, all of them share the stage tasks), as a small state machine that a warp drives convergently: every lane
 // of the warp calls trip() each round (it contains warp-wide barriers and votes); groups without a live candidate
@@ -604,5 +605,6 @@ struct GroupSolver {
     for (int i = 0; i < 4; ++i) xN[i] = s[(2 + i) * S];
   }
 };
+#endif  // __CUDACC__
 
 }  // namespace i2lqr

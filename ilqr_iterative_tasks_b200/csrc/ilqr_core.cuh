@@ -26,6 +26,10 @@
 
 #include "fastmath.cuh"
 
+#ifdef I2LQR_HOST_BUILD  // developer screens compile the core for the host (tools/host_core_check.cpp): one "lane"
+inline bool __any_sync(unsigned, bool p) { return p; }
+#endif
+
 namespace i2lqr {
 
 // Parameter block in kernel-argument (constant-bank) space, derived on the host from i2lqr_params.

@@ -78,6 +78,41 @@ def test_flat_batch_mid_horizons_vs_oracle(eng_mod, N):
     assert H.rel_err(out["uvar"][same], u[same]).max() <= H.RTOL
 
 
+@pytest.mark.parametrize("N,B,variant", [(26, 4096, "plain"), (50, 4096, "plain"), (50, 2048, "qr"), (50, 2048, "warm"), (200, 2048, "plain")])
+def test_streaming_placement_vs_oracle(eng_mod, N, B, variant):
+    """Long horizons (N >= 26, batches >= 2048) run the streaming placement: the working set in global memory, moved
+    through a shared-memory ring by bulk asynchronous copies (StreamScratch).  Against the oracle on the same inputs,
+    including non-zero Q / R and warm-started inputs; plus bit-identical reruns (the ring and its barriers carry no
+    state from one call to the next)."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    d = synth.flat_candidates(B, N, seed=synth.SEED + 500 + N)
+    kw = {}
+    if variant == "qr":
+        kw = dict(matrix_Q=np.diag([0.1, 0.2, 0.05, 0.01]), matrix_R=np.array([[0.1, 0.02], [0.02, 0.3]]))
+    p = _abi.default_params(num_horizon=N, **kw)
+    uinit = None
+    if variant == "warm":
+        # mild perturbation: with O(1) random controls over 50 stages the solve is ill-conditioned enough that ulp-level
+        # differences (FMA contraction) grow to 1e-3 with the discrete path still identical (tools/host_core_check.py
+        # shows the same figure for the host-compiled core), which would test conditioning, not the placement
+        uinit = np.random.default_rng(N).standard_normal((B, 2, N)) * np.array([0.15, 0.05])[None, :, None]
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, uvar_init=uinit)
+    again = e.solve_batch(d["x0"], d["x_term"], d["lamb_in"], obs, uvar_init=uinit)
+    assert e.last_stats()["solves"] == B
+    e.close()
+    for k in out:
+        assert np.array_equal(out[k], again[k]), k
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], d["lamb_in"], obs, nthreads=8, uvar_init=uinit)
+    same = H.same_discrete_path(out["iters"], out["lamb_out"], iters, lamb, "streaming placement, N=%d %s" % (N, variant))
+    tol = 1e-8 if variant == "warm" else H.RTOL  # warm: up to 150 iterations of 50 stages amplify the last ulp
+    assert H.rel_err(out["xvar"][same], x[same]).max() <= tol
+    assert H.rel_err(out["uvar"][same], u[same]).max() <= tol
+
+
 def test_flat_batch_size_boundaries(eng_mod):
     """Batch sizes around every launch-shape threshold (one lane, one warp, one CTA, the tensor-memory variant from
     8192 candidates, iteration-sliced passes from 131072): each equals the first B candidates of one big oracle run."""

@@ -418,8 +418,8 @@ __device__ __forceinline__ R chain_forward(const KParamsT<R>& p, const CandT<R>&
     // u + k + K (x - xo) with the sign-flipped gains of chain_riccati
     R ua = (uo[0] - g[0]) - fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
     R ud = (uo[1] - g[1]) - fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
-    ua = clipd(ua, -p.a_max, p.a_max);
-    ud = clipd(ud, -p.d_lim, p.d_lim);
+    ua = clipd(ua, p.a_min, p.a_max);
+    ud = clipd(ud, p.d_min, p.d_lim);
     if (kQR) {
       const R l_ctrl = quad2(p.Rm, ua, ud);
       Jn = Jn + quad4(p.Q, x[0] - c.xt[0], x[1] - c.xt[1], x[2] - c.xt[2], x[3] - c.xt[3]) + l_ctrl;

@@ -70,10 +70,10 @@ I2_CONST double kSinC[6] = {1.58969099521155010221e-10, -2.50507602534068634195e
 I2_CONST double kCosC[6] = {-1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
                             2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 
-// exp(x) for x already inside (-708, 709): k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite),
+// exp(x) for x already inside (-745, 709): k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite),
 // degree-13 Taylor polynomial on |r| <= ln2/2 (truncation < 2^-57, even / odd halves evaluated side by
-// side to halve the dependent chain), scaled by 2^k in two halves so that results in the denormal range
-// degrade gracefully to 0.
+// side to halve the dependent chain), scaled by 2^k through the exponent field; results below the normal
+// range (x < -707.7) are zero.
 I2_HD double exp_fast_bounded(double x) {
   const double magic = 6755399441055744.0;  // 2^52 + 2^51
   const double t = fma_(x, 1.4426950408889634, magic);
@@ -88,13 +88,19 @@ I2_HD double exp_fast_bounded(double x) {
     pe = fma_(pe, r2, kExpEven[i]);
     po = fma_(po, r2, kExpOdd[i]);
   }
-  // exp(r) = 1 + r + r^2 (pe + r po)
+  // exp(r) = 1 + r + r^2 (pe + r po), in [0.70, 1.42]
   const double q = fma_(po, r, pe);
   const double pr = fma_(q, r2, r) + 1.0;
-  const int k1 = k >> 1, k2 = k - k1;
-  const double s1 = bits_to_double((long long)(k1 + 1023) << 52);
-  const double s2 = bits_to_double((long long)(k2 + 1023) << 52);
-  return (pr * s1) * s2;
+  // times 2^k by adding k to the exponent field: exact, i.e. the very bits of the product pr * 2^k, as long as the
+  // result is a normal number (k >= -1021 here); below that the result is flushed to zero (the products used to
+  // degrade through the denormals -- a barrier term of 1e-308 changes nothing it is added to).  One integer add
+  // instead of two FP64 multiplications and the construction of their power-of-two operands.
+#ifdef __CUDA_ARCH__
+  const double scaled = __hiloint2double(__double2hiint(pr) + (k << 20), __double2loint(pr));
+#else
+  const double scaled = bits_to_double(double_to_bits(pr) + ((long long)k << 52));
+#endif
+  return k < -1021 ? 0.0 : scaled;
 }
 // x <= ~700 guaranteed by the caller, arbitrary below (underflows to 0)
 I2_HD double exp_fast_lo(double x) { return exp_fast_bounded(fmax(x, -745.0)); }
@@ -132,8 +138,14 @@ I2_HD void sincos_fast(double x, double* sn, double* cs) {
   const double c = fma_(pc * z, z, fma_(-0.5, z, 1.0));
   const bool swap = (k & 1) != 0;
   const double ss = swap ? c : s, cc = swap ? s : c;
+  // quadrant signs flipped in the sign bit (an integer operation on the high word instead of an FP64 negation and a select)
+#ifdef __CUDA_ARCH__
+  *sn = __hiloint2double(__double2hiint(ss) ^ ((k & 2) << 30), __double2loint(ss));
+  *cs = __hiloint2double(__double2hiint(cc) ^ (((k + 1) & 2) << 30), __double2loint(cc));
+#else
   *sn = (k & 2) ? -ss : ss;
   *cs = ((k + 1) & 2) ? -cc : cc;
+#endif
 }
 
 // ---- single precision (optional FP32 build): the CUDA library routines are already branch-light in float

@@ -192,16 +192,22 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   int scratch = smem_full * 4 <= kSmemLimit ? 0 : (smem_cur <= kSmemLimit ? 2 : 1);
   const bool tmem_ok = w.mode == 0 && !kp.has_qr && kp.N <= kTmemMaxHorizon && h->params.precision == 0;
   if (tmem_ok && w.n_items >= 8192) scratch = 3;
+  // ... and up to horizon 6 with the candidate's cold state parked as well: 128 registers, four CTAs per SM
+  static const bool no_lean = getenv("I2LQR_LEAN") && atoi(getenv("I2LQR_LEAN")) == 0;  // A-B switch
+  static const bool lean_pass0_only = getenv("I2LQR_LEAN") && atoi(getenv("I2LQR_LEAN")) == 2;  // A-B switch
+  // (all passes: mixing the 168-register and the 128-register kernel on an SM measured slower than either alone)
+  if (scratch == 3 && kp.N <= kLeanMaxHorizon && !no_lean && (w.pass == 0 || !lean_pass0_only)) scratch = 6;
   // long horizons (flat batches, FP64): the working set is streamed through shared memory with bulk asynchronous copies
   const bool stream_ok = w.mode == 0 && h->params.precision == 0;
   static const int stream_from = getenv("I2LQR_STREAM_FROM") ? atoi(getenv("I2LQR_STREAM_FROM")) : 26;  // tuning switch: first horizon that streams
   if (stream_ok && kp.N >= stream_from && w.n_items >= 2048) scratch = 4;
   if (force >= 0) scratch = force;
-  if (scratch >= 4 && !stream_ok) scratch = 2;
+  if ((scratch == 4 || scratch == 5) && !stream_ok) scratch = 2;
+  if (scratch == 6 && !(tmem_ok && kp.N <= kLeanMaxHorizon)) scratch = 3;
   if (scratch == 3 && !tmem_ok) scratch = 0;
   if (scratch == 0 && smem_full > kSmemLimit) scratch = 2;
   if (scratch == 2 && smem_cur > kSmemLimit) scratch = 1;
-  const int threads = scratch == 3 ? kTmemThreads : kSolveThreads;
+  const int threads = (scratch == 3 || scratch == 6) ? kTmemThreads : kSolveThreads;
   CU(h->ctl.ensure(kCtlWords));
   const int slot = h->ctl_next;
   h->ctl_next = (slot + 1) % kCtlSlots;
@@ -234,6 +240,7 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   } else {
     k64 = w.mode == 0 ? pick64(std::integral_constant<int, 0>()) : pick64(std::integral_constant<int, 1>());
     if (scratch == 3) k64 = solve_kernel<double, false, 3, 0, kTmemThreads>;
+    if (scratch == 6) k64 = solve_kernel<double, false, 6, 0, kTmemThreads>;
     if (scratch == 4) k64 = kp.has_qr ? solve_kernel<double, true, 4, 0, kSolveThreads> : solve_kernel<double, false, 4, 0, kSolveThreads>;
     if (scratch == 5) k64 = kp.has_qr ? solve_kernel<double, true, 5, 0, kSolveThreads> : solve_kernel<double, false, 5, 0, kSolveThreads>;
   }
@@ -241,7 +248,8 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   int per_sm = 0;
   size_t smem = scratch == 0 ? smem_full * rsz / sizeof(double)
                              : (scratch == 2 ? smem_cur : (scratch == 3 ? (size_t)kTmemThreads * 8 * kp.N * sizeof(double) : 0));
-  if (scratch >= 4) smem = stream_smem_bytes(scratch == 4 ? kStreamRing : 4);
+  if (scratch == 6) smem = (size_t)kTmemThreads * (8 * kp.N + 6) * sizeof(double);
+  if ((scratch == 4 || scratch == 5)) smem = stream_smem_bytes(scratch == 4 ? kStreamRing : 4);
   // tuning switch for occupancy experiments: pad the dynamic shared memory so that at most this many blocks fit
   static const int cap_blocks = getenv("I2LQR_MAX_BLOCKS_PER_SM") ? atoi(getenv("I2LQR_MAX_BLOCKS_PER_SM")) : 0;
   if (smem > 0 && cap_blocks > 0) smem = std::max(smem, (size_t)(kSmemLimit / cap_blocks) - 1024);
@@ -252,12 +260,12 @@ int launch_solve(i2lqr_handle* h, Work w, cudaStream_t st, int pipe = 0) {
   // tensor memory: 512 columns per SM, 128 / 256 / 512 per CTA (horizon up to 6 / 12 / 25); registers (168 x 128
   // threads) allow three CTAs.  The occupancy calculator does not know about tensor memory, so the grid is sized by
   // hand: what the columns, the registers and the shared memory each allow.
-  if (scratch == 3) {  // (a 4-CTA build capped at 128 registers spills and measured 12 % slower)
-    per_sm = std::min(3, 512 / tmem_columns(kp.N));
-    per_sm = std::max(1, std::min<int>(per_sm, (int)((kSmemLimit - 1024) / (smem + 1024))));
+  if (scratch == 3 || scratch == 6) {
+    per_sm = std::min(scratch == 6 ? 4 : 3, 512 / tmem_columns(kp.N));
+    per_sm = std::max(1, std::min<int>(per_sm, (int)((kSmemLimit + 1024) / (smem + 1024))));  // 228 KB per SM, 1 KB reserved per CTA
   }
   long long grid = std::min<long long>(blocks_needed, (long long)per_sm * h->n_sms);
-  if (scratch >= 4) {
+  if ((scratch == 4 || scratch == 5)) {
     static const int stream_blocks = getenv("I2LQR_STREAM_BLOCKS") ? atoi(getenv("I2LQR_STREAM_BLOCKS")) : 0;  // tuning switch: warps per SM
     if (stream_blocks > 0) grid = std::min<long long>(grid, (long long)stream_blocks * h->n_sms);
     CU(h->gscratch[pipe].ensure((size_t)grid * stream_warp_doubles(kp.N)));

@@ -44,6 +44,7 @@ struct KParamsT {
   int pad0;
   R dt, dt2;      // timestep, timestep**2
   R a_max, d_lim; // clip bounds
+  R a_min, d_min; // their negations (operands straight from the constant bank instead of a negation per use)
   R eps, lamb0, lamb_factor, max_lamb;
   R cg, ch, cq2;  // control barrier: q1*q2, q1*q2^2, q2
   R ca_lo, cd_lo; // exp(-2*q2*a_max), exp(-2*q2*delta_lim)
@@ -88,6 +89,23 @@ struct StageLoopDefaults {
   __device__ __forceinline__ void cpy_wait(int) const {}
   __device__ __forceinline__ void cpy_done(int) const {}
   __device__ __forceinline__ auto ldcs(int k, int i) const { return static_cast<const Derived*>(this)->ldc(k * 8 + i); }
+  // A candidate's cold state -- start state, cos / sin of its heading, terminal target: read once or twice per pass.
+  // By default it lives in the candidate's registers; a placement that is short of registers (TmemLeanScratch) parks it.
+  template <class C, typename R>
+  __device__ __forceinline__ void load_x0(const C& c, R (&v)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = c.x0[i];
+  }
+  template <class C, typename R>
+  __device__ __forceinline__ void load_cs0(const C& c, R& cs, R& sn) const {
+    cs = c.c0;
+    sn = c.s0;
+  }
+  template <class C, typename R>
+  __device__ __forceinline__ void load_xt(const C& c, R (&v)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = c.xt[i];
+  }
 };
 template <class Derived, typename R>
 struct GainsByElement : StageLoopDefaults<Derived> {
@@ -225,14 +243,72 @@ struct TmemScratch : StageLoopDefaults<TmemScratch<kStride>> {
     st16(taddr + k * 20, v);
     st4(taddr + k * 20 + 16, v + 8);
   }
+  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const { st16(taddr + k * 20, v); }
   __device__ __forceinline__ void ldg10(int k, double (&v)[10]) const {
     ld16(taddr + k * 20, v);
     ld4(taddr + k * 20 + 16, v + 8);
   }
-  __device__ __forceinline__ void stg8(int k, const double (&v)[8]) const { st16(taddr + k * 20, v); }
   __device__ __forceinline__ void ldg8(int k, double (&v)[8]) const { ld16(taddr + k * 20, v); }
   // a tcgen05.ld must not overtake the tcgen05.st that produced its data
   __device__ __forceinline__ void fence_gains() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+// TmemLeanScratch (horizons up to 6, flat batches): the tensor-memory placement with the candidate's cold state parked
+// as well -- start state and cos / sin of its heading in six more doubles of shared memory per lane, the terminal target
+// in the eight tensor-memory columns that the gains leave free of the CTA's 128 -- so that the kernel fits 128 registers
+// and FOUR CTAs (16 warps) share an SM instead of three.  Same arithmetic, same operands, same bits.
+template <int kStride>
+struct TmemLeanScratch : TmemScratch<kStride> {
+  using Base = TmemScratch<kStride>;
+  double* cold;     // shared: [6][kStride] behind the trajectory slots
+  uint32_t txt;     // tensor-memory address of the terminal target (4 doubles)
+  __device__ __forceinline__ void bind_lean(double* smem_lane, uint32_t tmem_addr, int N) {
+    Base::bind_tmem(smem_lane, tmem_addr);
+    cold = smem_lane + (size_t)8 * N * kStride;
+    txt = tmem_addr + 20 * N;
+  }
+  template <class C>
+  __device__ __forceinline__ void park_start(const C& c) const {  // any subset of lanes
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cold[i * kStride] = c.x0[i];
+    cold[4 * kStride] = c.c0;
+    cold[5 * kStride] = c.s0;
+  }
+  // all 32 lanes: lanes with `fresh` park the terminal target they hold in registers, the others keep theirs
+  template <class C>
+  __device__ __forceinline__ void park_target(const C& c, bool fresh) const {
+    double v[4];
+    ld_xt(v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fresh ? c.xt[i] : v[i];
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :
+                 : "r"(txt), "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])), "r"(__double2hiint(v[1])),
+                   "r"(__double2loint(v[2])), "r"(__double2hiint(v[2])), "r"(__double2loint(v[3])), "r"(__double2hiint(v[3]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  __device__ __forceinline__ void ld_xt(double (&v)[4]) const {
+    int r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(txt)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __hiloint2double(r[2 * i + 1], r[2 * i]);
+  }
+  template <class C>
+  __device__ __forceinline__ void load_x0(const C&, double (&v)[4]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = cold[i * kStride];
+  }
+  template <class C>
+  __device__ __forceinline__ void load_cs0(const C&, double& cs, double& sn) const {
+    cs = cold[4 * kStride];
+    sn = cold[5 * kStride];
+  }
+  template <class C>
+  __device__ __forceinline__ void load_xt(const C&, double (&v)[4]) const { ld_xt(v); }  // warp-collective
 };
 #endif
 
@@ -555,6 +631,11 @@ __device__ __forceinline__ R terminal_cost(const KParamsT<R>& p, const CandT<R>&
   return quad4(p.Qf, xN[0] - c.xt[0], xN[1] - c.xt[1], xN[2] - c.xt[2], xN[3] - c.xt[3]);
 }
 
+template <typename R>
+__device__ __forceinline__ R terminal_cost_to(const KParamsT<R>& p, const R (&xt)[4], const R* xN) {
+  return quad4(p.Qf, xN[0] - xt[0], xN[1] - xt[1], xN[2] - xt[2], xN[3] - xt[3]);
+}
+
 // Candidate start (utils/base.py:405-410 + the first rollout of iterative_ilqr.py:32-48).  With u0 == null the
 // inputs are zero (what calc_input passes): heading and speed stay put and every stage reuses
 // cos/sin(theta_0).  u0 (2,N) is the warm start of a direct `ilqr()` call.
@@ -568,8 +649,8 @@ __device__ __forceinline__ void init_candidate(const KParamsT<R>& p, CandT<R>& c
   for (int k = 0; k < N; ++k) {
     R ua = R(0.0), ud = R(0.0);
     if (u0 != nullptr) {
-      ua = clipd(R(u0[k]), -p.a_max, p.a_max);
-      ud = clipd(R(u0[N + k]), -p.d_lim, p.d_lim);
+      ua = clipd(R(u0[k]), p.a_min, p.a_max);
+      ud = clipd(R(u0[N + k]), p.d_min, p.d_lim);
     }
     if (kQR) {
       const R l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
@@ -606,7 +687,9 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
   for (int i = 0; i < 4; ++i) xN[i] = s.ldcs(N - 1, 2 + i);
   R Vx0, Vx1, Vx2, Vx3;
   {
-    R e0 = xN[0] - c.xt[0], e1 = xN[1] - c.xt[1], e2 = xN[2] - c.xt[2], e3 = xN[3] - c.xt[3];
+    R xt[4];
+    s.load_xt(c, xt);
+    R e0 = xN[0] - xt[0], e1 = xN[1] - xt[1], e2 = xN[2] - xt[2], e3 = xN[3] - xt[3];
     Vx0 = p.Qf2[0] * e0 + p.Qf2[1] * e1 + p.Qf2[2] * e2 + p.Qf2[3] * e3;
     Vx1 = p.Qf2[1] * e0 + p.Qf2[4] * e1 + p.Qf2[5] * e2 + p.Qf2[6] * e3;
     Vx2 = p.Qf2[2] * e0 + p.Qf2[5] * e1 + p.Qf2[7] * e2 + p.Qf2[8] * e3;
@@ -635,8 +718,10 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
       o[4] = s.ldcs(k, 7);
     }
     if (k == 0) {
+      R x0[4];
+      s.load_x0(c, x0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[5 + i] = c.x0[i];
+      for (int i = 0; i < 4; ++i) o[5 + i] = x0[i];
     } else {
       o[5] = s.ldcs(k - 1, 2);
       o[6] = s.ldcs(k - 1, 3);
@@ -790,8 +875,10 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
 template <bool kQR, int kN, class Scratch, typename R = typename Scratch::real>
 __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& c, const Scratch& s, R& Jtarget) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
-  R x[4] = {c.x0[0], c.x0[1], c.x0[2], c.x0[3]};
-  R cs = c.c0, sn = c.s0;
+  R x[4];
+  s.load_x0(c, x);
+  R cs, sn;
+  s.load_cs0(c, cs, sn);
   R Jn = R(0.0), Jt = R(0.0);
   R g[10], gn[10];  // gains of the current stage; the next stage's are loaded one stage ahead
   s.fwd_begin(N);
@@ -804,8 +891,7 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
     s.ldg10(k + 1 < N ? k + 1 : k, gn);  // clamped, not conditional: the prefetch must never leave the lane's strip
     R xo[4];
     if (k == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) xo[i] = c.x0[i];
+      s.load_x0(c, xo);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) xo[i] = s.ldcs(k - 1, 2 + i);
@@ -815,8 +901,8 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
     // u + k + K (x - xo) with the sign-flipped gains of backward_pass
     R ua = (uo0 - g[0]) - fma(g[5], d3, fma(g[4], d2, fma(g[3], d1, g[2] * d0)));
     R ud = (uo1 - g[1]) - fma(g[9], d3, fma(g[8], d2, fma(g[7], d1, g[6] * d0)));
-    ua = clipd(ua, -p.a_max, p.a_max);
-    ud = clipd(ud, -p.d_lim, p.d_lim);
+    ua = clipd(ua, p.a_min, p.a_max);
+    ud = clipd(ud, p.d_min, p.d_lim);
     if (kQR) {
       const R l_ctrl = quad2(p.Rm, ua, ud);
       Jn = Jn + quad4(p.Q, x[0] - c.xt[0], x[1] - c.xt[1], x[2] - c.xt[2], x[3] - c.xt[3]) + l_ctrl;
@@ -836,7 +922,9 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
     for (int i = 0; i < 10; ++i) g[i] = gn[i];
     s.fwd_done(k);
   }
-  const R T = terminal_cost(p, c, x);
+  R xt[4];
+  s.load_xt(c, xt);
+  const R T = terminal_cost_to(p, xt, x);
   Jtarget = Jt + T;
   return Jn + T;
 }
@@ -925,8 +1013,10 @@ __device__ __forceinline__ void store_candidate(const KParamsT<R>& p, const Cand
                                                 double* uvar) {
   const int N = kN > 0 ? kN : p.N;  // kN > 0: horizon known at compile time, stage loops fully unrolled
   if (xvar) {
+    R x0[4];
+    s.load_x0(c, x0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) xvar[i * (N + 1)] = c.x0[i];
+    for (int i = 0; i < 4; ++i) xvar[i * (N + 1)] = x0[i];
   #pragma unroll(kN > 0 ? kN : 1)
   for (int k = 0; k < N; ++k) {
 #pragma unroll

@@ -85,6 +85,7 @@ struct Work {
 // the few lanes that switch candidates in a trip never stalls the warp.  kMode 1: lambda chains of a
 // controller step; a lane walks the K candidates of its (episode, lap) in rank order carrying lambda
 // (utils/base.py:393,414).
+__device__ __forceinline__ void prefetch_l2(const void* q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
 enum : int { ST_NEED = 0, ST_INIT = 1, ST_RUN = 2, ST_DONE = 3, ST_FIN = 4, ST_PARK = 5 };
 #ifndef I2LQR_SERVICE_TRIPS
 #define I2LQR_SERVICE_TRIPS 2  // flat batches: candidate switches every this many trips of the warp loop (see solve_kernel)
@@ -104,22 +105,27 @@ struct ScratchSelect {
                typename std::conditional<kScratch == 1, GlobalScratch<R>,
                typename std::conditional<kScratch == 2, HybridScratch<R, kThreads>,
                typename std::conditional<kScratch == 3, TmemScratch<kThreads>,
-               typename std::conditional<kScratch == 4, StreamScratch<kStreamRing>, StreamScratch<4>>::type>::type>::type>::type>::type;
-};  // (kScratch 5 = the streaming placement with a 4-slot ring: half the shared memory per warp, twice the warps per SM)
+               typename std::conditional<kScratch == 4, StreamScratch<kStreamRing>,
+               typename std::conditional<kScratch == 6, TmemLeanScratch<kThreads>, StreamScratch<4>>::type>::type>::type>::type>::type>::type;
+};  // (kScratch 5 = the streaming placement with a 4-slot ring: half the shared memory per warp, twice the warps per SM;
+    //  kScratch 6 = the tensor-memory placement with the candidate's cold state parked too: 128 registers, four CTAs per SM)
+constexpr int kLeanMaxHorizon = 6;  // 20 N + 8 tensor-memory columns within a CTA's 128
 __host__ __device__ __forceinline__ size_t stream_smem_bytes(int ring = kStreamRing) { return (size_t)ring * 16 * 32 * sizeof(double) + ring * 8; }
 __host__ __device__ __forceinline__ size_t stream_warp_doubles(int N) { return (size_t)N * 16 * 32; }
 
 // R = double is the product path (results within 1e-9 of the reference); R = float is the optional FP32
 // build of BASELINE config 4 (inputs / outputs stay double, everything in between is single precision).
 template <typename R, bool kQR, int kScratch, int kMode, int kThreads>
-__global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : (kScratch == 5 ? 12 : 1))
+__global__ void __launch_bounds__(kThreads, kScratch == 3 ? 3 : (kScratch == 6 ? 4 : (kScratch == 5 ? 12 : 1)))
 solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work w) {
   extern __shared__ double smem_raw[];
   R* smem = reinterpret_cast<R*>(smem_raw);
   using ScratchT = typename ScratchSelect<R, kScratch, kThreads>::type;
   ScratchT s;
   __shared__ uint32_t tmem_base;
-  if constexpr (kScratch == 3) {
+  constexpr bool kTmem = kScratch == 3 || kScratch == 6;
+  constexpr bool kLean = kScratch == 6;
+  if constexpr (kTmem) {
     if (threadIdx.x < 32) {  // one warp allocates the CTA's tensor-memory columns
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                        (uint32_t)__cvta_generic_to_shared(&tmem_base)),
@@ -130,9 +136,16 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     }
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    s.bind_tmem(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
+    if constexpr (kLean) {
+      s.bind_lean(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16), p.N);
+      CandT<R> z = {};
+      s.park_start(z);
+      s.park_target(z, true);
+    } else {
+      s.bind_tmem(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16));
+    }
     for (int e = 0; e < 8 * p.N; ++e) s.stc(e, R(0.0));  // lanes without a live candidate iterate on zeros
-  } else if constexpr (kScratch >= 4) {
+  } else if constexpr (kScratch == 4 || kScratch == 5) {
     s.bind_stream(smem_raw, w.gscratch + (size_t)blockIdx.x * stream_warp_doubles(p.N), threadIdx.x & 31, p.N);
     for (int e = 0; e < 16 * p.N; ++e) s.gcur[(size_t)e * 32 + (threadIdx.x & 31)] = 0.0;  // lanes without a live candidate iterate on zeros
   } else {
@@ -143,20 +156,25 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
   const int N = p.N;
   CandT<R> c = {};
   int state = ST_NEED;
-  long long item = 0;
-  unsigned long long my_iters = 0, my_solves = 0;
+  // (the lean placement counts in 32 bits: a launch serves fewer than 2^31 candidates and a lane fewer than 2^32 iterations)
+  using index_t = typename std::conditional<kScratch == 6, int, long long>::type;
+  using count_t = typename std::conditional<kScratch == 6, unsigned, unsigned long long>::type;
+  index_t item = 0;
+  count_t my_iters = 0, my_solves = 0;
 
   if constexpr (kMode == 0) {
     // ---- prefetched next candidate
     bool have_next = false, exhausted = false;
-    long long n_item = 0;
+    index_t n_item = 0;
     long long n_total = w.n_items;
     if (w.pass > 0) {
       n_total = (long long)*w.resume_count;
       if (n_total > w.park_capacity) n_total = w.park_capacity;
     }
     const int park_words = 8 * N + 4;
-    long long n_idx = 0, idx = 0;  // position in the pass's work list (== candidate id in pass 0)
+    index_t n_idx = 0, idx = 0;  // position in the pass's work list (== candidate id in pass 0)
+    // (the lean placement keeps no prefetched inputs in registers: it asks for the lines in L2 and loads them when the
+    //  lane takes the candidate, a service trip or more later)
     double n_x0[4], n_xt[4], n_lamb = (double)p.lamb0;
     DevObstacle n_obs;
     n_obs.present = 0;
@@ -193,7 +211,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
             state = ST_NEED;
           }
         } else if (state == ST_FIN) {
-          store_candidate<kN>(p, c, s, w.xvar ? w.xvar + item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + item * 2 * N : nullptr);
+          store_candidate<kN>(p, c, s, w.xvar ? w.xvar + (long long)item * 4 * (N + 1) : nullptr, w.uvar ? w.uvar + (long long)item * 2 * N : nullptr);
           if (w.lamb_out) w.lamb_out[item] = (double)c.lamb;
           if (w.iters) w.iters[item] = c.iters;
           state = ST_NEED;
@@ -233,27 +251,45 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
           if ((int)lane == leader) base = atomicAdd(w.counter, (unsigned long long)__popc(want));
           base = __shfl_sync(0xffffffffu, base, leader);
           if (!have_next && !exhausted) {
-            n_idx = (long long)(base + __popc(want & ((1u << lane) - 1u)));
-            if (n_idx >= n_total) {
+            const long long fetched = (long long)(base + __popc(want & ((1u << lane) - 1u)));
+            n_idx = (index_t)fetched;
+            if (fetched >= n_total) {
               exhausted = true;
             } else {
-              n_item = w.pass > 0 ? (long long)w.resume_list[n_idx] : n_idx;
+              n_item = w.pass > 0 ? (index_t)w.resume_list[n_idx] : n_idx;
               have_next = true;
+              if constexpr (kLean) {
+                prefetch_l2(w.x0 + (long long)n_item * 4);
+                prefetch_l2(w.x_term + (long long)n_item * 4);
+                if (w.lamb_in) prefetch_l2(w.lamb_in + n_item);
+                if (w.n_obs > 1) prefetch_l2(w.obs + n_item);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                n_x0[i] = w.x0[n_item * 4 + i];
-                n_xt[i] = w.x_term[n_item * 4 + i];
+                for (int i = 0; i < 4; ++i) {
+                  n_x0[i] = w.x0[n_item * 4 + i];
+                  n_xt[i] = w.x_term[n_item * 4 + i];
+                }
+                if (w.lamb_in) n_lamb = w.lamb_in[n_item];
+                if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : n_item];
               }
-              if (w.lamb_in) n_lamb = w.lamb_in[n_item];
-              if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : n_item];
             }
           }
         }
         // (b) lanes that need a candidate take the prefetched one
+        bool took = false;
         if (state == ST_NEED) {
           if (have_next) {
             item = n_item;
             idx = n_idx;
+            if constexpr (kLean) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                n_x0[i] = w.x0[(long long)item * 4 + i];
+                n_xt[i] = w.x_term[(long long)item * 4 + i];
+              }
+              if (w.lamb_in) n_lamb = w.lamb_in[item];
+              if (w.n_obs != 0) n_obs = w.obs[w.n_obs == 1 ? 0 : item];
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               c.x0[i] = R(n_x0[i]);
@@ -262,8 +298,9 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
             c.lamb = R(n_lamb);
             load_obstacle(p, c, w.n_obs != 0 ? &n_obs : nullptr);
             sincos_fast(c.x0[3], &c.s0, &c.c0);
+            took = true;
             if (w.pass == 0) {
-              init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + item * 2 * N : nullptr);
+              init_candidate<kQR, kN>(p, c, s, w.u_init != nullptr ? w.u_init + (long long)item * 2 * N : nullptr);
             } else {  // resume a candidate parked by the previous pass
               const double* ps = w.resume_state + (size_t)idx * park_words;
               for (int e = 0; e < 8 * N; ++e) s.stc(e, R(ps[e]));
@@ -274,9 +311,14 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
             have_next = false;
             no_park = false;
             state = ST_RUN;
+            if constexpr (kLean) s.park_start(c);
           } else if (exhausted) {
             state = ST_DONE;
           }
+        }
+        if constexpr (kLean) {
+          __syncwarp();
+          s.park_target(c, took);  // warp-collective tensor-memory store
         }
       }
       if (__all_sync(0xffffffffu, state == ST_DONE)) break;
@@ -375,7 +417,7 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     atomicAdd(w.stats + 0, my_iters);
     atomicAdd(w.stats + 1, my_solves);
   }
-  if constexpr (kScratch == 3) {
+  if constexpr (kTmem) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32)

@@ -95,7 +95,7 @@ __device__ __forceinline__ R chain_init(const KParamsT<R>& p, const CandT<R>& c,
       const R l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
       J = J + l_state + quad2(p.Rm, ua, ud);
     }
-    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
+    const R sd = x[2] * p.dt + ua * p.hdt2;
     x[0] = x[0] + c.c0 * sd;
     x[1] = x[1] + c.s0 * sd;
     x[2] = x[2] + ua * p.dt;
@@ -146,13 +146,13 @@ __device__ __forceinline__ void chain_task_eval(const KParamsT<R>& p, const Cand
   const R dt = p.dt;
   const bool terminal = t.k == p.N;
   const R ua = t.ua, ud = t.ud, cs = t.cs, sn = t.sn;
-  const R sp = t.v1 * dt + (ua * p.dt2) / R(2.0);
+  const R sp = t.v1 * dt + ua * p.hdt2;
   o[0] = cs * dt;
   o[1] = -sp * sn;
   o[2] = sn * dt;
   o[3] = sp * cs;
-  o[4] = p.dt2 * cs / R(2.0);
-  o[5] = p.dt2 * sn / R(2.0);
+  o[4] = p.hdt2 * cs;
+  o[5] = p.hdt2 * sn;
   R lu0, lu1, luu00, luu11;
   {
     const R e1 = exp_fast_bounded(p.cq2 * (ua - p.a_max)), e3 = exp_fast_bounded(p.cq2 * (ud - p.d_lim));
@@ -431,7 +431,7 @@ __device__ __forceinline__ R chain_forward(const KParamsT<R>& p, const CandT<R>&
       dp[6 * S] = cs;
       dp[7 * S] = sn;
     }
-    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
+    const R sd = x[2] * p.dt + ua * p.hdt2;
     x[0] = x[0] + cs * sd;
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;

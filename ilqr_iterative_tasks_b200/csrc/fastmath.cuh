@@ -109,14 +109,23 @@ I2_HD double exp_fast(double x) { return exp_fast_bounded(fmin(fmax(x, -745.0), 
 // sin and cos of x for |x| <= 1e5 (larger or non-finite arguments take the library path): quadrant
 // reduction with a three-term pi/2 (k * P1, k * P2 exact for |k| < 2^20), fdlibm kernel polynomials
 // (|r| <= pi/4, < 1 ulp each).
+struct SinCos {
+  double sn, cs;
+};
+#ifdef __CUDACC__
+__device__ __noinline__ SinCos sincos_library(double x) {  // out of line: rare
+  SinCos r;
+  sincos(x, &r.sn, &r.cs);
+  return r;
+}
+#else
+inline SinCos sincos_library(double x) { return SinCos{sin(x), cos(x)}; }
+#endif
 I2_HD void sincos_fast(double x, double* sn, double* cs) {
   if (!(fabs(x) <= 1.0e5)) {
-#ifdef __CUDA_ARCH__
-    sincos(x, sn, cs);
-#else
-    *sn = sin(x);
-    *cs = cos(x);
-#endif
+    const SinCos r = sincos_library(x);
+    *sn = r.sn;
+    *cs = r.cs;
     return;
   }
   const double magic = 6755399441055744.0;

@@ -43,6 +43,8 @@ struct KParamsT {
   int has_qr;          // matrix_Q != 0 or matrix_R != 0
   int pad0;
   R dt, dt2;      // timestep, timestep**2
+  R hdt2;         // timestep**2 / 2: (u * dt2) / 2 and dt2 * c / 2 of the reference are u * hdt2 and hdt2 * c bit for bit
+                  // (halving is exact and commutes with the product's rounding), one multiplication less each
   R a_max, d_lim; // clip bounds
   R a_min, d_min; // their negations (operands straight from the constant bank instead of a negation per use)
   R eps, lamb0, lamb_factor, max_lamb;
@@ -597,17 +599,18 @@ __device__ __forceinline__ void obstacle_barrier_extra(const KParamsT<R>& p, con
 // reference's own runs: SURVEY.md 8a, a5) the clamp is the identity and the result is exactly
 // (Quu + lamb I)^-1, evaluated here in closed form with one reciprocal.  Otherwise the symmetric
 // eigen-decomposition is done by one Jacobi rotation (stable when |b| << |a-d|).
+#ifdef __CUDACC__
+#define I2_NOINLINE __device__ __noinline__
+#else
+#define I2_NOINLINE inline
+#endif
+// (the rare branch, kept out of line: inlined it is 200 instructions in the middle of every backward stage)
 template <typename R>
-__device__ __forceinline__ void quu_inverse(R a, R b, R d, R lamb, R& i00, R& i01,
-                                            R& i11) {
-  if (a * d - b * b >= R(0.0) && a + d >= R(0.0)) {
-    const R al = a + lamb, dl = d + lamb;
-    const R r = rcp_fast(al * dl - b * b);
-    i00 = dl * r;
-    i01 = -b * r;
-    i11 = al * r;
-    return;
-  }
+struct Sym2 {
+  R m00, m01, m11;
+};
+template <typename R>
+I2_NOINLINE Sym2<R> quu_inverse_clamped(R a, R b, R d, R lamb) {
   R c = R(1.0), s = R(0.0), e1 = a, e2 = d;
   if (b != R(0.0)) {
     R tau = (d - a) / (R(2.0) * b);
@@ -620,9 +623,27 @@ __device__ __forceinline__ void quu_inverse(R a, R b, R d, R lamb, R& i00, R& i0
   e1 = (e1 < R(0.0) ? R(0.0) : e1) + lamb;
   e2 = (e2 < R(0.0) ? R(0.0) : e2) + lamb;
   R r1 = R(1.0) / e1, r2 = R(1.0) / e2;
-  i00 = c * r1 * c + s * r2 * s;
-  i01 = s * r2 * c - c * r1 * s;
-  i11 = s * r1 * s + c * r2 * c;
+  Sym2<R> o;
+  o.m00 = c * r1 * c + s * r2 * s;
+  o.m01 = s * r2 * c - c * r1 * s;
+  o.m11 = s * r1 * s + c * r2 * c;
+  return o;
+}
+template <typename R>
+__device__ __forceinline__ void quu_inverse(R a, R b, R d, R lamb, R& i00, R& i01,
+                                            R& i11) {
+  if (a * d - b * b >= R(0.0) && a + d >= R(0.0)) {
+    const R al = a + lamb, dl = d + lamb;
+    const R r = rcp_fast(al * dl - b * b);
+    i00 = dl * r;
+    i01 = -b * r;
+    i11 = al * r;
+    return;
+  }
+  const Sym2<R> o = quu_inverse_clamped(a, b, d, lamb);
+  i00 = o.m00;
+  i01 = o.m01;
+  i11 = o.m11;
 }
 
 // Terminal cost (x_N - x_t)^T Qf (x_N - x_t)
@@ -656,7 +677,7 @@ __device__ __forceinline__ void init_candidate(const KParamsT<R>& p, CandT<R>& c
       const R l_state = quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]);
       J = J + l_state + quad2(p.Rm, ua, ud);
     }
-    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
+    const R sd = x[2] * p.dt + ua * p.hdt2;
     x[0] = x[0] + cs * sd;
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;
@@ -752,9 +773,9 @@ __device__ __forceinline__ void backward_pass(const KParamsT<R>& p, const CandT<
     const R cs = op[3], sn = op[4];     // cos / sin theta_{k+1}
     R xk[4] = {op[5], op[6], op[7], op[8]};
     // ---- linearisation at (v_{k+1}, theta_{k+1}, a_k): iterative_ilqr.py:92-99, kinetic_bicycle.py:30-52
-    const R sp = v1 * dt + (ua * p.dt2) / R(2.0);
+    const R sp = v1 * dt + ua * p.hdt2;
     const R al = cs * dt, be = -sp * sn, ga = sn * dt, de = sp * cs;
-    const R b0 = p.dt2 * cs / R(2.0), b1 = p.dt2 * sn / R(2.0);
+    const R b0 = p.hdt2 * cs, b1 = p.hdt2 * sn;
     // ---- stage cost derivatives: ilqr_helper.py:25-55, input barriers :83-103
     R lu0, lu1, luu00, luu11;
     {
@@ -908,7 +929,7 @@ __device__ __forceinline__ R forward_pass(const KParamsT<R>& p, const CandT<R>& 
       Jn = Jn + quad4(p.Q, x[0] - c.xt[0], x[1] - c.xt[1], x[2] - c.xt[2], x[3] - c.xt[3]) + l_ctrl;
       Jt = Jt + quad4(p.Q, x[0] - p.xtarget[0], x[1] - p.xtarget[1], x[2] - p.xtarget[2], x[3] - p.xtarget[3]) + l_ctrl;
     }
-    const R sd = x[2] * p.dt + (ua * p.dt2) / R(2.0);
+    const R sd = x[2] * p.dt + ua * p.hdt2;
     x[0] = x[0] + cs * sd;
     x[1] = x[1] + sn * sd;
     x[2] = x[2] + ua * p.dt;

@@ -137,7 +137,11 @@ solve_kernel(const __grid_constant__ KParamsT<R> p, const __grid_constant__ Work
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if constexpr (kLean) {
-      s.bind_lean(smem + threadIdx.x, tmem_base + (((threadIdx.x >> 5) * 32u) << 16), p.N);
+      // (the thread index goes through an opaque move: otherwise the lane's shared-memory base is re-derived from
+      //  SR_TID.X -- six instructions -- in every stage of every loop rather than kept in its register)
+      unsigned tid = threadIdx.x;
+      asm volatile("mov.u32 %0, %0;" : "+r"(tid));
+      s.bind_lean(smem + tid, tmem_base + (((tid >> 5) * 32u) << 16), p.N);
       CandT<R> z = {};
       s.park_start(z);
       s.park_target(z, true);

@@ -37,6 +37,7 @@ inline const char* fill_kparams(const i2lqr_params& p, KParams* k) {
   k->max_relax = p.max_relax_iter;
   k->dt = p.timestep;
   k->dt2 = p.timestep * p.timestep;
+  k->hdt2 = k->dt2 / 2.0;
   k->a_max = p.a_max;
   k->d_lim = p.delta_lim;
   k->a_min = -p.a_max;
@@ -75,7 +76,7 @@ inline KParamsT<float> to_float(const KParams& k) {
   KParamsT<float> f;
   f.N = k.N; f.N_param = k.N_param; f.K = k.K; f.L = k.L; f.max_iter = k.max_iter; f.max_relax = k.max_relax;
   f.has_qr = k.has_qr; f.pad0 = 0;
-  f.dt = (float)k.dt; f.dt2 = (float)k.dt2; f.a_max = (float)k.a_max; f.d_lim = (float)k.d_lim; f.a_min = (float)k.a_min; f.d_min = (float)k.d_min;
+  f.dt = (float)k.dt; f.dt2 = (float)k.dt2; f.hdt2 = f.dt2 / 2.0f; f.a_max = (float)k.a_max; f.d_lim = (float)k.d_lim; f.a_min = (float)k.a_min; f.d_min = (float)k.d_min;
   f.eps = (float)k.eps; f.lamb0 = (float)k.lamb0; f.lamb_factor = (float)k.lamb_factor; f.max_lamb = (float)k.max_lamb;
   f.cg = (float)k.cg; f.ch = (float)k.ch; f.cq2 = (float)k.cq2; f.ca_lo = (float)k.ca_lo; f.cd_lo = (float)k.cd_lo;
   f.og = (float)k.og; f.oh = (float)k.oh; f.oq2 = (float)k.oq2; f.one_margin = (float)k.one_margin;

@@ -30,15 +30,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram bytes of the dominant launch (pass 0 over 2^20 candidates) from profiles/r01_solve_kernel_v7_summary.txt
-NCU_TRAFFIC_BYTES = 129926656 + 298526976
+# dram bytes of the dominant launch (pass 0 over 2^20 candidates) from profiles/r02_solve_kernel_v8_lean_pass0_summary.txt
+NCU_TRAFFIC_BYTES = 135843072 + 307914752
 # what the kernel EXECUTES (it exploits the sparsity of A / B / Vxx, so fewer flops than the dense algorithmic count) and
 # how busy the FP64 pipe is, from the committed ncu capture of the same launch -- a static annotation of the line, the live
 # numbers are `achieved` / `frac`
 NCU_EXECUTED = {
-    "source": "profiles/r01_solve_kernel_v7_summary.txt (ncu --set full, pass-0 launch over 2^20 candidates)",
-    "pipe_fp64_busy": 0.612, "executed_tflops": 15.4, "executed_frac_of_measured_peak": 0.46,
-    "note": "SASS mix 520.7 M DFMA + 210.9 M DMUL + 75.7 M DADD warp instructions x 29.09 active lanes = 38.6 GFLOP per launch",
+    "source": "profiles/r02_solve_kernel_v8_lean_pass0_summary.txt (ncu --set full, pass-0 launch over 2^20 candidates, 2.32 ms)",
+    "pipe_fp64_busy": 0.632, "executed_tflops": 16.6, "executed_frac_of_measured_peak": 0.49,
+    "note": "SASS mix 538.7 M DFMA + 191.1 M DMUL + 67.9 M DADD warp instructions x 28.90 active lanes = 38.6 GFLOP per launch; "
+            "3.86 warps per SM sub-partition (128 registers, four CTAs per SM)",
 }
 METRIC = "candidate iLQR solves/sec"
 UNIT = "solves/s"
@@ -608,8 +609,8 @@ def run_ours(args):
                 "bound": "fp64_fma", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "traffic": NCU_TRAFFIC_BYTES if (B == 1 << 20 and N == 6) else None,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the pass-0 launch (2^20 candidates), one ncu --set full "
-                                "capture: profiles/r01_solve_kernel_v7_summary.txt; algorithmic bytes per launch = %d" % (B * bytes_per_solve(N)),
-                "kernel": "solve_kernel<double, kQR=false, kScratch=3 (tensor-memory gains), kMode=0, 128 threads>", "kernel_ms": avg_ms,
+                                "capture: profiles/r02_solve_kernel_v8_lean_pass0_summary.txt; algorithmic bytes per launch = %d" % (B * bytes_per_solve(N)),
+                "kernel": "solve_kernel<double, kQR=false, kScratch=6 (lean tensor-memory placement: gains and terminal target in tensor memory, 128 registers, four CTAs per SM), kMode=0, 128 threads>", "kernel_ms": avg_ms,
                 "isolated": {"launch_ms": kernel_ms, "achieved": flops / (kernel_ms * 1e-3) / 1e12,
                              "frac": flops / (kernel_ms * 1e-3) / 1e12 / fp64_peak,
                              "note": "one launch at a time on one stream (what ncu sees); the timed region pipelines "

@@ -323,7 +323,7 @@ def _episodes_parity(p, sc, lap0, keep, n_eps=64, n_laps=2):
             "ok": bool(all(r[0] for r in res) and worst < 1e-8), "checker": "oracle closed loop (tests/helpers.py), %.1f s" % (time.perf_counter() - t0)}  # fmt: skip
 
 
-def host_ceiling_probe(dev, dist, torch, nbytes, reps=3):
+def host_ceiling_probe(dev, dist, torch, nbytes, reps=3, h2d_bytes=0):
     """What the host side of PCIe gives every rank when ALL ranks copy at once: pinned D2H (and H2D) of one step's
     result bytes, barrier-aligned, best of `reps`; max-over-ranks time -> aggregate GB/s.  This is the ceiling `e2e`
     is measured against (the single-NUMA VMs of this pool cap aggregate device-to-host traffic well below N links)."""
@@ -349,6 +349,31 @@ def host_ceiling_probe(dev, dist, torch, nbytes, reps=3):
             best = min(best, float(t[0]))
         out[name + "_gbs_per_gpu"] = n / best / 1e9
         out[name + "_gbs_aggregate"] = n * world / best / 1e9
+    # duplex: the pipeline uploads the next step's inputs WHILE it downloads results, and both directions share the host's
+    # memory system -- so the download rate with a concurrent upload of one step's input bytes is the ceiling that applies
+    if h2d_bytes:
+        m = int(h2d_bytes)
+        hin = torch.empty(m, dtype=torch.uint8).pin_memory()
+        din = torch.empty(m, dtype=torch.uint8, device=dev)
+        up = torch.cuda.Stream(dev)
+        best = float("inf")
+        for _ in range(reps + 1):
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(up):
+                din.copy_(hin, non_blocking=True)
+            hbuf.copy_(dbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t[0]))
+        out["d2h_gbs_aggregate_duplex"] = n * world / best / 1e9
+        out["duplex_h2d_bytes"] = m
     out["bytes"] = n
     return out
 
@@ -550,7 +575,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_min_s = time.perf_counter() - t0
     barrier()
-    ceiling = host_ceiling_probe(dev, dist, torch, B * (16 * N + 32 * (N + 1) + 8 + 4))
+    ceiling = host_ceiling_probe(dev, dist, torch, B * (16 * N + 32 * (N + 1) + 8 + 4), h2d_bytes=B * 120)
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_s * 1e3, kernel_ms, float(iters_total), e2e_min_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -596,9 +621,11 @@ def run_ours(args):
                     "host_ceiling": ceiling,
                     "d2h_gbs_aggregate": d2h * world / (e2e_ms / args.steps * 1e-3) / 1e9,
                     "frac_of_d2h_ceiling": d2h * world / (e2e_ms / args.steps * 1e-3) / 1e9 / ceiling["d2h_gbs_aggregate"],
+                    "frac_of_duplex_ceiling": d2h * world / (e2e_ms / args.steps * 1e-3) / 1e9 / ceiling["d2h_gbs_aggregate_duplex"],
                     "ceiling_note": "host_ceiling = all ranks copying one step's result bytes device-to-host at once (pinned, barrier-aligned, "
                                     "max over ranks); e2e is download-bound, so d2h_gbs_aggregate / host_ceiling.d2h_gbs_aggregate is how close the "
-                                    "pipeline runs to what the box gives"},
+                                    "pipeline runs to what the box gives; d2h_gbs_aggregate_duplex = the same download with one step's input "
+                                    "bytes going up at the same time, as they do in the pipeline"},
             "e2e_min": {"value": B * world * args.steps / (e2e_min_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_min_ms / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 12,
                         "note": "VARIANT, not the headline: same host call with uvar / xvar declined (NULL) -- only lamb_out and the iteration "

@@ -680,7 +680,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-latency", action="store_true", help="skip the controller-step latency probe")
     ap.add_argument("--no-pipeline", action="store_true", help="one handle / one stream: steps strictly back to back")
-    ap.add_argument("--pipeline", type=int, default=4, help="handles (streams) that consecutive steps rotate over")
+    ap.add_argument("--pipeline", type=int, default=6, help="handles (streams) that consecutive steps rotate over")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of the `sustained` leg (0 = skip)")
     ap.add_argument("--no-episodes", action="store_true", help="skip the BASELINE config 3 leg (`episodes` object)")
     ap.add_argument("--no-split", action="store_true", help="skip the NCCL split-step leg (`split_step` object, world >= 2)")

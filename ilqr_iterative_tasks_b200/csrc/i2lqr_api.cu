@@ -1354,7 +1354,8 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, cons
   // (entries the workers cannot reach in time are solved in place by the resolvers: correct, just no faster than the chain itself)
   int S = spec_set_size();
   const long long group_slots = (resident - chains) * per_warp;
-  while (S > 4 && chains * std::max(1, a.k_eff - 1) * S > 2 * group_slots) S /= 2;
+  static const int waves = getenv("I2LQR_SPEC_WAVES") ? std::max(1, atoi(getenv("I2LQR_SPEC_WAVES"))) : 8;  // tuning switch (2: 1.38 ms per step at 62 episodes, 8: 1.25)
+  while (S > 4 && chains * std::max(1, a.k_eff - 1) * S > waves * group_slots) S /= 2;
   a.S = S;
   const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * S + per_warp - 1) / per_warp);
   const long long grid = std::min<long long>(resident, chains + workers);

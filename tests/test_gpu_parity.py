@@ -113,6 +113,39 @@ def test_streaming_placement_vs_oracle(eng_mod, N, B, variant):
     assert H.rel_err(out["uvar"][same], u[same]).max() <= tol
 
 
+@pytest.mark.parametrize("N,variant", [(2, "plain"), (3, "plain"), (5, "plain"), (6, "shared_obstacle"), (6, "no_obstacle"), (6, "warm"), (4, "null_outputs")])
+def test_lean_tensor_memory_placement_vs_oracle(eng_mod, N, variant):
+    """Batches of >= 8192 candidates at horizons <= 6 run the LEAN tensor-memory variant (solve_kernel<double,0,6,0,128>: the
+    candidate's start state parked in shared memory, its terminal target in the tensor-memory columns behind the gains, inputs
+    loaded when the lane takes the candidate).  Horizons below 6 move the parked target's column offset; a shared obstacle, no
+    obstacle, lambda_in = NULL and warm starts exercise the other branches of the candidate switch; declined outputs the store."""
+    from ilqr_iterative_tasks_b200 import _abi, synth
+    from oracle import oracle
+
+    B = 8192 + 57
+    d = synth.flat_candidates(B, N, seed=synth.SEED + 700 + N)
+    p = _abi.default_params(num_horizon=N)
+    obs = _abi.obstacle_array(d["obs"], d["mode"])
+    lamb_in, uinit = d["lamb_in"], None
+    if variant == "shared_obstacle":
+        obs, lamb_in = _abi.Obstacle(3.0, 0.5, 3.0, 2.0, 0.4, 1, 1), None
+    elif variant == "no_obstacle":
+        obs = None
+    elif variant == "warm":
+        uinit = np.random.default_rng(N).standard_normal((B, 2, N)) * np.array([0.5, 0.2])[None, :, None]
+    e = eng_mod.Engine(p)
+    out = e.solve_batch(d["x0"], d["x_term"], lamb_in, obs, uvar_init=uinit)
+    assert e.last_stats()["solves"] == B
+    if variant == "null_outputs":
+        only = e.solve_batch(d["x0"], d["x_term"], lamb_in, obs, want=("lamb_out", "iters"))
+        assert np.array_equal(only["iters"], out["iters"]) and np.array_equal(only["lamb_out"], out["lamb_out"])
+    e.close()
+    u, x, lamb, iters = oracle.ilqr_batch(p, d["x0"], d["x_term"], np.ones(B) * p.lamb if lamb_in is None else lamb_in, obs, nthreads=8, uvar_init=uinit)
+    same = H.same_discrete_path(out["iters"], out["lamb_out"], iters, lamb, "lean tensor-memory variant, N=%d %s" % (N, variant))
+    assert H.rel_err(out["xvar"][same], x[same]).max() <= H.RTOL
+    assert H.rel_err(out["uvar"][same], u[same]).max() <= H.RTOL
+
+
 def test_flat_batch_size_boundaries(eng_mod):
     """Batch sizes around every launch-shape threshold (one lane, one warp, one CTA, the tensor-memory variant from
     8192 candidates, iteration-sliced passes from 131072): each equals the first B candidates of one big oracle run."""

@@ -324,7 +324,9 @@ int launch_chain(i2lqr_handle* h, Work w, cudaStream_t st) {
   if (fp32 && scratch == 2) scratch = 1;
   static const int force_rungs = getenv("I2LQR_RUNGS") ? atoi(getenv("I2LQR_RUNGS")) : 0;  // tuning switch
   const long long slots = 4LL * h->n_sms;  // one warp per SM sub-partition
-  int rungs = w.n_items * 4 <= slots * 32 ? 4 : (w.n_items * 2 <= slots * 32 ? 2 : 1);
+  // (four rungs up to TWO warps per sub-partition: at 8192 chains -- a 4096-episode lap at full load -- steps take 3.3-5.3 ms
+  //  against 3.8-5.4 ms with two rungs in one warp per sub-partition; beyond that the rungs are dropped for lanes)
+  int rungs = w.n_items * 4 <= 2 * slots * 32 ? 4 : (w.n_items * 2 <= slots * 32 ? 2 : 1);
   if (force_rungs == 1 || force_rungs == 2 || force_rungs == 4) rungs = force_rungs;
   const void* kern;
   if (fp32)
@@ -1244,7 +1246,12 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));  // the host vectors go out of scope
   }
   if (chains > h->sp_cmax || K != h->sp_K || S != h->sp_S || n_episodes > h->sp_E || N != h->sp_N) {
-    const int cmax = std::max(chains, h->sp_cmax), E = std::max(n_episodes, h->sp_E);
+    // sized once for the largest step this handle can ever route here (its own episode count, capped by the form's limit):
+    // the tail of a batched lap enters with a different episode count every lap, and growing the tables then means
+    // cudaFree + cudaMalloc of ~70 MB in the middle of the lap (a device-wide synchronisation: measured as single steps of
+    // up to 145 ms in a 4096-episode lap)
+    const int e_cap = std::max(1, std::min(h->E, spec_max_chains() / std::max(1, h->L)));
+    const int cmax = std::max(std::max(chains, h->sp_cmax), e_cap * h->L), E = std::max(std::max(n_episodes, h->sp_E), e_cap);
     const size_t entries = (size_t)kOuter * cmax * K * S;
     CU(h->sp_state.ensure(entries));
     CU(h->sp_lamb.ensure(entries));
@@ -1266,6 +1273,22 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     h->sp_S = S;
     h->sp_N = N;
   }
+  return 0;
+}
+
+// Everything the one-launch step needs the first time it runs -- its tables, the kernel's image (the runtime loads a
+// function when it is first referenced) and its attributes -- done at set-up time, so that the first small step of a
+// batched lap does not pay for it in the middle of the lap (measured: one step of 7 ... 41 ms).
+int spec_prepare(i2lqr_handle* h, cudaStream_t st) {
+  const int e_cap = std::max(1, std::min(h->E, spec_max_chains() / std::max(1, h->L)));
+  if (!spec_eligible(h, e_cap)) return 0;
+  if (spec_ensure(h, e_cap, st)) return 1;
+  const void* kern = h->kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
+  const size_t smem = spec_smem_bytes(h);
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
   return 0;
 }
 
@@ -1820,6 +1843,7 @@ int i2lqr_episodes_begin(i2lqr_handle* h, const double* x_init, const double* go
   CU(cudaMemsetAsync(h->ep_status.p, 0, E * sizeof(int), st));
   std::vector<int> hor(E, (int)N);
   CU(cudaMemcpyAsync(h->ep_horizon.p, hor.data(), E * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (spec_prepare(h, st)) return 1;
   CU(cudaStreamSynchronize(st));
   h->ep_ready = true;
   h->ep_lap_index = 0;

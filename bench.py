@@ -423,6 +423,9 @@ def run_ours(args):
     # iteration-count tail of step k (its resume passes: a few 150-iteration stragglers, 1.5 ms of sequential trips) is
     # still draining.  Measured on one B200 at 24 steps: 2 streams 367, 3: 390, 4: 402, 8: 412 M solves/s
     n_pipe = 1 if args.no_pipeline else max(1, args.pipeline)
+    # the end-to-end arm keeps at most four caller threads (one handle and one set of pinned buffers each): it is bound by the
+    # download direction of PCIe from two threads on, and with eight ranks on a 32-CPU box more threads only oversubscribe the host
+    n_host = min(n_pipe, 4)
     engs = [engine.Engine(params, device=local) for _ in range(n_pipe)]
     eng = engs[0]
     dev = torch.device("cuda", local)
@@ -439,7 +442,7 @@ def run_ours(args):
             "lamb_out": torch.empty(B, dtype=torch.float64).pin_memory(),
             "iters": torch.empty(B, dtype=torch.int32).pin_memory(),
         }
-        for _ in range(n_pipe)
+        for _ in range(n_host)
     ]
     # ---- HBM-resident arm (value + roofline)
     g_x0, g_xt, g_lamb, g_obs = h_x0.to(dev), h_xt.to(dev), h_lamb.to(dev), h_obs.to(dev)
@@ -552,11 +555,11 @@ def run_ours(args):
         for _ in range(n):
             engs[i].solve_batch(x0_np, xt_np, lamb_np, obs_np, out=outs_np[i])
 
-    for i in range(n_pipe):
+    for i in range(n_host):
         host_steps(i, 1)
     barrier()
-    share = [args.steps // n_pipe + (1 if i < args.steps % n_pipe else 0) for i in range(n_pipe)]
-    threads = [threading.Thread(target=host_steps, args=(i, share[i])) for i in range(n_pipe)]
+    share = [args.steps // n_host + (1 if i < args.steps % n_host else 0) for i in range(n_host)]
+    threads = [threading.Thread(target=host_steps, args=(i, share[i])) for i in range(n_host)]
     t0 = time.perf_counter()
     for t in threads:
         t.start()
@@ -574,10 +577,10 @@ def run_ours(args):
         for _ in range(n):
             engs[i].solve_batch(x0_np, xt_np, lamb_np, obs_np, want=("lamb_out", "iters"), out=min_np[i])
 
-    for i in range(n_pipe):
+    for i in range(n_host):
         host_steps_min(i, 1)
     barrier()
-    threads = [threading.Thread(target=host_steps_min, args=(i, share[i])) for i in range(n_pipe)]
+    threads = [threading.Thread(target=host_steps_min, args=(i, share[i])) for i in range(n_host)]
     t0 = time.perf_counter()
     for t in threads:
         t.start()
@@ -628,7 +631,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(B, N, world, n_pipe, args.pre_warm_s),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
-                    "api": "i2lqr_solve_batch (ctypes), pinned host buffers, %d host threads each driving its own handle" % n_pipe,
+                    "api": "i2lqr_solve_batch (ctypes), pinned host buffers, %d host threads each driving its own handle" % n_host,
                     "host_ceiling": ceiling,
                     "d2h_gbs_aggregate": d2h * world / (e2e_ms / args.steps * 1e-3) / 1e9,
                     "frac_of_d2h_ceiling": d2h * world / (e2e_ms / args.steps * 1e-3) / 1e9 / ceiling["d2h_gbs_aggregate"],

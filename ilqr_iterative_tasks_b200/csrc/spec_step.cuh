@@ -27,7 +27,10 @@ namespace i2lqr {
 constexpr int kSpecMaxSet = 32;      // speculation set entries (one per lane of the resolver)
 constexpr int kSpecHist = 64;        // histogram slots (two per lane)
 constexpr int kSpecRungs = 4;
-constexpr int kSpecWorkerGroup = 4;  // lanes per speculative candidate: 8 candidates per worker warp
+#ifndef I2LQR_SPEC_WG
+#define I2LQR_SPEC_WG 4
+#endif
+constexpr int kSpecWorkerGroup = I2LQR_SPEC_WG;  // lanes per speculative candidate: 8 candidates per worker warp (compile-time knob for A-B builds)
 constexpr int kSpecPubWords = 6;
 constexpr int kSpecInlineEpisodes = 8;  // steps of up to this many episodes need no copy at all: state in the launch parameters, results by zero-copy stores
 // per episode in host_out: u (2), x_pred (4 (N+1)), u_pred (2 N), winner cost | winner index | lap, rank | shrink

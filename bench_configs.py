@@ -160,6 +160,35 @@ def horizon_sweep(device=0):
             row["device_resident"]["placement"] = "trajectory in shared memory, gains in tensor memory"
         del g, g_obs, out
         torch.cuda.empty_cache()
+        if N > 25:
+            # ---- the same kernel on a 2^22-candidate batch.  A streaming launch ends with the 0.09 % of candidates that run all 150
+            # iterations -- 150 x N stages x 1.9 us of sequential work each (14 ms at N = 50) after the last fresh candidate was
+            # taken, i.e. a quarter of a 2^20-candidate launch at a few lanes per warp; four times the candidates quarter that share
+            # and show the rate the bulk of the launch runs at.  Both rows are reported.
+            BL = 1 << 22
+            dl = synth.flat_candidates(BL, N, seed=synth.SEED + N)
+            obs_l = _abi.obstacle_array(dl["obs"], dl["mode"])
+            gl = {k: torch.from_numpy(np.ascontiguousarray(dl[k])).to(dev) for k in ("x0", "x_term", "lamb_in")}
+            gl_obs = torch.from_numpy(obs_l.view(np.uint8).reshape(BL, -1).copy()).to(dev)
+            out_l = (torch.empty((BL, 2, N), dtype=torch.float64, device=dev), torch.empty((BL, 4, N + 1), dtype=torch.float64, device=dev),
+                     torch.empty(BL, dtype=torch.float64, device=dev), torch.empty(BL, dtype=torch.int32, device=dev))  # fmt: skip
+            best_l = None
+            for rep in range(2):
+                e.solve_batch_device(BL, gl["x0"].data_ptr(), gl["x_term"].data_ptr(), gl["lamb_in"].data_ptr(), gl_obs.data_ptr(), BL,
+                                     out_l[0].data_ptr(), out_l[1].data_ptr(), out_l[2].data_ptr(), out_l[3].data_ptr(), stream=stream.cuda_stream)
+                st = e.sync_stats(stream.cuda_stream)
+                if rep and (best_l is None or st["kernel_ms"] < best_l["kernel_ms"]):
+                    best_l = st
+            tfl = best_l["ilqr_iterations"] * flops_per_iteration(N) / (best_l["kernel_ms"] * 1e-3) / 1e12
+            gbl = best_l["ilqr_iterations"] * N * STREAM_DOUBLES_PER_STAGE * 8 / (best_l["kernel_ms"] * 1e-3) / 1e9
+            row["device_resident_large"] = {
+                "B": BL, "kernel_ms": best_l["kernel_ms"], "launches": best_l["launches"], "solves_per_s": BL / (best_l["kernel_ms"] * 1e-3),
+                "iters_per_solve": best_l["ilqr_iterations"] / BL, "algorithmic_tflops": tfl, "frac_of_fp64_peak": tfl / peak,
+                "scratch_traffic_gbs": gbl, "frac_of_hbm_peak": gbl / hbm_peak if hbm_peak else None,
+                "finite": bool(torch.isfinite(out_l[1]).all()),
+            }  # fmt: skip
+            del gl, gl_obs, out_l, dl, obs_l
+            torch.cuda.empty_cache()
         # ---- host-pointer call, 65536 candidates, pinned buffers (pageable memory would serialise and dominate the timing)
         Bh = 1 << 16
 

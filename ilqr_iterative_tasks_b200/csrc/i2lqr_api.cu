@@ -1227,6 +1227,13 @@ void spec_seed_patterns(const i2lqr_params& p, std::vector<unsigned long long>* 
   for (size_t i = 0; i < seen.size() && i < (size_t)kSpecHist; ++i) memcpy(&(*keys)[i], &seen[i], 8);
 }
 
+// The most episodes of this handle a step can have and still take the one-launch form (chain limit and table limit).
+int spec_episode_cap(const i2lqr_handle* h) {
+  const long long L = std::max(1, h->L), K = std::max(1, h->K);
+  const long long by_chains = spec_max_chains() / L, by_table = kSpecMaxEntries / ((long long)kOuter * K * kSpecMaxSet) / L;
+  return (int)std::max<long long>(1, std::min<long long>(h->E, std::min(by_chains, by_table)));
+}
+
 int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
   const int chains = n_episodes * h->L, S = kSpecMaxSet, K = h->K, N = h->kp.N;  // tables hold the largest set; a launch may use fewer
   const bool first = h->sp_hist_key.p == nullptr;
@@ -1250,7 +1257,7 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
     // the tail of a batched lap enters with a different episode count every lap, and growing the tables then means
     // cudaFree + cudaMalloc of ~70 MB in the middle of the lap (a device-wide synchronisation: measured as single steps of
     // up to 145 ms in a 4096-episode lap)
-    const int e_cap = std::max(1, std::min(h->E, spec_max_chains() / std::max(1, h->L)));
+    const int e_cap = spec_episode_cap(h);
     const int cmax = std::max(std::max(chains, h->sp_cmax), e_cap * h->L), E = std::max(std::max(n_episodes, h->sp_E), e_cap);
     const size_t entries = (size_t)kOuter * cmax * K * S;
     CU(h->sp_state.ensure(entries));
@@ -1280,7 +1287,7 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
 // function when it is first referenced) and its attributes -- done at set-up time, so that the first small step of a
 // batched lap does not pay for it in the middle of the lap (measured: one step of 7 ... 41 ms).
 int spec_prepare(i2lqr_handle* h, cudaStream_t st) {
-  const int e_cap = std::max(1, std::min(h->E, spec_max_chains() / std::max(1, h->L)));
+  const int e_cap = spec_episode_cap(h);
   if (!spec_eligible(h, e_cap)) return 0;
   if (spec_ensure(h, e_cap, st)) return 1;
   const void* kern = h->kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;

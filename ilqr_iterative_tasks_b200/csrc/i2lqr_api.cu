@@ -1283,6 +1283,14 @@ int spec_ensure(i2lqr_handle* h, int n_episodes, cudaStream_t st) {
   return 0;
 }
 
+// The one-launch step in its two worker shapes: kSpecWorkerGroup (4) lanes per speculative candidate, eight candidates per
+// worker warp -- or a whole warp per candidate, for steps whose table fits one wave of warps (one controller at the
+// reference's default K = 8, L = 2: 448 entries; rounds of a candidate that shares no warp are a third shorter).
+const void* spec_kernel(bool has_qr, int wg) {
+  if (wg == 32) return has_qr ? (const void*)spec_step_kernel<true, 32> : (const void*)spec_step_kernel<false, 32>;
+  return has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
+}
+
 // Everything the one-launch step needs the first time it runs -- its tables, the kernel's image (the runtime loads a
 // function when it is first referenced) and its attributes -- done at set-up time, so that the first small step of a
 // batched lap does not pay for it in the middle of the lap (measured: one step of 7 ... 41 ms).
@@ -1290,12 +1298,14 @@ int spec_prepare(i2lqr_handle* h, cudaStream_t st) {
   const int e_cap = spec_episode_cap(h);
   if (!spec_eligible(h, e_cap)) return 0;
   if (spec_ensure(h, e_cap, st)) return 1;
-  const void* kern = h->kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
   const size_t smem = spec_smem_bytes(h);
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
+  for (int wg : {kSpecWorkerGroup, 32}) {
+    const void* kern = spec_kernel(h->kp.has_qr, wg);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
+  }
   return 0;
 }
 
@@ -1369,15 +1379,28 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, cons
   }
   // (lanes per speculative candidate: 4 and 8 measured the same step latency at the config-2 shape, 16 / 32 are 10-18 % slower:
   // fewer candidates in flight, more entries the resolver finds not started)
-  const void* kern = kp.has_qr ? (const void*)spec_step_kernel<true> : (const void*)spec_step_kernel<false>;
-  const int per_warp = 32 / kSpecWorkerGroup;
   const size_t smem = spec_smem_bytes(h);
+  const long long chains = (long long)sc.n_episodes * h->L;
+  // worker shape: a warp per speculative candidate while ONE outer iteration's entries fit one wave of warps, else eight per warp
+  static const int force_wg = getenv("I2LQR_SPEC_WG") ? atoi(getenv("I2LQR_SPEC_WG")) : 0;  // A-B switch: 4 | 32
+  int wg = kSpecWorkerGroup;
+  {
+    const void* k32 = spec_kernel(kp.has_qr, 32);
+    CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(k32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm32 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, k32, kSolveThreads, smem));
+    const long long resident32 = (long long)per_sm32 * h->n_sms;
+    if (chains * std::max(1, a.k_eff - 1) * spec_set_size() <= resident32 - chains) wg = 32;
+  }
+  if (force_wg == 4 || force_wg == 32) wg = force_wg == 4 ? kSpecWorkerGroup : 32;
+  const void* kern = spec_kernel(kp.has_qr, wg);
+  const int per_warp = 32 / wg;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSolveThreads, smem));
   if (per_sm < 1) return fail("speculative step kernel does not fit on an SM");
-  const long long chains = (long long)sc.n_episodes * h->L;
   const long long resident = (long long)per_sm * h->n_sms;
   if (resident <= chains) return fail("internal: no room for worker warps");
   // speculation set size: all of it while one wave of worker groups covers the table, halved down to 4 when the chains are many
@@ -1390,7 +1413,7 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, cons
   const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * S + per_warp - 1) / per_warp);
   const long long grid = std::min<long long>(resident, chains + workers);
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;
-  if (debug) fprintf(stderr, "[i2lqr] spec step: chains %lld S %d grid %lld smem %zu per_sm %d epoch %u\n", chains, a.S, grid, smem, per_sm, a.epoch);
+  if (debug) fprintf(stderr, "[i2lqr] spec step: chains %lld S %d lanes per candidate %d grid %lld smem %zu per_sm %d epoch %u\n", chains, a.S, wg, grid, smem, per_sm, a.epoch);
   void* args[2] = {(void*)&kp, (void*)&a};
   CU(cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(kSolveThreads), args, smem, st));
   h->last_launches += 1;

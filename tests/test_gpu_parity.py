@@ -348,6 +348,8 @@ def test_controller_step_kernel_variants_agree():
     # the speculative one-launch form (spec_step.cuh) with speculation sets of 1 / 8 / 24 (default) / 32 lambda values:
     # hits, waits and misses fall differently in each, the results may not
     variants += [{"I2LQR_SPEC_S": "1"}, {"I2LQR_SPEC_S": "8"}, {"I2LQR_SPEC_S": "24"}, {"I2LQR_SPEC_S": "32"}]
+    # ... and with a whole warp per speculative candidate instead of four lanes (the shape small steps take by default)
+    variants += [{"I2LQR_SPEC_WG": "32"}, {"I2LQR_SPEC_WG": "32", "I2LQR_SPEC_S": "8"}]
     for env in variants:
         full = dict(os.environ)
         full.update(env)

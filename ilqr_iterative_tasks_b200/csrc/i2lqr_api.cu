@@ -1410,6 +1410,11 @@ int launch_spec_step(i2lqr_handle* h, const StepScope& sc, cudaStream_t st, cons
   static const int waves = getenv("I2LQR_SPEC_WAVES") ? std::max(1, atoi(getenv("I2LQR_SPEC_WAVES"))) : 8;  // tuning switch (2: 1.38 ms per step at 62 episodes, 8: 1.25)
   while (S > 4 && chains * std::max(1, a.k_eff - 1) * S > waves * group_slots) S /= 2;
   a.S = S;
+  // (two bands only when the table needs more than two waves of lane groups -- 60 ... 128 episodes of a batched lap's tail:
+  //  1.27 -> 1.18 ms per step at 62 episodes; at 1.4 waves, the K = 64, L = 8 controller, the plain rank-major order is
+  //  5 % faster, and within one wave the order does not matter)
+  static const int band_env = getenv("I2LQR_SPEC_BAND") ? atoi(getenv("I2LQR_SPEC_BAND")) : 8;  // tuning switch; 0 = one band
+  a.band = (band_env > 0 && chains * std::max(1, a.k_eff - 1) * S > 2 * group_slots) ? band_env : 0;
   const long long workers = std::max<long long>(1, (chains * std::max(1, a.k_eff - 1) * S + per_warp - 1) / per_warp);
   const long long grid = std::min<long long>(resident, chains + workers);
   static const bool debug = getenv("I2LQR_DEBUG") != nullptr;

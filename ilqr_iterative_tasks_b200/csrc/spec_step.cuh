@@ -52,6 +52,7 @@ struct SpecArgs {
   const DevObstacle* ep_obs_extra;  // (E, kMaxExtraObstacles) or null
   const int* ep_n_extra;       // (E)
   int S;                       // speculation set size in use, <= kSpecMaxSet
+  int band;                    // the workers start the `band` most frequent values of every (rank, chain) before the rest (0 / >= S: one band)
   int c_max;                   // chains the tables are laid out for (>= n_episodes * L)
   int e_stride;                // episodes the per-episode control words are laid out for (>= n_episodes)
   // ---- step workspace (the arrays the three-kernel form uses)
@@ -441,8 +442,8 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
   } else {
     // =============================================================== worker: speculative candidates, 8 per warp
     // Lane group g of all workers owns the table entries q = g, g + n_groups, g + 2 n_groups, ... of every outer
-    // iteration, in the j-major order q = ((j - 1) * n_chains + chain) * S + s, so that the candidates a resolver reaches
-    // first are started first.  The groups of a warp run their candidates in lock step, so whatever one group does
+    // iteration, in the j-major order q = ((j - 1) * n_chains + chain) * S + s (per band of lambda values, see below), so
+    // that the candidates a resolver reaches first are started first.  The groups of a warp run their candidates in lock step, so whatever one group does
     // between candidates is paid by all eight: picking the next entry is therefore fully pipelined.  While a candidate
     // runs, its group fetches the NEXT entry's published record in two asynchronous stages (stamped index word, then
     // terminal point / cost-to-go / resolver progress), each consumed a round after it was issued; when the candidate
@@ -459,6 +460,8 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
     const unsigned long long gid = (unsigned long long)(ticket - n_chains) * (32 / G) + (lane / G);
     const int k_eff = a.k_eff < K ? a.k_eff : K;
     const unsigned long long per_it = (unsigned long long)n_chains * (k_eff > 1 ? k_eff - 1 : 0) * S;
+    const int band = a.band > 0 && a.band < S ? a.band : S;
+    const unsigned long long band_entries = (unsigned long long)n_chains * (k_eff > 1 ? k_eff - 1 : 0) * band;
     int state = per_it == 0 ? W_DONE : W_NEED;
     // running candidate
     int it = 0, j = 0, chain = 0;
@@ -556,9 +559,20 @@ spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ Spec
           if (++pf_it == kOuter || pf_q >= per_it) list_done = true;
         }
         if (!list_done) {
-          pf_s = (int)(pf_q % S);
-          pf_chain = (int)((pf_q / S) % n_chains);
-          pf_j = 1 + (int)(pf_q / ((unsigned long long)S * n_chains));
+          // two bands: the `band` most frequent lambda values of every (rank, chain) first, the rest of the set after them --
+          // each band in the rank-major order above.  With more entries than lane groups (several waves) the likely hits of
+          // ALL ranks are then under way in the first wave instead of only the first ranks' full sets.
+          if (pf_q < band_entries) {
+            pf_s = (int)(pf_q % band);
+            pf_chain = (int)((pf_q / band) % n_chains);
+            pf_j = 1 + (int)(pf_q / ((unsigned long long)band * n_chains));
+          } else {
+            const unsigned long long q2 = pf_q - band_entries;
+            const int rest = S - band;
+            pf_s = band + (int)(q2 % rest);
+            pf_chain = (int)((q2 / rest) % n_chains);
+            pf_j = 1 + (int)(q2 / ((unsigned long long)rest * n_chains));
+          }
           pf_idx = (((size_t)pf_it * a.c_max + pf_chain) * K + pf_j) * S + pf_s;
           if (rung == 0) pf_word = ld_acquire_u64(a.pub + (((size_t)pf_it * a.c_max + pf_chain) * K + pf_j) * kSpecPubWords);
           pf_stage = 1;

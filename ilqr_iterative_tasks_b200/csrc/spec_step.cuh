@@ -156,8 +156,13 @@ __device__ __forceinline__ SpecLap spec_lap(const SpecArgs& a, int ep, int lrel)
   return l;
 }
 
+#ifdef I2LQR_SPEC_MAXREG  // compile-time knob for A-B builds: registers per thread (more resident warps, i.e. lane groups)
+#define I2_SPEC_BOUNDS __maxnreg__(I2LQR_SPEC_MAXREG)
+#else
+#define I2_SPEC_BOUNDS __launch_bounds__(kSolveThreads, 1)
+#endif
 template <bool kQR, int kWG = kSpecWorkerGroup>
-__global__ void __launch_bounds__(kSolveThreads, 1)
+__global__ void I2_SPEC_BOUNDS
 spec_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ SpecArgs a) {
   extern __shared__ double smem[];
   constexpr unsigned kFull = 0xffffffffu;
